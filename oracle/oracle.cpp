@@ -1,0 +1,512 @@
+// Oracle tier (b): multithreaded C++17 CPU restatement of the prover hot path.
+//
+// TEST INFRASTRUCTURE ONLY -- never linked into, loaded by or called from the product library.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
+//
+// PARITY UNPINNED: the algorithms live in crates absent from /root/reference
+//   halo2_proofs 0.2.0 @ a95945254dcc61acc1648c6039faeff85bc2440f (Cargo.lock:619-621)
+//   pasta_curves 0.4.1 (Cargo.lock:847-849)
+// and the reference's own tests pin no prover outputs (src/test_utils.rs:56-70: accept/reject only).
+// This file restates the published algorithms of those crates; it is cross-checked against the
+// independent Python big-int model (oracle/pasta_model.py) and frozen vectors in tests/golden/.
+//
+// Restated routines (reached from the reference at src/test_utils.rs:21-49):
+//   pasta_curves::fields::{Fp,Fq}            4 x u64 Montgomery, R = 2^256            -> struct Fe<M>
+//   pasta_curves::curves::{Ep,Eq}(+Affine)   y^2 = x^3 + 5, Jacobian, mixed add       -> struct Jac<M>
+//   halo2_proofs::arithmetic::best_multiexp  c = ceil(ln n), 256/c+1 unsigned windows,
+//                                            one full Pippenger per thread slice       -> orc_msm
+//   halo2_proofs::arithmetic::best_fft       bit-reverse + radix-2 DIT, twiddle table  -> orc_fft
+//   halo2_proofs::poly::EvaluationDomain     lagrange_to_coeff / coeff_to_extended /
+//                                            extended_to_coeff / divide_by_vanishing   -> orc_domain_*
+// All field elements cross the ABI as uint64_t[4] little-endian limbs in MONTGOMERY form.
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <thread>
+#include <algorithm>
+#include <functional>
+
+typedef unsigned __int128 u128;
+typedef uint64_t u64;
+
+struct ModP {
+  static constexpr u64 M[4] = {0x992d30ed00000001ULL, 0x224698fc094cf91bULL, 0, 0x4000000000000000ULL};
+  static constexpr u64 INV = 0x992d30ecffffffffULL;
+  static constexpr u64 R[4] = {0x34786d38fffffffdULL, 0x992c350be41914adULL, 0xffffffffffffffffULL, 0x3fffffffffffffffULL};
+  static constexpr u64 R2[4] = {0x8c78ecb30000000fULL, 0xd7d30dbd8b0de0e7ULL, 0x7797a99bc3c95d18ULL, 0x096d41af7b9cb714ULL};
+  // canonical (non-Montgomery) constants
+  static constexpr u64 ROOT[4] = {0xbdad6fabd87ea32fULL, 0xea322bf2b7bb7584ULL, 0x362120830561f81aULL, 0x2bce74deac30ebdaULL};
+  static constexpr u64 ZETA[4] = {0x1dad5ebdfdfe4ab9ULL, 0x1d1f8bd237ad3149ULL, 0x2caad5dc57aab1b0ULL, 0x12ccca834acdba71ULL};
+};
+struct ModQ {
+  static constexpr u64 M[4] = {0x8c46eb2100000001ULL, 0x224698fc0994a8ddULL, 0, 0x4000000000000000ULL};
+  static constexpr u64 INV = 0x8c46eb20ffffffffULL;
+  static constexpr u64 R[4] = {0x5b2b3e9cfffffffdULL, 0x992c350be3420567ULL, 0xffffffffffffffffULL, 0x3fffffffffffffffULL};
+  static constexpr u64 R2[4] = {0xfc9678ff0000000fULL, 0x67bb433d891a16e3ULL, 0x7fae231004ccf590ULL, 0x096d41af7ccfdaa9ULL};
+  static constexpr u64 ROOT[4] = {0xa70e2c1102b6d05fULL, 0x9bb97ea3c106f049ULL, 0x9e5c4dfd492ae26eULL, 0x2de6a9b8746d3f58ULL};
+  static constexpr u64 ZETA[4] = {0x2aa9d2e050aa0e4fULL, 0x0fed467d47c033afULL, 0x511db4d81cf70f5aULL, 0x06819a58283e528eULL};
+};
+
+template <class Mod>
+struct Fe {
+  u64 v[4];
+  static Fe zero() { Fe r; memset(r.v, 0, 32); return r; }
+  static Fe one() { Fe r; memcpy(r.v, Mod::R, 32); return r; }
+  static Fe load(const u64* p) { Fe r; memcpy(r.v, p, 32); return r; }
+  void store(u64* p) const { memcpy(p, v, 32); }
+  bool is_zero() const { return (v[0] | v[1] | v[2] | v[3]) == 0; }
+  bool operator==(const Fe& o) const { return v[0] == o.v[0] && v[1] == o.v[1] && v[2] == o.v[2] && v[3] == o.v[3]; }
+  bool operator!=(const Fe& o) const { return !(*this == o); }
+
+  static inline bool geq_mod(const u64* a) {
+    for (int i = 3; i >= 0; --i) {
+      if (a[i] > Mod::M[i]) return true;
+      if (a[i] < Mod::M[i]) return false;
+    }
+    return true;
+  }
+  static inline void sub_mod(u64* a) {
+    u64 borrow = 0;
+    for (int i = 0; i < 4; ++i) {
+      u128 d = (u128)a[i] - Mod::M[i] - borrow;
+      a[i] = (u64)d;
+      borrow = (u64)(d >> 64) & 1;
+    }
+  }
+  Fe operator+(const Fe& o) const {
+    Fe r; u64 c = 0;
+    for (int i = 0; i < 4; ++i) { u128 s = (u128)v[i] + o.v[i] + c; r.v[i] = (u64)s; c = (u64)(s >> 64); }
+    if (geq_mod(r.v)) sub_mod(r.v);     // both < 2^255 so no carry out of limb 3
+    return r;
+  }
+  Fe operator-(const Fe& o) const {
+    Fe r; u64 b = 0;
+    for (int i = 0; i < 4; ++i) { u128 d = (u128)v[i] - o.v[i] - b; r.v[i] = (u64)d; b = (u64)(d >> 64) & 1; }
+    if (b) { u64 c = 0; for (int i = 0; i < 4; ++i) { u128 s = (u128)r.v[i] + Mod::M[i] + c; r.v[i] = (u64)s; c = (u64)(s >> 64); } }
+    return r;
+  }
+  Fe neg() const { return zero() - *this; }
+  Fe dbl() const { return *this + *this; }
+  // schoolbook 4x4 + word-by-word Montgomery reduction (pasta_curves `montgomery_reduce`)
+  Fe operator*(const Fe& o) const {
+    u64 t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) {
+      u64 carry = 0;
+      for (int j = 0; j < 4; ++j) {
+        u128 x = (u128)v[i] * o.v[j] + t[i + j] + carry;
+        t[i + j] = (u64)x; carry = (u64)(x >> 64);
+      }
+      t[i + 4] = carry;
+    }
+    u64 carry2 = 0;
+    for (int i = 0; i < 4; ++i) {
+      u64 k = t[i] * Mod::INV;
+      u64 carry = 0;
+      for (int j = 0; j < 4; ++j) {
+        u128 x = (u128)k * Mod::M[j] + t[i + j] + carry;
+        t[i + j] = (u64)x; carry = (u64)(x >> 64);
+      }
+      u128 x = (u128)t[i + 4] + carry + carry2;
+      t[i + 4] = (u64)x; carry2 = (u64)(x >> 64);
+    }
+    Fe r; memcpy(r.v, t + 4, 32);
+    if (carry2 || geq_mod(r.v)) sub_mod(r.v);
+    return r;
+  }
+  Fe sqr() const { return (*this) * (*this); }
+  Fe pow(const u64* e, int limbs) const {
+    Fe acc = one();
+    for (int i = limbs - 1; i >= 0; --i)
+      for (int b = 63; b >= 0; --b) {
+        acc = acc.sqr();
+        if ((e[i] >> b) & 1) acc = acc * (*this);
+      }
+    return acc;
+  }
+  Fe inv() const {   // a^(p-2); 0 -> 0
+    u64 e[4]; memcpy(e, Mod::M, 32); e[0] -= 2;
+    return pow(e, 4);
+  }
+  static Fe from_canonical(const u64* c) { Fe a = load(c); return a * load(Mod::R2); }
+  void to_canonical(u64* out) const { Fe o; memset(o.v, 0, 32); o.v[0] = 1; Fe r = (*this) * o; r.store(out); }
+  static Fe from_u64(u64 x) { u64 c[4] = {x, 0, 0, 0}; return from_canonical(c); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// curve: y^2 = x^3 + 5, Jacobian coordinates, identity <=> z == 0
+// ---------------------------------------------------------------------------------------------
+template <class Mod>
+struct Aff { Fe<Mod> x, y; bool inf; };
+
+template <class Mod>
+struct Jac {
+  typedef Fe<Mod> F;
+  F x, y, z;
+  static Jac identity() { Jac r; r.x = F::zero(); r.y = F::zero(); r.z = F::zero(); return r; }
+  bool is_identity() const { return z.is_zero(); }
+  static Jac from_affine(const Aff<Mod>& a) {
+    if (a.inf) return identity();
+    Jac r; r.x = a.x; r.y = a.y; r.z = F::one(); return r;
+  }
+  Jac dbl() const {   // dbl-2009-l (a = 0)
+    if (is_identity()) return *this;
+    F a = x.sqr(), b = y.sqr(), c = b.sqr();
+    F d = ((x + b).sqr() - a - c).dbl();
+    F e = a.dbl() + a, f = e.sqr();
+    Jac r;
+    r.z = (z * y).dbl();
+    r.x = f - d.dbl();
+    r.y = e * (d - r.x) - c.dbl().dbl().dbl();
+    return r;
+  }
+  Jac add(const Jac& o) const {   // add-2007-bl with explicit special cases
+    if (is_identity()) return o;
+    if (o.is_identity()) return *this;
+    F z1z1 = z.sqr(), z2z2 = o.z.sqr();
+    F u1 = x * z2z2, u2 = o.x * z1z1;
+    F s1 = y * z2z2 * o.z, s2 = o.y * z1z1 * z;
+    if (u1 == u2) { if (s1 == s2) return dbl(); return identity(); }
+    F h = u2 - u1, i = h.dbl().sqr(), j = h * i, r = (s2 - s1).dbl(), v = u1 * i;
+    Jac out;
+    out.x = r.sqr() - j - v.dbl();
+    out.y = r * (v - out.x) - (s1 * j).dbl();
+    out.z = ((z + o.z).sqr() - z1z1 - z2z2) * h;
+    return out;
+  }
+  Jac add_affine(const Aff<Mod>& o) const {   // madd-2007-bl
+    if (o.inf) return *this;
+    if (is_identity()) return from_affine(o);
+    F z1z1 = z.sqr();
+    F u2 = o.x * z1z1, s2 = o.y * z1z1 * z;
+    if (x == u2) { if (y == s2) return dbl(); return identity(); }
+    F h = u2 - x, hh = h.sqr(), i = hh.dbl().dbl(), j = h * i, r = (s2 - y).dbl(), v = x * i;
+    Jac out;
+    out.x = r.sqr() - j - v.dbl();
+    out.y = r * (v - out.x) - (y * j).dbl();
+    out.z = (z + h).sqr() - z1z1 - hh;
+    return out;
+  }
+  Aff<Mod> to_affine() const {
+    Aff<Mod> a;
+    if (is_identity()) { a.x = F::zero(); a.y = F::zero(); a.inf = true; return a; }
+    F zi = z.inv(), zi2 = zi.sqr();
+    a.x = x * zi2; a.y = y * zi2 * zi; a.inf = false;
+    return a;
+  }
+};
+
+// C-ABI affine layout: x[4], y[4] Montgomery; identity encoded as x = y = 0.
+template <class Mod>
+static Aff<Mod> load_affine(const u64* p) {
+  Aff<Mod> a; a.x = Fe<Mod>::load(p); a.y = Fe<Mod>::load(p + 4);
+  a.inf = a.x.is_zero() && a.y.is_zero();
+  return a;
+}
+template <class Mod>
+static void store_affine(u64* p, const Aff<Mod>& a) {
+  if (a.inf) { memset(p, 0, 64); return; }
+  a.x.store(p); a.y.store(p + 4);
+}
+
+static void parallel_for(size_t n, int threads, const std::function<void(size_t, size_t, int)>& fn) {
+  if (threads <= 1 || n < (size_t)threads) { fn(0, n, 0); return; }
+  std::vector<std::thread> th;
+  size_t chunk = (n + threads - 1) / threads;
+  for (int t = 0; t < threads; ++t) {
+    size_t lo = std::min(n, (size_t)t * chunk), hi = std::min(n, lo + chunk);
+    if (lo >= hi) break;
+    th.emplace_back(fn, lo, hi, t);
+  }
+  for (auto& x : th) x.join();
+}
+
+// ---------------------------------------------------------------------------------------------
+// best_multiexp
+// ---------------------------------------------------------------------------------------------
+template <class SMod>
+static inline size_t get_at(size_t segment, size_t c, const u64* repr /*canonical 4xu64*/) {
+  size_t skip_bits = segment * c, skip_bytes = skip_bits / 8;
+  if (skip_bytes >= 32) return 0;
+  uint8_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const uint8_t* bytes = (const uint8_t*)repr;
+  for (size_t i = 0; i < 8 && skip_bytes + i < 32; ++i) v[i] = bytes[skip_bytes + i];
+  u64 tmp; memcpy(&tmp, v, 8);
+  tmp >>= skip_bits - skip_bytes * 8;
+  tmp %= (1ULL << c);
+  return (size_t)tmp;
+}
+
+template <class BMod, class SMod>
+static void multiexp_serial(const u64* coeffs_mont, const u64* bases, size_t n, Jac<BMod>& acc) {
+  std::vector<u64> repr(n * 4);
+  for (size_t i = 0; i < n; ++i) Fe<SMod>::load(coeffs_mont + 4 * i).to_canonical(&repr[4 * i]);
+  size_t c = n < 4 ? 1 : n < 32 ? 3 : (size_t)std::ceil(std::log((double)n));
+  size_t segments = 256 / c + 1;
+  enum Kind : uint8_t { NONE, AFFINE, PROJ };
+  std::vector<Kind> kind((1u << c) - 1);
+  std::vector<Aff<BMod>> baff((1u << c) - 1);
+  std::vector<Jac<BMod>> bproj((1u << c) - 1);
+  for (size_t seg = segments; seg-- > 0;) {
+    for (size_t i = 0; i < c; ++i) acc = acc.dbl();
+    std::fill(kind.begin(), kind.end(), NONE);
+    for (size_t i = 0; i < n; ++i) {
+      size_t d = get_at<SMod>(seg, c, &repr[4 * i]);
+      if (!d) continue;
+      Aff<BMod> b = load_affine<BMod>(bases + 8 * i);
+      size_t k = d - 1;
+      if (kind[k] == NONE) { baff[k] = b; kind[k] = AFFINE; }
+      else if (kind[k] == AFFINE) { bproj[k] = Jac<BMod>::from_affine(baff[k]).add_affine(b); kind[k] = PROJ; }
+      else bproj[k] = bproj[k].add_affine(b);
+    }
+    Jac<BMod> running = Jac<BMod>::identity();
+    for (size_t k = kind.size(); k-- > 0;) {
+      if (kind[k] == AFFINE) running = running.add_affine(baff[k]);
+      else if (kind[k] == PROJ) running = running.add(bproj[k]);
+      acc = acc.add(running);
+    }
+  }
+}
+
+template <class BMod, class SMod>
+static void best_multiexp(const u64* coeffs, const u64* bases, size_t n, int threads, u64* out_affine) {
+  Jac<BMod> total = Jac<BMod>::identity();
+  if (threads < 1) threads = 1;
+  if (n > (size_t)threads) {
+    size_t chunk = n / threads;
+    size_t num_chunks = (n + chunk - 1) / chunk;
+    std::vector<Jac<BMod>> results(num_chunks, Jac<BMod>::identity());
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < num_chunks; ++t) {
+      size_t lo = t * chunk, hi = std::min(n, lo + chunk);
+      th.emplace_back([=, &results]() { multiexp_serial<BMod, SMod>(coeffs + 4 * lo, bases + 8 * lo, hi - lo, results[t]); });
+    }
+    for (auto& x : th) x.join();
+    for (auto& r : results) total = total.add(r);
+  } else {
+    multiexp_serial<BMod, SMod>(coeffs, bases, n, total);
+  }
+  store_affine<BMod>(out_affine, total.to_affine());
+}
+
+// ---------------------------------------------------------------------------------------------
+// best_fft
+// ---------------------------------------------------------------------------------------------
+static inline size_t bitrev(size_t n, unsigned l) {
+  size_t r = 0;
+  for (unsigned i = 0; i < l; ++i) { r = (r << 1) | (n & 1); n >>= 1; }
+  return r;
+}
+
+template <class Mod>
+static void fft_inplace(Fe<Mod>* a, Fe<Mod> omega, unsigned log_n, int threads) {
+  typedef Fe<Mod> F;
+  size_t n = (size_t)1 << log_n;
+  for (size_t k = 0; k < n; ++k) { size_t rk = bitrev(k, log_n); if (k < rk) std::swap(a[k], a[rk]); }
+  std::vector<F> tw(std::max<size_t>(n / 2, 1));
+  tw[0] = F::one();
+  for (size_t i = 1; i < n / 2; ++i) tw[i] = tw[i - 1] * omega;
+  size_t chunk = 2, tchunk = n / 2;
+  for (unsigned s = 0; s < log_n; ++s) {
+    size_t half = chunk / 2;
+    // butterflies of one stage are independent: split the n/2 butterflies over threads
+    parallel_for(n / 2, threads, [&](size_t lo, size_t hi, int) {
+      for (size_t b = lo; b < hi; ++b) {
+        size_t blk = b / half, i = b % half;
+        F* x = a + blk * chunk + i;
+        F* y = x + half;
+        F t = i == 0 ? *y : (*y) * tw[i * tchunk];
+        F u = *x;
+        *x = u + t; *y = u - t;
+      }
+    });
+    chunk *= 2; tchunk /= 2;
+  }
+}
+
+template <class Mod>
+struct Domain {
+  typedef Fe<Mod> F;
+  unsigned k, ext_k, qdeg;
+  F omega, omega_inv, ext_omega, ext_omega_inv, g_coset, g_coset_inv, ifft_div, ext_ifft_div;
+  std::vector<F> t_eval;   // inverted
+  Domain(unsigned j, unsigned k_) {
+    k = k_; qdeg = j - 1;
+    u64 n = 1ULL << k;
+    ext_k = k;
+    while ((1ULL << ext_k) < n * qdeg) ++ext_k;
+    ext_omega = F::from_canonical(Mod::ROOT);
+    for (unsigned i = ext_k; i < 32; ++i) ext_omega = ext_omega.sqr();
+    omega = ext_omega;
+    for (unsigned i = k; i < ext_k; ++i) omega = omega.sqr();
+    omega_inv = omega.inv(); ext_omega_inv = ext_omega.inv();
+    g_coset = F::from_canonical(Mod::ZETA); g_coset_inv = g_coset.sqr();
+    u64 e[1] = {n};
+    F orig = g_coset.pow(e, 1), step = ext_omega.pow(e, 1), cur = orig;
+    do { t_eval.push_back(cur); cur = cur * step; } while (cur != orig);
+    for (auto& t : t_eval) t = (t - F::one()).inv();
+    ifft_div = F::from_u64(n).inv();
+    ext_ifft_div = F::from_u64(1ULL << ext_k).inv();
+  }
+  void zeta_powers(F* a, size_t len, bool into, int threads) const {
+    F cp[2] = {into ? g_coset : g_coset_inv, into ? g_coset_inv : g_coset};
+    parallel_for(len, threads, [&](size_t lo, size_t hi, int) {
+      for (size_t i = lo; i < hi; ++i) { size_t r = i % 3; if (r) a[i] = a[i] * cp[r - 1]; }
+    });
+  }
+  void scale(F* a, size_t len, F s, int threads) const {
+    parallel_for(len, threads, [&](size_t lo, size_t hi, int) { for (size_t i = lo; i < hi; ++i) a[i] = a[i] * s; });
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// exported C entry points; field: 0 = Fp, 1 = Fq; curve: 0 = pallas (coords Fp, scalars Fq), 1 = vesta
+// ---------------------------------------------------------------------------------------------
+#define DISPATCH_FIELD(field, ...) do { if ((field) == 0) { typedef ModP Mod; __VA_ARGS__; } else { typedef ModQ Mod; __VA_ARGS__; } } while (0)
+
+extern "C" {
+
+int orc_hw_threads() { int t = (int)std::thread::hardware_concurrency(); return t > 0 ? t : 1; }
+
+void orc_to_mont(int field, const u64* canon, u64* mont, size_t n) {
+  DISPATCH_FIELD(field, for (size_t i = 0; i < n; ++i) Fe<Mod>::from_canonical(canon + 4 * i).store(mont + 4 * i));
+}
+void orc_from_mont(int field, const u64* mont, u64* canon, size_t n) {
+  DISPATCH_FIELD(field, for (size_t i = 0; i < n; ++i) Fe<Mod>::load(mont + 4 * i).to_canonical(canon + 4 * i));
+}
+// elementwise op on Montgomery vectors: 0 add, 1 sub, 2 mul, 3 inv(a), 4 sqr(a)
+void orc_field_op(int field, int op, const u64* a, const u64* b, u64* out, size_t n) {
+  DISPATCH_FIELD(field, for (size_t i = 0; i < n; ++i) {
+    typedef Fe<Mod> F;
+    F x = F::load(a + 4 * i), y = b ? F::load(b + 4 * i) : F::zero(), r;
+    switch (op) { case 0: r = x + y; break; case 1: r = x - y; break; case 2: r = x * y; break; case 3: r = x.inv(); break; default: r = x.sqr(); }
+    r.store(out + 4 * i);
+  });
+}
+
+void orc_fft(int field, u64* a, unsigned log_n, const u64* omega_mont, int threads) {
+  DISPATCH_FIELD(field, fft_inplace<Mod>((Fe<Mod>*)a, Fe<Mod>::load(omega_mont), log_n, threads));
+}
+
+void orc_msm(int curve, const u64* scalars, const u64* bases, size_t n, int threads, u64* out_affine) {
+  if (curve == 0) best_multiexp<ModP, ModQ>(scalars, bases, n, threads, out_affine);
+  else best_multiexp<ModQ, ModP>(scalars, bases, n, threads, out_affine);
+}
+
+// points: out[i] = P0 + i*D (affine, C-ABI layout), i < n  -- test-input generator
+void orc_points_progression(int curve, const u64* p0, const u64* d, size_t n, int threads, u64* out) {
+  auto run = [&](auto tag) {
+    typedef decltype(tag) Mod;
+    Aff<Mod> P0 = load_affine<Mod>(p0), D = load_affine<Mod>(d);
+    parallel_for(n, threads, [&](size_t lo, size_t hi, int) {
+      if (lo >= hi) return;
+      // start = P0 + lo*D by double-and-add, then step; normalise in blocks with batch inversion
+      Jac<Mod> step = Jac<Mod>::identity(), base = Jac<Mod>::from_affine(D);
+      for (size_t e = lo; e; e >>= 1) { if (e & 1) step = step.add(base); base = base.dbl(); }
+      Jac<Mod> cur = Jac<Mod>::from_affine(P0).add(step);
+      const size_t B = 1024;
+      std::vector<Jac<Mod>> blk(B);
+      std::vector<Fe<Mod>> pre(B);
+      for (size_t s = lo; s < hi; s += B) {
+        size_t m = std::min(B, hi - s);
+        for (size_t i = 0; i < m; ++i) { blk[i] = cur; cur = cur.add_affine(D); }
+        Fe<Mod> acc = Fe<Mod>::one();
+        for (size_t i = 0; i < m; ++i) { pre[i] = acc; if (!blk[i].is_identity()) acc = acc * blk[i].z; }
+        Fe<Mod> inv = acc.inv();
+        for (size_t i = m; i-- > 0;) {
+          Aff<Mod> a;
+          if (blk[i].is_identity()) { a.inf = true; a.x = a.y = Fe<Mod>::zero(); }
+          else {
+            Fe<Mod> zi = inv * pre[i]; inv = inv * blk[i].z;
+            Fe<Mod> zi2 = zi.sqr();
+            a.x = blk[i].x * zi2; a.y = blk[i].y * zi2 * zi; a.inf = false;
+          }
+          store_affine<Mod>(out + 8 * (s + i), a);
+        }
+      }
+    });
+  };
+  if (curve == 0) run(ModP()); else run(ModQ());
+}
+
+// scalar multiplication k*P (k canonical 4xu64), affine in/out
+void orc_point_mul(int curve, const u64* k_canon, const u64* p, u64* out) {
+  auto run = [&](auto tag) {
+    typedef decltype(tag) Mod;
+    Aff<Mod> P = load_affine<Mod>(p);
+    Jac<Mod> acc = Jac<Mod>::identity();
+    for (int i = 3; i >= 0; --i) for (int b = 63; b >= 0; --b) { acc = acc.dbl(); if ((k_canon[i] >> b) & 1) acc = acc.add_affine(P); }
+    store_affine<Mod>(out, acc.to_affine());
+  };
+  if (curve == 0) run(ModP()); else run(ModQ());
+}
+
+// sum of two affine points (C-ABI layout)
+void orc_point_add(int curve, const u64* a, const u64* b, u64* out) {
+  auto run = [&](auto tag) {
+    typedef decltype(tag) Mod;
+    store_affine<Mod>(out, Jac<Mod>::from_affine(load_affine<Mod>(a)).add_affine(load_affine<Mod>(b)).to_affine());
+  };
+  if (curve == 0) run(ModP()); else run(ModQ());
+}
+
+// 32-byte compressed encoding (pasta GroupEncoding): x LE canonical, bit 255 = y & 1; identity = zeros
+void orc_point_compress(int curve, const u64* pts, size_t n, uint8_t* out) {
+  auto run = [&](auto tag) {
+    typedef decltype(tag) Mod;
+    for (size_t i = 0; i < n; ++i) {
+      Aff<Mod> a = load_affine<Mod>(pts + 8 * i);
+      if (a.inf) { memset(out + 32 * i, 0, 32); continue; }
+      u64 x[4], y[4]; a.x.to_canonical(x); a.y.to_canonical(y);
+      memcpy(out + 32 * i, x, 32);
+      out[32 * i + 31] |= (uint8_t)((y[0] & 1) << 7);
+    }
+  };
+  if (curve == 0) run(ModP()); else run(ModQ());
+}
+
+// EvaluationDomain transforms. cols are batch contiguous vectors.
+void orc_lagrange_to_coeff(int field, unsigned j, unsigned k, u64* cols, size_t batch, int threads) {
+  DISPATCH_FIELD(field, {
+    Domain<Mod> d(j, k); size_t n = (size_t)1 << k;
+    for (size_t b = 0; b < batch; ++b) {
+      Fe<Mod>* a = (Fe<Mod>*)cols + b * n;
+      fft_inplace<Mod>(a, d.omega_inv, k, threads);
+      d.scale(a, n, d.ifft_div, threads);
+    }
+  });
+}
+void orc_coeff_to_extended(int field, unsigned j, unsigned k, const u64* coeff, u64* ext, size_t batch, int threads) {
+  DISPATCH_FIELD(field, {
+    Domain<Mod> d(j, k); size_t n = (size_t)1 << k, en = (size_t)1 << d.ext_k;
+    for (size_t b = 0; b < batch; ++b) {
+      Fe<Mod>* e = (Fe<Mod>*)ext + b * en;
+      memcpy((void*)e, coeff + 4 * b * n, 32 * n);
+      memset((void*)(e + n), 0, 32 * (en - n));
+      d.zeta_powers(e, n, true, threads);
+      fft_inplace<Mod>(e, d.ext_omega, d.ext_k, threads);
+    }
+  });
+}
+// ext (2^ext_k, modified in place) -> out (n*(j-1)); if divide != 0 first multiplies by 1/(X^n - 1) on the coset
+void orc_extended_to_coeff(int field, unsigned j, unsigned k, u64* ext, u64* out, int divide, int threads) {
+  DISPATCH_FIELD(field, {
+    Domain<Mod> d(j, k); size_t n = (size_t)1 << k, en = (size_t)1 << d.ext_k;
+    Fe<Mod>* e = (Fe<Mod>*)ext;
+    if (divide) {
+      size_t m = d.t_eval.size();
+      parallel_for(en, threads, [&](size_t lo, size_t hi, int) { for (size_t i = lo; i < hi; ++i) e[i] = e[i] * d.t_eval[i % m]; });
+    }
+    fft_inplace<Mod>(e, d.ext_omega_inv, d.ext_k, threads);
+    d.scale(e, en, d.ext_ifft_div, threads);
+    d.zeta_powers(e, en, false, threads);
+    memcpy(out, ext, 32 * n * d.qdeg);
+  });
+}
+unsigned orc_domain_info(int field, unsigned j, unsigned k, u64* omega, u64* ext_omega) {
+  unsigned ek = 0;
+  DISPATCH_FIELD(field, { Domain<Mod> d(j, k); d.omega.store(omega); d.ext_omega.store(ext_omega); ek = d.ext_k; });
+  return ek;
+}
+
+}  // extern "C"
