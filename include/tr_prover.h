@@ -1,0 +1,120 @@
+/* tr_prover.h -- C ABI of the B200 (sm_100a) backend for the data-parallel core of the halo2/IPA prover
+ * that proves the TinyRAM circuit of Orbis-Tertius/tiny-ram-halo2.
+ *
+ * The reference crate has no FFI of its own: it reaches the prover through halo2_proofs' free functions and
+ * EvaluationDomain methods (un-vendored dependency halo2_proofs 0.2.0 @ a95945254dcc, /root/reference/Cargo.lock:619-621),
+ * called from /root/reference/src/test_utils.rs:21-49 (Params::new, keygen_vk/pk, create_proof).  Each entry point
+ * below names the halo2_proofs routine it stands in for; INTEGRATION.md shows the Rust-side binding.
+ *
+ * Conventions
+ *   status      0 = ok, < 0 = error (TRP_E_*); message via trp_last_error(ctx).  Never aborts, never throws.
+ *   field elem  uint64_t[4], little-endian limbs, MONTGOMERY form (exactly what pasta_curves' Fp/Fq hold in
+ *               memory), value < modulus.
+ *   affine pt   { uint64_t x[4]; uint64_t y[4]; } Montgomery; the identity is encoded as x = y = 0.
+ *   jacobian pt { x[4], y[4], z[4] } Montgomery; identity <=> z = 0.  Results are returned NORMALISED
+ *               (z = 1 in Montgomery form, or x = y = z = 0): a valid Jacobian representative whose affine
+ *               form / 32-byte encoding is the unique group element the CPU prover computes.
+ *   curve       0 = Pallas (coordinates Fp, scalars Fq), 1 = Vesta (coordinates Fq, scalars Fp).  The
+ *               reference proves over Fp and commits on Vesta (src/test_utils.rs:2,12,21,40) => curve = 1.
+ *               NTT / domain entry points work over the curve's SCALAR field.
+ *   ownership   caller owns all host buffers; the library owns device memory behind handles.
+ *   threading   a ctx is bound to one device and one stream; calls on one ctx are serialised internally;
+ *               distinct ctxs are independent.
+ *   host/dev    trp_*      take HOST pointers (copies inside the call, synchronous);
+ *               trp_dev_*  take DEVICE pointers, enqueue on the ctx stream and return without synchronising
+ *               (results are valid after trp_ctx_sync or stream synchronisation).
+ */
+#ifndef TR_PROVER_H
+#define TR_PROVER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRP_OK 0
+#define TRP_E_INVALID (-1)   /* bad argument / size mismatch (halo2 would panic on assert_eq!) */
+#define TRP_E_CUDA (-2)      /* CUDA runtime error */
+#define TRP_E_OOM (-3)       /* device allocation failed */
+#define TRP_E_NODEVICE (-4)  /* no usable CUDA device: there is no CPU fallback */
+
+#define TRP_CURVE_PALLAS 0
+#define TRP_CURVE_VESTA 1
+
+typedef struct trp_ctx trp_ctx;
+typedef struct trp_bases trp_bases;
+typedef struct trp_domain trp_domain;
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+int trp_ctx_create(trp_ctx** out, int device, int curve);
+void trp_ctx_destroy(trp_ctx* ctx);
+const char* trp_last_error(const trp_ctx* ctx);
+/* Use an externally owned CUDA stream (cudaStream_t passed as void*); NULL restores the ctx's own stream. */
+int trp_ctx_set_stream(trp_ctx* ctx, void* cuda_stream);
+int trp_ctx_sync(trp_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+uint64_t trp_ctx_launch_count(const trp_ctx* ctx);
+const char* trp_version(void);
+
+/* ---- MSM: halo2_proofs::arithmetic::best_multiexp(coeffs, bases) -> C::Curve ---------------------------
+ * and poly::commitment::Params::{commit, commit_lagrange} which append blind * w and call it.
+ * Bases (Params.g / Params.g_lagrange ++ [w]) are uploaded once and reused by hundreds of MSMs.            */
+int trp_bases_load(trp_ctx* ctx, const uint64_t* affine_xy /* n x 8 */, size_t n, trp_bases** out);
+int trp_dev_bases_load(trp_ctx* ctx, const uint64_t* d_affine_xy, size_t n, trp_bases** out);
+/* flags: bit 0 = keep one bucket set per window (no precomputed table), bit 1 = force the precomputed
+ * table of 2^(c*w) * P_i multiples (default: precompute when the table fits the memory budget). */
+int trp_bases_load_ex(trp_ctx* ctx, const uint64_t* affine_xy, size_t n, int flags, trp_bases** out);
+size_t trp_bases_len(const trp_bases* b);
+/* out = { window bits c, number of windows, 1 if the multiples were precomputed } */
+int trp_bases_describe(const trp_bases* b, unsigned out[3]);
+void trp_bases_free(trp_bases* b);
+/* sum_i scalars[i] * bases[i], i < n <= len(bases) (a prefix of the loaded bases).  n = 0 gives the identity. */
+int trp_msm(trp_ctx* ctx, const trp_bases* bases, const uint64_t* scalars /* n x 4 */, size_t n,
+            uint64_t out_jacobian[12]);
+/* m independent MSMs over the same bases; scalars is m contiguous columns of n. */
+int trp_msm_batch(trp_ctx* ctx, const trp_bases* bases, const uint64_t* scalars /* m x n x 4 */, size_t n,
+                  size_t m, uint64_t* out_jacobian /* m x 12 */);
+int trp_dev_msm_batch(trp_ctx* ctx, const trp_bases* bases, const uint64_t* d_scalars, size_t n, size_t m,
+                      uint64_t* d_out_jacobian /* m x 12, device */);
+
+/* ---- NTT: halo2_proofs::arithmetic::best_fft(a, omega, log_n) (field instance) -------------------------
+ * In place, natural order in and out: a[k] <- sum_j a[j] * omega^(j k); batch contiguous vectors of 2^log_n. */
+int trp_ntt(trp_ctx* ctx, uint64_t* a, size_t batch, unsigned log_n, const uint64_t omega[4]);
+int trp_dev_ntt(trp_ctx* ctx, uint64_t* d_a, size_t batch, unsigned log_n, const uint64_t omega[4]);
+
+/* ---- EvaluationDomain: halo2_proofs::poly::EvaluationDomain::new(j, k) and its transforms ---------------- */
+int trp_domain_create(trp_ctx* ctx, unsigned k, unsigned j, trp_domain** out);
+void trp_domain_free(trp_domain* d);
+unsigned trp_domain_extended_k(const trp_domain* d);
+/* omega, extended_omega, g_coset (zeta), g_coset_inv as Montgomery limbs: out[4][4] */
+int trp_domain_constants(const trp_domain* d, uint64_t out[16]);
+/* lagrange_to_coeff: iNTT with omega^-1 then * 2^-k; batch columns of n = 2^k, in place */
+int trp_lagrange_to_coeff(trp_domain* d, uint64_t* cols, size_t batch);
+int trp_dev_lagrange_to_coeff(trp_domain* d, uint64_t* d_cols, size_t batch);
+/* coeff_to_lagrange: plain NTT with omega (EvaluationDomain::coeff_to_lagrange is not in 0.2.0; used by tests) */
+int trp_coeff_to_lagrange(trp_domain* d, uint64_t* cols, size_t batch);
+/* coeff_to_extended: a[i] *= zeta^(i mod 3), zero-pad to 2^extended_k, NTT with extended_omega */
+int trp_coeff_to_extended(trp_domain* d, const uint64_t* coeff /* batch x n */, uint64_t* ext /* batch x 2^ext_k */,
+                          size_t batch);
+int trp_dev_coeff_to_extended(trp_domain* d, const uint64_t* d_coeff, uint64_t* d_ext, size_t batch);
+/* extended_to_coeff (optionally preceded by divide_by_vanishing_poly): ext is consumed (overwritten);
+ * out_coeff receives n * (j - 1) coefficients. */
+int trp_extended_to_coeff(trp_domain* d, uint64_t* ext /* 2^ext_k */, uint64_t* out_coeff /* n*(j-1) */,
+                          int divide_by_vanishing);
+int trp_dev_extended_to_coeff(trp_domain* d, uint64_t* d_ext, uint64_t* d_out_coeff, int divide_by_vanishing);
+
+/* ---- glue / debug: elementwise field kernels over the ctx's scalar (field=0) or base (field=1) field ----
+ * op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 sqr(a).  Host pointers.  Used by parity tests of K1 and by K7 callers. */
+int trp_field_op(trp_ctx* ctx, int which_field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+
+/* ---- microbenchmarks used by bench.py to measure the integer-pipe roofline denominator -------------------
+ * kind 0: independent IMAD.WIDE chains, 1: IMAD (32-bit), 2: IADD3, 3: mixed IMAD.WIDE + IADD3, 4: field mul.
+ * Returns achieved G-ops/s in *out_gops (ops = thread-level instructions, or field muls for kind 4). */
+int trp_microbench(trp_ctx* ctx, int kind, int iters, double* out_gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TR_PROVER_H */

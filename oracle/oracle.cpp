@@ -450,6 +450,18 @@ void orc_point_add(int curve, const u64* a, const u64* b, u64* out) {
   if (curve == 0) run(ModP()); else run(ModQ());
 }
 
+// Jacobian (x, y, z) -> affine, n points
+void orc_jacobian_to_affine(int curve, const u64* jac, size_t n, u64* out) {
+  auto run = [&](auto tag) {
+    typedef decltype(tag) Mod;
+    for (size_t i = 0; i < n; ++i) {
+      Jac<Mod> p; p.x = Fe<Mod>::load(jac + 12 * i); p.y = Fe<Mod>::load(jac + 12 * i + 4); p.z = Fe<Mod>::load(jac + 12 * i + 8);
+      store_affine<Mod>(out + 8 * i, p.to_affine());
+    }
+  };
+  if (curve == 0) run(ModP()); else run(ModQ());
+}
+
 // 32-byte compressed encoding (pasta GroupEncoding): x LE canonical, bit 255 = y & 1; identity = zeros
 void orc_point_compress(int curve, const u64* pts, size_t n, uint8_t* out) {
   auto run = [&](auto tag) {

@@ -115,6 +115,14 @@ def point_add(curve, a, b):
     return out
 
 
+def jacobian_to_affine(curve, jac):
+    """(..., 3, 4) Jacobian Montgomery limbs -> (..., 8) affine; identity -> zeros."""
+    jac = _u64(jac); n = jac.size // 12
+    out = np.zeros((n, 8), dtype=np.uint64)
+    lib().orc_jacobian_to_affine(curve, _p(jac), ctypes.c_size_t(n), _p(out))
+    return out[0] if jac.ndim == 2 else out.reshape(jac.shape[:-2] + (8,))
+
+
 def point_compress(curve, pts):
     pts = _u64(pts); n = pts.size // 8
     out = np.zeros((n, 32), dtype=np.uint8)

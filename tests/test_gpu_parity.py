@@ -1,0 +1,186 @@
+"""GPU parity tests: every hot-path entry point of the C ABI against the CPU oracle, bit-exact.
+
+All calls go through libtrp.so's extern "C" surface (via the ctypes mirror package).  Results are compared as
+canonical objects: field vectors limb-for-limb, group elements after normalisation to affine (the Jacobian
+representative best_multiexp returns is not unique on the CPU either)."""
+import numpy as np
+import pytest
+
+from util import O, pm, make_points, scalars_uniform, scalars_tinyram, affine_of, generator
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as ge
+    return ge.load_package()
+
+
+@pytest.fixture(scope="module")
+def ctxs(pkg):
+    return {O.VESTA: pkg.Context(0, pkg.VESTA), O.PALLAS: pkg.Context(0, pkg.PALLAS)}
+
+
+# ---- K1 field arithmetic --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("curve", [O.VESTA, O.PALLAS])
+@pytest.mark.parametrize("which", [0, 1])
+def test_field_ops(ctxs, curve, which):
+    ctx = ctxs[curve]
+    field = O.SCALAR_FIELD[curve] if which == 0 else O.BASE_FIELD[curve]
+    p = O.MODULUS[field]
+    edge = [0, 1, 2, p - 1, p - 2, (1 << 254) - 1, 1 << 254, (1 << 32) - 1, 1 << 32, p >> 1]
+    a = np.concatenate([O.ints_to_limbs(edge), O.random_field_mont(field, 4000, 1)])
+    b = np.concatenate([O.ints_to_limbs(list(reversed(edge))), O.random_field_mont(field, 4000, 2)])
+    for op in ("add", "sub", "mul"):
+        assert np.array_equal(ctx.field_op(op, a, b, which_field=which), O.field_op(field, op, a, b)), op
+    assert np.array_equal(ctx.field_op("sqr", a, which_field=which), O.field_op(field, "sqr", a))
+    assert np.array_equal(ctx.field_op("inv", a[:300], which_field=which), O.field_op(field, "inv", a[:300]))
+
+
+# ---- K4 NTT ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("curve", [O.VESTA, O.PALLAS])
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 5, 9, 10, 11, 12, 13, 16, 18])
+def test_best_fft(pkg, ctxs, curve, log_n):
+    ctx = ctxs[curve]
+    field = O.SCALAR_FIELD[curve]
+    F = {O.FP: pm.Fp, O.FQ: pm.Fq}[field]
+    omega = O.to_mont(field, O.ints_to_limbs([F.root_of_unity(log_n)]))[0]
+    batch = 3 if log_n <= 13 else 1
+    a = O.random_field_mont(field, batch << log_n, 30 + log_n).reshape(batch, 1 << log_n, 4)
+    got = pkg.best_fft(ctx, a, omega, log_n)
+    for b in range(batch):
+        assert np.array_equal(got[b], O.fft(field, a[b], log_n, omega)), (log_n, b)
+
+
+def test_best_fft_rejects_bad_length(pkg, ctxs):
+    ctx = ctxs[O.VESTA]
+    omega = O.to_mont(O.FP, O.ints_to_limbs([pm.Fp.root_of_unity(4)]))[0]
+    with pytest.raises(ValueError):
+        pkg.best_fft(ctx, np.zeros((15, 4), dtype=np.uint64), omega, 4)
+
+
+def test_ntt_roundtrip_2_20(pkg, ctxs):
+    """size-independent property at BASELINE size: iNTT(NTT(a)) * n^-1 == a (lagrange_to_coeff o coeff_to_lagrange)."""
+    ctx = ctxs[O.VESTA]
+    dom = pkg.EvaluationDomain(ctx, 6, 20)
+    a = O.random_field_mont(O.FP, 1 << 20, 31)
+    lag = dom.coeff_to_lagrange(a)
+    assert np.array_equal(dom.lagrange_to_coeff(lag), a)
+    # and one spot-check of the forward transform against the oracle at full size
+    assert np.array_equal(lag, O.fft(O.FP, a, 20, dom.omega))
+
+
+# ---- K5 EvaluationDomain ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("curve", [O.VESTA, O.PALLAS])
+@pytest.mark.parametrize("j,k", [(6, 1), (6, 4), (6, 8), (6, 11), (3, 5), (4, 6), (9, 7), (2, 6)])
+def test_domain_transforms(pkg, ctxs, curve, j, k):
+    ctx = ctxs[curve]
+    field = O.SCALAR_FIELD[curve]
+    dom = pkg.EvaluationDomain(ctx, j, k)
+    ek, om, eom = O.domain_info(field, j, k)
+    assert dom.extended_k == ek
+    assert np.array_equal(dom.omega, om) and np.array_equal(dom.extended_omega, eom)
+    n = 1 << k
+    cols = O.random_field_mont(field, 3 * n, 50 + k).reshape(3, n, 4)
+    coeff = dom.lagrange_to_coeff(cols)
+    assert np.array_equal(coeff, O.lagrange_to_coeff(field, j, k, cols).reshape(3, n, 4))
+    ext = dom.coeff_to_extended(coeff)
+    assert np.array_equal(ext, O.coeff_to_extended(field, j, k, coeff))
+    h = O.random_field_mont(field, 1 << ek, 60 + k)
+    for divide in (False, True):
+        got = dom.extended_to_coeff(h, divide_by_vanishing_poly=divide)
+        assert np.array_equal(got, O.extended_to_coeff(field, j, k, h, divide=divide)), divide
+    # extended_to_coeff undoes coeff_to_extended (upper coefficients are zero)
+    back = dom.extended_to_coeff(ext[1])
+    assert np.array_equal(back[:n], coeff[1]) and not back[n:].any()
+
+
+# ---- K3 MSM ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("curve", [O.VESTA, O.PALLAS])
+@pytest.mark.parametrize("flags", [1, 2])      # 1 = per-window bucket sets, 2 = precomputed multiples
+@pytest.mark.parametrize("n", [0, 1, 2, 5, 33, 1000, (1 << 12) + 1])
+def test_best_multiexp_small(pkg, ctxs, curve, flags, n):
+    ctx = ctxs[curve]
+    pts = make_points(curve, max(n, 1))[:n]
+    sc = scalars_uniform(curve, max(n, 1), 20 + n)[:n]
+    bases = pkg.Bases(ctx, pts, flags)
+    got = pkg.best_multiexp(ctx, sc, bases)
+    want = O.msm(curve, sc, pts) if n else np.zeros(8, dtype=np.uint64)
+    assert np.array_equal(affine_of(curve, got), want)
+
+
+@pytest.mark.parametrize("flags", [1, 2])
+def test_best_multiexp_edge_cases(pkg, ctxs, flags):
+    """zero / one / p-1 scalars, repeated bases (P + P), inverse pairs (P - P), identity bases, all-equal scalars."""
+    curve = O.VESTA
+    ctx = ctxs[curve]
+    n = 600
+    pts = make_points(curve, n, 77)
+    p = O.MODULUS[O.FP]
+    pts[1] = pts[0]                                   # duplicate base
+    neg = pts[2].copy()
+    negy = O.field_op(O.FQ, "sub", np.zeros((1, 4), dtype=np.uint64), neg[4:].reshape(1, 4))[0]
+    pts[3, :4] = neg[:4]; pts[3, 4:] = negy           # pts[3] = -pts[2]
+    pts[7] = 0                                        # identity base
+    canon = O.from_mont(O.FP, scalars_uniform(curve, n, 5))
+    special = [0, 1, p - 1, 2, (1 << 16) - 1, 1 << 16, (1 << 15), (1 << 255) % p, p - 2]
+    for i, v in enumerate(special):
+        canon[10 + i] = O.ints_to_limbs([v])[0]
+    canon[0] = canon[1] = O.ints_to_limbs([5])[0]     # 5*P + 5*P
+    canon[2] = canon[3] = O.ints_to_limbs([9])[0]     # 9*P - 9*P
+    sc = O.to_mont(O.FP, canon)
+    bases = pkg.Bases(ctx, pts, flags)
+    assert np.array_equal(affine_of(curve, pkg.best_multiexp(ctx, sc, bases)), O.msm(curve, sc, pts))
+    # all scalars equal (one bucket per window receives everything), all ones, all zero
+    for v in (1, 0, 0x1234567, p - 1):
+        sc = O.to_mont(O.FP, np.tile(O.ints_to_limbs([v]), (n, 1)))
+        assert np.array_equal(affine_of(curve, pkg.best_multiexp(ctx, sc, bases)), O.msm(curve, sc, pts)), v
+    # all bases equal: every bucket add hits the doubling path
+    same = np.tile(pts[5], (n, 1))
+    b2 = pkg.Bases(ctx, same, flags)
+    sc = scalars_uniform(curve, n, 9)
+    assert np.array_equal(affine_of(curve, pkg.best_multiexp(ctx, sc, b2)), O.msm(curve, sc, same))
+    # prefix MSM (n smaller than the loaded bases) and a batch of columns
+    sc3 = scalars_uniform(curve, 3 * 100, 10).reshape(3, 100, 4)
+    got = pkg.best_multiexp(ctx, sc3, bases)
+    for k in range(3):
+        assert np.array_equal(affine_of(curve, got[k]), O.msm(curve, sc3[k], pts[:100]))
+
+
+def test_best_multiexp_rejects_length_mismatch(pkg, ctxs):
+    ctx = ctxs[O.VESTA]
+    bases = pkg.Bases(ctx, make_points(O.VESTA, 8))
+    with pytest.raises(ValueError):
+        pkg.best_multiexp(ctx, np.zeros((9, 4), dtype=np.uint64), bases)
+
+
+@pytest.mark.parametrize("shape", ["uniform", "tinyram"])
+def test_best_multiexp_2_16(pkg, ctxs, shape):
+    curve = O.VESTA
+    ctx = ctxs[curve]
+    n = (1 << 16) + 1
+    pts = make_points(curve, n)
+    sc = scalars_uniform(curve, n) if shape == "uniform" else scalars_tinyram(curve, n)
+    bases = pkg.Bases(ctx, pts)
+    assert np.array_equal(affine_of(curve, pkg.best_multiexp(ctx, sc, bases)), O.msm(curve, sc, pts))
+
+
+def test_commit_lagrange_linearity_2_20(pkg, ctxs):
+    """BASELINE size (k = 20): commit(a) + commit(b) == commit(a + b) with independent blinds, both scalar shapes;
+    plus a direct oracle comparison of one of the three MSMs."""
+    curve = O.VESTA
+    ctx = ctxs[curve]
+    k = 20
+    n = 1 << k
+    pts = make_points(curve, 2 * n + 1)
+    params = pkg.Params(ctx, k, pts[:n], pts[n:2 * n], pts[2 * n])
+    a = scalars_uniform(curve, n, 1); b = scalars_tinyram(curve, n, 2)
+    ra, rb = scalars_uniform(curve, 2, 3)
+    ab = ctx.field_op("add", a, b); rab = ctx.field_op("add", ra.reshape(1, 4), rb.reshape(1, 4))[0]
+    ca = affine_of(curve, params.commit_lagrange(a, ra))
+    cb = affine_of(curve, params.commit_lagrange(b, rb))
+    cab = affine_of(curve, params.commit_lagrange(ab, rab))
+    assert np.array_equal(O.point_add(curve, ca, cb), cab)
+    want = O.msm(curve, np.concatenate([b, rb.reshape(1, 4)]), np.concatenate([pts[n:2 * n], pts[2 * n:2 * n + 1]]))
+    assert np.array_equal(cb, want)

@@ -1,0 +1,163 @@
+"""ctypes binding of libtrp.so (include/tr_prover.h).  Fails loudly when the library or a GPU is missing."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libtrp.so")
+
+PALLAS, VESTA = 0, 1
+
+TRP_OK, TRP_E_INVALID, TRP_E_CUDA, TRP_E_OOM, TRP_E_NODEVICE = 0, -1, -2, -3, -4
+_ERR_NAMES = {-1: "TRP_E_INVALID", -2: "TRP_E_CUDA", -3: "TRP_E_OOM", -4: "TRP_E_NODEVICE"}
+
+# every symbol include/tr_prover.h declares (tests check that the library exports them all)
+EXPORTED_SYMBOLS = [
+    "trp_ctx_create", "trp_ctx_destroy", "trp_last_error", "trp_ctx_set_stream", "trp_ctx_sync",
+    "trp_ctx_launch_count", "trp_version",
+    "trp_bases_load", "trp_dev_bases_load", "trp_bases_load_ex", "trp_bases_len", "trp_bases_describe", "trp_bases_free",
+    "trp_msm", "trp_msm_batch", "trp_dev_msm_batch",
+    "trp_ntt", "trp_dev_ntt",
+    "trp_domain_create", "trp_domain_free", "trp_domain_extended_k", "trp_domain_constants",
+    "trp_lagrange_to_coeff", "trp_dev_lagrange_to_coeff", "trp_coeff_to_lagrange",
+    "trp_coeff_to_extended", "trp_dev_coeff_to_extended", "trp_extended_to_coeff", "trp_dev_extended_to_coeff",
+    "trp_field_op", "trp_microbench",
+]
+
+
+class TrpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{_ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return _SO
+
+
+def build_library(force: bool = False, jobs: int = 8) -> str:
+    """Compile csrc/*.cu for sm_100a into libtrp.so (nvcc cross-compiles without a GPU)."""
+    csrc = os.path.join(_HERE, "csrc")
+    cmd = ["make", "-C", csrc, f"-j{jobs}"]
+    if force:
+        cmd.append("-B")
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise TrpError(TRP_E_NODEVICE, f"{_SO} is missing: build it with __graft_entry__.build() "
+                                       "(there is no CPU fallback)")
+    L = ctypes.CDLL(_SO)
+    vp, sz, u, i = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint, ctypes.c_int
+    L.trp_ctx_create.argtypes = [ctypes.POINTER(vp), i, i]
+    L.trp_ctx_destroy.argtypes = [vp]; L.trp_ctx_destroy.restype = None
+    L.trp_last_error.argtypes = [vp]; L.trp_last_error.restype = ctypes.c_char_p
+    L.trp_ctx_set_stream.argtypes = [vp, vp]
+    L.trp_ctx_sync.argtypes = [vp]
+    L.trp_ctx_launch_count.argtypes = [vp]; L.trp_ctx_launch_count.restype = ctypes.c_uint64
+    L.trp_version.restype = ctypes.c_char_p
+    L.trp_bases_load.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
+    L.trp_dev_bases_load.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
+    L.trp_bases_load_ex.argtypes = [vp, vp, sz, i, ctypes.POINTER(vp)]
+    L.trp_bases_len.argtypes = [vp]; L.trp_bases_len.restype = sz
+    L.trp_bases_describe.argtypes = [vp, vp]
+    L.trp_bases_free.argtypes = [vp]; L.trp_bases_free.restype = None
+    L.trp_msm.argtypes = [vp, vp, vp, sz, vp]
+    L.trp_msm_batch.argtypes = [vp, vp, vp, sz, sz, vp]
+    L.trp_dev_msm_batch.argtypes = [vp, vp, vp, sz, sz, vp]
+    L.trp_ntt.argtypes = [vp, vp, sz, u, vp]
+    L.trp_dev_ntt.argtypes = [vp, vp, sz, u, vp]
+    L.trp_domain_create.argtypes = [vp, u, u, ctypes.POINTER(vp)]
+    L.trp_domain_free.argtypes = [vp]; L.trp_domain_free.restype = None
+    L.trp_domain_extended_k.argtypes = [vp]; L.trp_domain_extended_k.restype = u
+    L.trp_domain_constants.argtypes = [vp, vp]
+    L.trp_lagrange_to_coeff.argtypes = [vp, vp, sz]
+    L.trp_dev_lagrange_to_coeff.argtypes = [vp, vp, sz]
+    L.trp_coeff_to_lagrange.argtypes = [vp, vp, sz]
+    L.trp_coeff_to_extended.argtypes = [vp, vp, vp, sz]
+    L.trp_dev_coeff_to_extended.argtypes = [vp, vp, vp, sz]
+    L.trp_extended_to_coeff.argtypes = [vp, vp, vp, i]
+    L.trp_dev_extended_to_coeff.argtypes = [vp, vp, vp, i]
+    L.trp_field_op.argtypes = [vp, i, i, vp, vp, vp, sz]
+    L.trp_microbench.argtypes = [vp, i, i, ctypes.POINTER(ctypes.c_double)]
+    _lib = L
+    return L
+
+
+def as_u64(a, copy=False):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a.copy() if copy else a
+
+
+def ptr(a):
+    """host numpy array -> void*; int -> device pointer as void*."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Context:
+    """One device + one stream + one commitment curve (trp_ctx).  curve = VESTA is what the reference uses
+    (Params<EqAffine>, src/test_utils.rs:12,21): scalars / NTT field Fp, point coordinates Fq."""
+
+    def __init__(self, device: int = 0, curve: int = VESTA):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.trp_ctx_create(ctypes.byref(h), device, curve)
+        if rc != TRP_OK:
+            why = {TRP_E_NODEVICE: "no CUDA device is visible (this backend has no CPU fallback)",
+                   TRP_E_INVALID: "invalid device or curve id"}.get(rc, "context creation failed")
+            raise TrpError(rc, why)
+        self.handle = h
+        self.device, self.curve = device, curve
+
+    def check(self, rc):
+        if rc != TRP_OK:
+            raise TrpError(rc, self.lib.trp_last_error(self.handle).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self.check(self.lib.trp_ctx_set_stream(self.handle, ctypes.c_void_p(cuda_stream_ptr or 0)))
+
+    def sync(self):
+        self.check(self.lib.trp_ctx_sync(self.handle))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.trp_ctx_launch_count(self.handle))
+
+    def field_op(self, op, a, b=None, which_field=0):
+        code = {"add": 0, "sub": 1, "mul": 2, "inv": 3, "sqr": 4}[op]
+        a = as_u64(a); out = np.empty_like(a)
+        bb = as_u64(b) if b is not None else None
+        self.check(self.lib.trp_field_op(self.handle, which_field, code, ptr(a), ptr(bb), ptr(out), a.size // 4))
+        return out
+
+    def microbench(self, kind, iters=256) -> float:
+        v = ctypes.c_double()
+        self.check(self.lib.trp_microbench(self.handle, kind, iters, ctypes.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.trp_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

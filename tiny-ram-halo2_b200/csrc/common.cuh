@@ -1,0 +1,118 @@
+// Shared host-side plumbing for the C ABI: context, error reporting, workspace arena, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tr_prover.h"
+#include "ff.cuh"
+
+struct TwiddleTable {
+  unsigned log_n;        // table holds omega^i for i < 2^(log_n-1)
+  uint64_t omega[4];
+  void* d_tab;
+};
+
+struct trp_ctx {
+  int device = 0;
+  int curve = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::mutex mu;
+  uint64_t launches = 0;
+  int sm_count = 148;
+  // scratch arena (grown on demand, never shrunk)
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // small pinned staging buffer for results
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  std::vector<TwiddleTable> twiddles;
+};
+
+struct trp_bases {
+  trp_ctx* ctx;
+  size_t n;
+  void* d_xy;   // n x 64 B affine
+};
+
+#define TRP_FAIL(ctx, code, ...)                              \
+  do {                                                        \
+    char _buf[512];                                           \
+    snprintf(_buf, sizeof(_buf), __VA_ARGS__);                \
+    (ctx)->err = _buf;                                        \
+    return (code);                                            \
+  } while (0)
+
+#define TRP_CUDA(ctx, expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      int _code = (_e == cudaErrorMemoryAllocation) ? TRP_E_OOM : TRP_E_CUDA;                        \
+      TRP_FAIL(ctx, _code, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    }                                                                                                \
+  } while (0)
+
+#define TRP_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != TRP_OK) return _rc; \
+  } while (0)
+
+// check the launch that was just issued
+#define TRP_LAUNCHED(ctx)                      \
+  do {                                         \
+    (ctx)->launches++;                         \
+    TRP_CUDA(ctx, cudaGetLastError());         \
+  } while (0)
+
+// grow-only scratch arena
+inline int trp_ws_reserve(trp_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->ws_bytes) return TRP_OK;
+  if (ctx->ws) {
+    TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    TRP_CUDA(ctx, cudaFree(ctx->ws));
+    ctx->ws = nullptr; ctx->ws_bytes = 0;
+  }
+  size_t want = bytes + (bytes >> 3);
+  cudaError_t e = cudaMalloc(&ctx->ws, want);
+  if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&ctx->ws, want); }
+  if (e != cudaSuccess) { cudaGetLastError(); TRP_FAIL(ctx, TRP_E_OOM, "workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e)); }
+  ctx->ws_bytes = want;
+  return TRP_OK;
+}
+
+// bump allocator over the arena (256-byte aligned)
+struct WsCursor {
+  char* base; size_t off; size_t cap;
+  template <class T> T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+inline size_t ws_align(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// entry points implemented per translation unit
+int trp_ntt_impl(trp_ctx* ctx, int field, const void* d_src, void* d_dst, size_t batch, unsigned log_n,
+                 const uint64_t omega[4], size_t src_stride, size_t dst_stride, unsigned n_src,
+                 const void* d_pre, unsigned pre_period, const void* d_post, unsigned post_period, unsigned n_dst,
+                 void* d_tmp /* batch*2^log_n elements, needed iff src==dst and passes>1 */);
+size_t trp_ntt_passes(unsigned log_n);
+int trp_msm_impl(trp_ctx* ctx, const trp_bases* bases, const void* d_scalars, size_t n, size_t m, void* d_out_jac,
+                 void* ws, size_t ws_bytes);
+size_t trp_msm_ws_bytes(const trp_bases* bases, size_t n);
+int trp_bases_create(trp_ctx* ctx, const void* src, bool src_on_device, size_t n, int flags, trp_bases** out);
+void trp_bases_destroy(trp_bases* b);
+int trp_bases_info(const trp_bases* b, unsigned* c, unsigned* W, unsigned* precomp);
+int trp_field_op_impl(trp_ctx* ctx, int field, int op, const void* d_a, const void* d_b, void* d_out, size_t n);
+int trp_microbench_impl(trp_ctx* ctx, int kind, int iters, double* out_gops);
+
+// field ids used internally: 0 = Fp, 1 = Fq
+inline int scalar_field_of(int curve) { return curve == TRP_CURVE_PALLAS ? 1 : 0; }
+inline int base_field_of(int curve) { return curve == TRP_CURVE_PALLAS ? 0 : 1; }

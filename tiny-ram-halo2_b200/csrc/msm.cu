@@ -1,0 +1,556 @@
+// K3: Pippenger multi-scalar multiplication on Pallas / Vesta for sm_100a.
+//
+// Replaces halo2_proofs::arithmetic::best_multiexp (and Params::commit / commit_lagrange which call it),
+// halo2_proofs 0.2.0 @ a95945254dcc (Cargo.lock:619-621), reached from the reference at
+// /root/reference/src/test_utils.rs:23,25,41.  The CPU routine runs one unsigned-window Pippenger per rayon
+// thread slice; the group element it returns is unique, so only the algorithm's RESULT is shared with it.
+//
+// Pipeline per MSM (all on device, no host synchronisation):
+//   1. hist      scalar -> canonical -> signed c-bit digits; warp-aggregated histogram of bucket sizes
+//   2. scan      exclusive prefix sum -> bucket offsets
+//   3. scatter   counting sort of (point index | sign) entries into bucket order
+//   4. accumulate  multi-level segmented reduction: every task adds <= L consecutive entries of one bucket
+//                (mixed XYZZ adds for level 1, full adds above), so run time is independent of how skewed
+//                the bucket sizes are (TinyRAM columns are mostly 0/1: one bucket gets ~n entries)
+//   5. reduce    sum_b (b+1) * B_b per bucket set by chunked running sums, block tree-sum
+//   6. final     Horner over bucket sets (none when bases are precomputed) -> Jacobian point
+//
+// Bases are static (Params.g_lagrange ++ [w]); with 180 GB of HBM the loader precomputes 2^(c*w) * P_i for
+// every window w so that all windows share ONE bucket set: no per-window reduction, no doubling chain, long
+// uniform bucket runs.  When that table would not fit the budget the windows keep separate bucket sets.
+#include "common.cuh"
+#include "ec.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+using namespace ff;
+using namespace ec;
+
+struct MsmGeom {
+  unsigned c;        // window bits
+  unsigned W;        // number of windows
+  unsigned nsets;    // bucket sets: 1 (precomputed bases) or W
+  unsigned B;        // buckets per set = 2^(c-1)
+  unsigned nb;       // nsets * B
+  unsigned precomp;  // 1: entry index = w * stride + i into the precomputed table
+  size_t stride;     // number of loaded bases (table row length)
+};
+
+struct trp_bases_impl {
+  trp_bases pub;
+  MsmGeom g;
+};
+
+namespace {
+
+constexpr unsigned L1 = 64;     // entries per level-1 task
+constexpr unsigned L2 = 16;     // partials per task at levels >= 2
+constexpr unsigned RED_S = 16;  // buckets per running-sum chunk
+constexpr int ACC_THREADS = 128;
+
+__device__ __forceinline__ unsigned extract_bits(const uint32_t* v, unsigned off, unsigned c) {
+  unsigned idx = off >> 5, sh = off & 31;
+  if (idx >= 8) return 0;
+  uint64_t lo = v[idx];
+  uint64_t hi = idx + 1 < 8 ? v[idx + 1] : 0;
+  uint64_t x = (lo | (hi << 32)) >> sh;
+  return (unsigned)(x & ((1u << c) - 1));
+}
+
+// Signed-digit recoding shared by hist and scatter: digit d_w in [-2^(c-1), 2^(c-1)), sum d_w 2^(cw) = scalar.
+// f(w, key, neg) is called for every window by every lane (key = 0xffffffff for zero digits) so that
+// warp-collective code inside f stays converged.
+template <class SPR, class F>
+__device__ __forceinline__ void for_each_digit(const uint4* scalars, size_t i, size_t n, const MsmGeom& g, F f) {
+  uint32_t v[8];
+  if (i < n) {
+    Fe<SPR> s = fe_from_mont(fe_load<SPR>(scalars + 2 * i));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = s.v[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0;
+  }
+  unsigned carry = 0;
+  const unsigned half = 1u << (g.c - 1);
+  for (unsigned w = 0; w < g.W; ++w) {
+    unsigned raw = extract_bits(v, w * g.c, g.c) + carry;
+    unsigned neg = raw >= half;
+    unsigned mag = neg ? (2 * half - raw) : raw;
+    carry = neg;
+    unsigned key = mag ? ((g.precomp ? 0u : w * g.B) + mag - 1) : 0xffffffffu;
+    f(w, key, neg);
+  }
+}
+
+template <class SPR>
+__global__ void msm_hist_kernel(const uint4* scalars, size_t n, MsmGeom g, uint32_t* counts) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for_each_digit<SPR>(scalars, i, n, g, [&](unsigned, unsigned key, unsigned) {
+    unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key != 0xffffffffu && (unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(&counts[key], __popc(peers));
+  });
+}
+
+template <class SPR>
+__global__ void msm_scatter_kernel(const uint4* scalars, size_t n, MsmGeom g, uint32_t* cursor, uint32_t* entries) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31;
+  for_each_digit<SPR>(scalars, i, n, g, [&](unsigned w, unsigned key, unsigned neg) {
+    unsigned peers = __match_any_sync(0xffffffffu, key);
+    unsigned leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if (key != 0xffffffffu && leader == lane) base = atomicAdd(&cursor[key], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (key != 0xffffffffu) {
+      unsigned rank = __popc(peers & ((1u << lane) - 1));
+      uint32_t idx = (uint32_t)(g.precomp ? (size_t)w * g.stride + i : i);
+      entries[base + rank] = idx | (neg << 31);
+    }
+  });
+}
+
+// ---- exclusive scan of uint32 (n <= 4096 * 1024) -----------------------------------------------------------
+constexpr int SCAN_T = 512, SCAN_ITEMS = 8, SCAN_BLOCK = SCAN_T * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[32];
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t s = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+    warp_sums[lane] = s;
+  }
+  __syncthreads();
+  uint32_t prefix = wid ? warp_sums[wid - 1] : 0;
+  if (total) *total = warp_sums[(blockDim.x >> 5) - 1];
+  __syncthreads();
+  return prefix + x - v;
+}
+
+// mode 0: in = counts as is; mode 1: in = ceil((off[i+1]-off[i]) / L) (task counts derived from offsets)
+__device__ __forceinline__ uint32_t scan_input(const uint32_t* in, size_t i, size_t n, int mode, unsigned L) {
+  if (i >= n) return 0;
+  if (mode == 0) return in[i];
+  uint32_t cnt = in[i + 1] - in[i];
+  return (cnt + L - 1) / L;
+}
+
+__global__ void scan_local_kernel(const uint32_t* in, uint32_t* out, uint32_t* block_sums, size_t n, int mode, unsigned L) {
+  size_t base = (size_t)blockIdx.x * SCAN_BLOCK + (size_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = scan_input(in, base + k, n, mode, L); sum += v[k]; }
+  uint32_t total;
+  uint32_t pre = block_exclusive_scan(sum, &total);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) out[base + k] = pre; pre += v[k]; }
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void scan_sums_kernel(uint32_t* block_sums, unsigned nblocks, uint32_t* grand_total) {
+  // single block of SCAN_T threads, nblocks <= SCAN_BLOCK
+  size_t base = (size_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = base + k < nblocks ? block_sums[base + k] : 0; sum += v[k]; }
+  uint32_t total;
+  uint32_t pre = block_exclusive_scan(sum, &total);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < nblocks) block_sums[base + k] = pre; pre += v[k]; }
+  if (threadIdx.x == 0) *grand_total = total;
+}
+// out[i] += block_sums[block]; optionally mirror into out2 (cursor copy); out[n] = total
+__global__ void scan_add_kernel(uint32_t* out, uint32_t* out2, const uint32_t* block_sums, const uint32_t* grand_total, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t v = out[i] + block_sums[i / SCAN_BLOCK];
+    out[i] = v;
+    if (out2) out2[i] = v;
+  } else if (i == n) {
+    out[n] = *grand_total;
+  }
+}
+
+// ---- accumulation ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned find_segment(const uint32_t* off, unsigned nseg, uint32_t t) {
+  // largest b in [0, nseg) with off[b] <= t   (off is non-decreasing, off[nseg] > t)
+  unsigned lo = 0, hi = nseg;
+  while (hi - lo > 1) {
+    unsigned mid = (lo + hi) >> 1;
+    if (__ldg(off + mid) <= t) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <class BPR>
+__device__ __forceinline__ Affine<BPR> load_affine(const uint4* bases, size_t idx) {
+  const uint4* p = bases + 4 * idx;
+  uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+  Affine<BPR> r;
+  r.x.v[0] = a.x; r.x.v[1] = a.y; r.x.v[2] = a.z; r.x.v[3] = a.w; r.x.v[4] = b.x; r.x.v[5] = b.y; r.x.v[6] = b.z; r.x.v[7] = b.w;
+  r.y.v[0] = c.x; r.y.v[1] = c.y; r.y.v[2] = c.z; r.y.v[3] = c.w; r.y.v[4] = d.x; r.y.v[5] = d.y; r.y.v[6] = d.z; r.y.v[7] = d.w;
+  return r;
+}
+template <class BPR>
+__device__ __forceinline__ XYZZ<BPR> load_xyzz(const uint4* p) {
+  XYZZ<BPR> r;
+  r.x = fe_load<BPR>(p); r.y = fe_load<BPR>(p + 2); r.zz = fe_load<BPR>(p + 4); r.zzz = fe_load<BPR>(p + 6);
+  return r;
+}
+template <class BPR>
+__device__ __forceinline__ void store_xyzz(uint4* p, const XYZZ<BPR>& a) {
+  fe_store(p, a.x); fe_store(p + 2, a.y); fe_store(p + 4, a.zz); fe_store(p + 6, a.zzz);
+}
+
+// level 1: entries (index | sign) -> affine bases, mixed adds
+template <class BPR>
+__global__ void __launch_bounds__(ACC_THREADS) msm_accum_l1_kernel(const uint32_t* entries, const uint32_t* in_off,
+                                                                 const uint32_t* task_off, unsigned nb,
+                                                                 const uint4* bases, uint4* partials) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= __ldg(task_off + nb)) return;
+  unsigned b = find_segment(task_off, nb, t);
+  uint32_t j = t - __ldg(task_off + b);
+  uint32_t start = __ldg(in_off + b) + j * L1;
+  uint32_t end = min(start + L1, __ldg(in_off + b + 1));
+  XYZZ<BPR> acc = xyzz_identity<BPR>();
+  for (uint32_t e = start; e < end; ++e) {
+    uint32_t ent = __ldg(entries + e);
+    Affine<BPR> p = load_affine<BPR>(bases, ent & 0x7fffffffu);
+    if (ent >> 31) p.y = fe_neg(p.y);
+    xyzz_add_mixed(acc, p);
+  }
+  store_xyzz(partials + 8 * (size_t)t, acc);
+}
+
+// levels >= 2: partial sums of the previous level, full adds
+template <class BPR>
+__global__ void __launch_bounds__(ACC_THREADS) msm_accum_ln_kernel(const uint4* in, const uint32_t* in_off,
+                                                                 const uint32_t* task_off, unsigned nb, uint4* partials) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= __ldg(task_off + nb)) return;
+  unsigned b = find_segment(task_off, nb, t);
+  uint32_t j = t - __ldg(task_off + b);
+  uint32_t start = __ldg(in_off + b) + j * L2;
+  uint32_t end = min(start + L2, __ldg(in_off + b + 1));
+  XYZZ<BPR> acc = load_xyzz<BPR>(in + 8 * (size_t)start);
+  for (uint32_t e = start + 1; e < end; ++e) xyzz_add(acc, load_xyzz<BPR>(in + 8 * (size_t)e));
+  store_xyzz(partials + 8 * (size_t)t, acc);
+}
+
+// ---- bucket reduction -------------------------------------------------------------------------------------
+// After the last level every bucket has 0 or 1 partial: B_b = part[off[b]] if off[b+1] > off[b] else identity.
+template <class BPR>
+__device__ __forceinline__ XYZZ<BPR> bucket_value(const uint4* part, const uint32_t* off, unsigned b) {
+  uint32_t o = __ldg(off + b);
+  if (__ldg(off + b + 1) > o) return load_xyzz<BPR>(part + 8 * (size_t)o);
+  return xyzz_identity<BPR>();
+}
+
+template <class BPR>
+__device__ __forceinline__ XYZZ<BPR> xyzz_mul_small(const XYZZ<BPR>& p, unsigned k) {
+  XYZZ<BPR> acc = xyzz_identity<BPR>();
+  if (k == 0 || xyzz_is_identity(p)) return acc;
+  int top = 31 - __clz(k);
+  for (int bit = top; bit >= 0; --bit) {
+    xyzz_dbl(acc);
+    if ((k >> bit) & 1) xyzz_add(acc, p);
+  }
+  return acc;
+}
+
+// chunk of RED_S consecutive buckets [lo, lo+S) of one set: sum_{b} (b+1) B_b = running-sum part + lo * (sum B_b)
+template <class BPR>
+__global__ void __launch_bounds__(ACC_THREADS) msm_reduce_chunks_kernel(const uint4* part, const uint32_t* off, MsmGeom g, uint4* chunk_out) {
+  unsigned chunks_per_set = g.B / RED_S ? g.B / RED_S : 1;
+  unsigned S = g.B < RED_S ? g.B : RED_S;
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.nsets * chunks_per_set) return;
+  unsigned set = t / chunks_per_set, ch = t % chunks_per_set;
+  unsigned lo = ch * S;
+  XYZZ<BPR> run = xyzz_identity<BPR>(), acc = xyzz_identity<BPR>();
+  for (int k = (int)S - 1; k >= 0; --k) {
+    XYZZ<BPR> bv = bucket_value<BPR>(part, off, set * g.B + lo + k);
+    xyzz_add(run, bv);
+    xyzz_add(acc, run);
+  }
+  XYZZ<BPR> scaled = xyzz_mul_small(run, lo);
+  xyzz_add(acc, scaled);
+  store_xyzz(chunk_out + 8 * (size_t)t, acc);
+}
+
+// one block per set: sum the chunk results -> set_sums[set]
+template <class BPR>
+__global__ void __launch_bounds__(256) msm_reduce_sets_kernel(const uint4* chunk_in, unsigned chunks_per_set, uint4* set_sums) {
+  __shared__ uint4 sm[256 * 8];
+  unsigned set = blockIdx.x;
+  const uint4* in = chunk_in + 8 * (size_t)set * chunks_per_set;
+  XYZZ<BPR> acc = xyzz_identity<BPR>();
+  for (unsigned k = threadIdx.x; k < chunks_per_set; k += blockDim.x) xyzz_add(acc, load_xyzz<BPR>(in + 8 * (size_t)k));
+  store_xyzz(sm + 8 * threadIdx.x, acc);
+  __syncthreads();
+  for (unsigned s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      XYZZ<BPR> a = load_xyzz<BPR>(sm + 8 * threadIdx.x);
+      xyzz_add(a, load_xyzz<BPR>(sm + 8 * (threadIdx.x + s)));
+      store_xyzz(sm + 8 * threadIdx.x, a);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    uint4* o = set_sums + 8 * (size_t)set;
+    for (int k = 0; k < 8; ++k) o[k] = sm[k];
+  }
+}
+
+// Horner over sets (window w has weight 2^(c*w)) and conversion XYZZ -> Jacobian (X*ZZ^4... no inversion):
+// (X', Y', Z') = (X * ZZ^4, Y * ZZZ^4, ZZ * ZZZ) since Z'^2 = ZZ^5 and Z'^3 = ZZZ^5.
+template <class BPR>
+__global__ void msm_final_kernel(const uint4* set_sums, MsmGeom g, uint4* out_jac) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  XYZZ<BPR> acc = load_xyzz<BPR>(set_sums + 8 * (size_t)(g.nsets - 1));
+  for (int w = (int)g.nsets - 2; w >= 0; --w) {
+    for (unsigned k = 0; k < g.c; ++k) xyzz_dbl(acc);
+    xyzz_add(acc, load_xyzz<BPR>(set_sums + 8 * (size_t)w));
+  }
+  Fe<BPR> X, Y, Z;
+  if (xyzz_is_identity(acc)) {
+    X = fe_zero<BPR>(); Y = fe_zero<BPR>(); Z = fe_zero<BPR>();
+  } else {
+    Fe<BPR> zz2 = fe_sqr(acc.zz), zzz2 = fe_sqr(acc.zzz);
+    X = fe_mul(acc.x, fe_sqr(zz2));
+    Y = fe_mul(acc.y, fe_sqr(zzz2));
+    Z = fe_mul(acc.zz, acc.zzz);
+  }
+  fe_store(out_jac, X); fe_store(out_jac + 2, Y); fe_store(out_jac + 4, Z);
+}
+
+template <class BPR>
+__global__ void msm_identity_kernel(uint4* out_jac) {
+  if (threadIdx.x < 6) out_jac[threadIdx.x] = make_uint4(0, 0, 0, 0);
+}
+
+// ---- base precomputation: table[w][i] = 2^(c*w) * P_i, affine ---------------------------------------------------
+// One thread per base: walk the doubling chain once (kept in local memory), then normalise all W-1 multiples
+// with a single inversion (Montgomery's trick); the prefix products are stashed in the output slots.
+constexpr unsigned PRECOMP_MAX_W = 64;
+template <class BPR>
+__global__ void __launch_bounds__(128) msm_precompute_kernel(uint4* table, size_t n, unsigned c, unsigned W) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<BPR> p = load_affine<BPR>(table, i);
+  if (affine_is_identity(p)) {
+    for (unsigned w = 1; w < W; ++w)
+      for (int k = 0; k < 4; ++k) table[4 * (w * n + i) + k] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  XYZZ<BPR> chain[PRECOMP_MAX_W - 1];
+  XYZZ<BPR> q = xyzz_from_affine(p);
+  Fe<BPR> prod = fe_one<BPR>();
+  for (unsigned w = 1; w < W; ++w) {
+    for (unsigned k = 0; k < c; ++k) xyzz_dbl(q);     // odd prime order: never reaches the identity
+    chain[w - 1] = q;
+    fe_store(table + 4 * (w * n + i), prod);          // prefix product of the elements before w
+    prod = fe_mul(prod, fe_mul(q.zz, q.zzz));
+  }
+  Fe<BPR> inv = fe_inv(prod);
+  for (unsigned w = W - 1; w >= 1; --w) {
+    uint4* slot = table + 4 * (w * n + i);
+    const XYZZ<BPR> e = chain[w - 1];
+    Fe<BPR> einv = fe_mul(inv, fe_load<BPR>(slot));   // 1 / (zz * zzz) of element w
+    inv = fe_mul(inv, fe_mul(e.zz, e.zzz));
+    fe_store(slot, fe_mul(e.x, fe_mul(einv, e.zzz)));       // X / ZZ
+    fe_store(slot + 2, fe_mul(e.y, fe_mul(einv, e.zz)));    // Y / ZZZ
+  }
+}
+
+unsigned choose_c(size_t n) {
+  unsigned lg = 0;
+  while (((size_t)2 << lg) <= n) ++lg;   // floor(log2 n) for n >= 1
+  int c = (int)lg - 4;
+  if (c < 4) c = 4;
+  if (c > 16) c = 16;
+  if (const char* e = getenv("TRP_MSM_C")) { int v = atoi(e); if (v >= 2 && v <= 16) c = v; }
+  return (unsigned)c;
+}
+
+int run_scan(trp_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t* out2, uint32_t* block_sums, uint32_t* total,
+             size_t n, int mode, unsigned L) {
+  unsigned nblocks = (unsigned)((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
+  if (nblocks > SCAN_BLOCK) TRP_FAIL(ctx, TRP_E_INVALID, "scan of %zu elements exceeds the supported size", n);
+  scan_local_kernel<<<nblocks, SCAN_T, 0, ctx->stream>>>(in, out, block_sums, n, mode, L);
+  TRP_LAUNCHED(ctx);
+  scan_sums_kernel<<<1, SCAN_T, 0, ctx->stream>>>(block_sums, nblocks, total);
+  TRP_LAUNCHED(ctx);
+  scan_add_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(out, out2, block_sums, total, n);
+  TRP_LAUNCHED(ctx);
+  return TRP_OK;
+}
+
+// Worst-case task counts per level (entries may all fall into one bucket, or spread over all of them).
+std::vector<size_t> plan_levels(const MsmGeom& g, size_t n) {
+  const size_t M = n * g.W;
+  std::vector<size_t> level_tasks;
+  size_t single = (M + L1 - 1) / L1;            // tasks if ONE bucket held every entry
+  size_t bound = single + g.nb;                 // sum_b ceil(cnt_b / L1) <= M / L1 + nb
+  level_tasks.push_back(bound);
+  while (single > 1) {
+    single = (single + L2 - 1) / L2;
+    bound = (bound + L2 - 1) / L2 + g.nb;
+    level_tasks.push_back(bound);
+  }
+  return level_tasks;
+}
+
+template <class BPR, class SPR>
+int msm_one(trp_ctx* ctx, const trp_bases_impl* bs, const uint4* d_scalars, size_t n, uint4* d_out, char* ws, size_t ws_cap) {
+  const MsmGeom& g = bs->g;
+  if (n == 0) {
+    msm_identity_kernel<BPR><<<1, 32, 0, ctx->stream>>>(d_out);
+    TRP_LAUNCHED(ctx);
+    return TRP_OK;
+  }
+  const size_t M = n * g.W;   // upper bound on entries
+  if (M >= (size_t)1 << 31) TRP_FAIL(ctx, TRP_E_INVALID, "MSM of %zu points x %u windows exceeds the 2^31 entry limit", n, g.W);
+  std::vector<size_t> level_tasks = plan_levels(g, n);
+  WsCursor cur{ws, 0, ws_cap};
+  uint32_t* counts = cur.take<uint32_t>(g.nb + 1);
+  uint32_t* offsets = cur.take<uint32_t>(g.nb + 1);
+  uint32_t* cursor = cur.take<uint32_t>(g.nb + 1);
+  uint32_t* block_sums = cur.take<uint32_t>(SCAN_BLOCK);
+  uint32_t* total = cur.take<uint32_t>(4);
+  uint32_t* entries = cur.take<uint32_t>(M);
+  uint32_t* task_off[2] = {cur.take<uint32_t>(g.nb + 1), cur.take<uint32_t>(g.nb + 1)};
+  uint4* part[2] = {cur.take<uint4>(8 * level_tasks[0]), cur.take<uint4>(8 * (level_tasks.size() > 1 ? level_tasks[1] : 1))};
+  unsigned chunks_per_set = g.B / RED_S ? g.B / RED_S : 1;
+  uint4* chunk_out = cur.take<uint4>(8 * (size_t)g.nsets * chunks_per_set);
+  uint4* set_sums = cur.take<uint4>(8 * (size_t)g.nsets);
+  if (cur.off > ws_cap) TRP_FAIL(ctx, TRP_E_INVALID, "internal: MSM workspace underestimated (%zu > %zu)", cur.off, ws_cap);
+
+  TRP_CUDA(ctx, cudaMemsetAsync(counts, 0, (g.nb + 1) * sizeof(uint32_t), ctx->stream));
+  unsigned sblocks = (unsigned)((n + 127) / 128);
+  msm_hist_kernel<SPR><<<sblocks, 128, 0, ctx->stream>>>(d_scalars, n, g, counts);
+  TRP_LAUNCHED(ctx);
+  TRP_TRY(run_scan(ctx, counts, offsets, cursor, block_sums, total, g.nb, 0, 1));
+  msm_scatter_kernel<SPR><<<sblocks, 128, 0, ctx->stream>>>(d_scalars, n, g, cursor, entries);
+  TRP_LAUNCHED(ctx);
+
+  // level 1
+  TRP_TRY(run_scan(ctx, offsets, task_off[0], nullptr, block_sums, total, g.nb, 1, L1));
+  msm_accum_l1_kernel<BPR><<<(unsigned)((level_tasks[0] + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(
+      entries, offsets, task_off[0], g.nb, (const uint4*)bs->pub.d_xy, part[0]);
+  TRP_LAUNCHED(ctx);
+  int curp = 0;
+  for (size_t lv = 1; lv < level_tasks.size(); ++lv) {
+    TRP_TRY(run_scan(ctx, task_off[curp], task_off[curp ^ 1], nullptr, block_sums, total, g.nb, 1, L2));
+    msm_accum_ln_kernel<BPR><<<(unsigned)((level_tasks[lv] + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(
+        part[curp], task_off[curp], task_off[curp ^ 1], g.nb, part[curp ^ 1]);
+    TRP_LAUNCHED(ctx);
+    curp ^= 1;
+  }
+  unsigned nchunks = g.nsets * chunks_per_set;
+  msm_reduce_chunks_kernel<BPR><<<(nchunks + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, ctx->stream>>>(part[curp], task_off[curp], g, chunk_out);
+  TRP_LAUNCHED(ctx);
+  msm_reduce_sets_kernel<BPR><<<g.nsets, 256, 0, ctx->stream>>>(chunk_out, chunks_per_set, set_sums);
+  TRP_LAUNCHED(ctx);
+  msm_final_kernel<BPR><<<1, 32, 0, ctx->stream>>>(set_sums, g, d_out);
+  TRP_LAUNCHED(ctx);
+  return TRP_OK;
+}
+
+size_t msm_ws_bytes(const MsmGeom& g, size_t n) {
+  const size_t M = n * g.W;
+  std::vector<size_t> lt = plan_levels(g, n);
+  size_t t0 = lt[0], t1 = lt.size() > 1 ? lt[1] : 1;
+  unsigned chunks_per_set = g.B / RED_S ? g.B / RED_S : 1;
+  size_t b = 0;
+  b += 5 * ws_align((g.nb + 1) * 4) + ws_align(SCAN_BLOCK * 4) + ws_align(16);
+  b += ws_align(M * 4);
+  b += ws_align(t0 * 128) + ws_align(t1 * 128);
+  b += ws_align((size_t)g.nsets * chunks_per_set * 128) + ws_align((size_t)g.nsets * 128);
+  return b + 4096;
+}
+
+}  // namespace
+
+// ---- C-ABI facing implementation -------------------------------------------------------------------------------
+int trp_bases_create(trp_ctx* ctx, const void* src, bool src_on_device, size_t n, int flags, trp_bases** out) {
+  if (!out) TRP_FAIL(ctx, TRP_E_INVALID, "out is NULL");
+  if (n > ((size_t)1 << 27)) TRP_FAIL(ctx, TRP_E_INVALID, "too many bases (%zu)", n);
+  trp_bases_impl* b = new trp_bases_impl();
+  b->pub.ctx = ctx; b->pub.n = n; b->pub.d_xy = nullptr;
+  MsmGeom& g = b->g;
+  g.c = choose_c(n ? n : 1);
+  g.W = (256 + g.c - 1) / g.c;
+  g.B = 1u << (g.c - 1);
+  g.stride = n;
+  size_t budget = (size_t)48 << 30;
+  if (const char* e = getenv("TRP_MSM_PRECOMP_BUDGET_MB")) budget = (size_t)atoll(e) << 20;
+  bool precomp = (flags & 1) ? false : ((flags & 2) ? true : (n * 64 * g.W <= budget));
+  if ((size_t)g.W * n >= ((size_t)1 << 31)) precomp = false;
+  if (n == 0 || g.W > PRECOMP_MAX_W) precomp = false;
+  g.precomp = precomp ? 1 : 0;
+  g.nsets = precomp ? 1 : g.W;
+  g.nb = g.nsets * g.B;
+  size_t bytes = (precomp ? (size_t)g.W : 1) * (n ? n : 1) * 64;
+  cudaError_t e = cudaMalloc(&b->pub.d_xy, bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); delete b; TRP_FAIL(ctx, TRP_E_OOM, "allocating %zu bytes for bases failed: %s", bytes, cudaGetErrorString(e)); }
+  if (n) {
+    e = cudaMemcpyAsync(b->pub.d_xy, src, n * 64, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(b->pub.d_xy); delete b; TRP_FAIL(ctx, TRP_E_CUDA, "bases upload failed: %s", cudaGetErrorString(e)); }
+    if (precomp) {
+      unsigned blocks = (unsigned)((n + 127) / 128);
+      if (base_field_of(ctx->curve) == 0) msm_precompute_kernel<FpParams><<<blocks, 128, 0, ctx->stream>>>((uint4*)b->pub.d_xy, n, g.c, g.W);
+      else msm_precompute_kernel<FqParams><<<blocks, 128, 0, ctx->stream>>>((uint4*)b->pub.d_xy, n, g.c, g.W);
+      ctx->launches++;
+      e = cudaGetLastError();
+      if (e != cudaSuccess) { cudaFree(b->pub.d_xy); delete b; TRP_FAIL(ctx, TRP_E_CUDA, "precompute launch failed: %s", cudaGetErrorString(e)); }
+    }
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(b->pub.d_xy); delete b; TRP_FAIL(ctx, TRP_E_CUDA, "bases load failed: %s", cudaGetErrorString(e)); }
+  }
+  *out = &b->pub;
+  return TRP_OK;
+}
+
+void trp_bases_destroy(trp_bases* b) {
+  if (!b) return;
+  trp_bases_impl* impl = reinterpret_cast<trp_bases_impl*>(b);
+  if (b->d_xy) cudaFree(b->d_xy);
+  delete impl;
+}
+
+int trp_bases_info(const trp_bases* b, unsigned* c, unsigned* W, unsigned* precomp) {
+  const trp_bases_impl* impl = reinterpret_cast<const trp_bases_impl*>(b);
+  if (c) *c = impl->g.c;
+  if (W) *W = impl->g.W;
+  if (precomp) *precomp = impl->g.precomp;
+  return TRP_OK;
+}
+
+size_t trp_msm_ws_bytes(const trp_bases* bases, size_t n) {
+  return msm_ws_bytes(reinterpret_cast<const trp_bases_impl*>(bases)->g, n);
+}
+
+int trp_msm_impl(trp_ctx* ctx, const trp_bases* bases, const void* d_scalars, size_t n, size_t m, void* d_out_jac,
+                 void* ws, size_t ws_bytes) {
+  const trp_bases_impl* bs = reinterpret_cast<const trp_bases_impl*>(bases);
+  if (n > bases->n) TRP_FAIL(ctx, TRP_E_INVALID, "MSM length %zu exceeds the %zu loaded bases", n, bases->n);
+  if (ws_bytes < msm_ws_bytes(bs->g, n)) TRP_FAIL(ctx, TRP_E_INVALID, "internal: MSM workspace too small");
+  for (size_t k = 0; k < m; ++k) {
+    const uint4* sc = (const uint4*)d_scalars + 2 * k * n;
+    uint4* out = (uint4*)d_out_jac + 6 * k;
+    int rc;
+    if (ctx->curve == TRP_CURVE_PALLAS) rc = msm_one<FpParams, FqParams>(ctx, bs, sc, n, out, (char*)ws, ws_bytes);
+    else rc = msm_one<FqParams, FpParams>(ctx, bs, sc, n, out, (char*)ws, ws_bytes);
+    if (rc != TRP_OK) return rc;
+  }
+  return TRP_OK;
+}
