@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the prover hot path on B200.
+
+Workload (BASELINE.json configs[1]/[3] at k = 20): one step = a batch of M = 8 commit_lagrange-shaped MSMs
+(n = 2^20 + 1 Vesta points each, uniform 255-bit Fp scalars) against one resident base set, i.e. 8 of the ~500
+column commitments of a TinyRAM create_proof at k = 20.  Metric: MSM throughput in Mpts/s (whole job, all ranks).
+Inputs exceed L2 (256 MiB of scalars + 1 GiB precomputed base table per step vs 126 MB L2), so no flush is needed.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [...]                          # CPU restatement of halo2's best_multiexp (oracle)
+
+N > 1 is launched by torchrun (one rank per GPU); columns are sharded across ranks (weak scaling: every rank commits
+its own M columns), the only exchange is an all_gather of the M x 96-byte results.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_LOG = 20
+N_POINTS = (1 << K_LOG) + 1
+M_COLS = 8
+METRIC = "msm_throughput"
+UNIT = "Mpts/s"
+WORKLOAD = f"commit_lagrange-shaped MSM batch: {M_COLS} columns x (2^{K_LOG}+1) Vesta points, uniform Fp scalars (TinyRAM create_proof k={K_LOG} column commitments)"
+FMUL_PER_MIXED_ADD = 10          # XYZZ madd-2008-s: 8M + 2S
+MACS_PER_FMUL = 128              # generic 8x8-limb CIOS: 64 product + 64 reduction 32x32->64 MACs
+
+
+def _config(extra=None):
+    c = {"workload": WORKLOAD, "k": K_LOG, "columns_per_step": M_COLS, "points_per_msm": N_POINTS, "curve": "vesta",
+         "l2_policy": "inputs larger than L2 (256 MiB scalars + 1 GiB base table per step)"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk); smax.append(mx)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:   # region shorter than the sampling period: fall back to all samples
+            for ts, line in self.lines:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+def _traffic_from_profiles():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any (profiles/*.json)."""
+    p = os.path.join(ROOT, "profiles", "msm_accum_l1_ncu.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# -------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of halo2_proofs::arithmetic::best_multiexp on the host cores
+# -------------------------------------------------------------------------------------------------------------
+def _cpu_inputs(n_cols):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import make_points
+    pts = make_points(O.VESTA, N_POINTS)
+    rng = np.random.Generator(np.random.PCG64(20))
+    sc = rng.integers(0, 1 << 64, size=(n_cols, N_POINTS, 4), dtype=np.uint64)
+    sc[..., 3] &= np.uint64((1 << 62) - 1)
+    return O, pts, sc
+
+
+def cpu_baseline_sample():
+    """One column (1/8 of a step) of the same workload on all host threads: ~10-30 s of CPU work."""
+    O, pts, sc = _cpu_inputs(1)
+    cores = O.hw_threads()
+    O.msm(O.VESTA, sc[0][:4096], pts[:4096], threads=cores)     # warm the thread pool / page in
+    t = time.perf_counter()
+    O.msm(O.VESTA, sc[0], pts, threads=cores)
+    dt = time.perf_counter() - t
+    return {"value": N_POINTS / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 of {M_COLS} columns: one best_multiexp of 2^{K_LOG}+1 points, {cores} threads, oracle/liboracle.so "
+                      f"(C++ restatement of halo2_proofs 0.2.0; the Rust reference cannot be built here)", "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    O, pts, sc = _cpu_inputs(1)
+    cores = O.hw_threads()
+    for _ in range(max(args.warmup, 0)):
+        O.msm(O.VESTA, sc[0][: 1 << 16], pts[: 1 << 16], threads=cores)      # warm-up on a small slice
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.msm(O.VESTA, sc[0], pts, threads=cores)                             # bounded sample: 1 column per step
+    dt = time.perf_counter() - t0
+    value = args.steps * N_POINTS / dt / 1e6
+    sample = (f"each step = 1 of {M_COLS} columns (one best_multiexp of 2^{K_LOG}+1 points) on {cores} host threads; "
+              "CPU restatement of halo2_proofs 0.2.0 best_multiexp (oracle/oracle.cpp), not the Rust crate")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32x8 (255-bit Montgomery)", "data": "synthetic", "config": _config(),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------------------------------------
+# GPU arm
+# -------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this backend has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pkg = ge.load_package()
+    from tiny_ram_halo2_b200 import synthetic
+    from tiny_ram_halo2_b200._lib import ptr
+    ctx = pkg.Context(local_rank, pkg.VESTA)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    lib = ctx.lib
+    n, m = N_POINTS, M_COLS
+
+    # ---- inputs, resident in HBM --------------------------------------------------------------------------------
+    import ctypes
+    d_pts = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    synthetic.device_points(ctx, n, d_pts.data_ptr())
+    hb = ctypes.c_void_p()
+    t_load = time.perf_counter()
+    ctx.check(lib.trp_dev_bases_load(ctx.handle, d_pts.data_ptr(), n, ctypes.byref(hb)))
+    ctx.sync()
+    t_load = time.perf_counter() - t_load
+    desc = (ctypes.c_uint * 3)()
+    ctx.check(lib.trp_bases_describe(hb, desc))
+    c_bits, windows, precomp = int(desc[0]), int(desc[1]), bool(desc[2])
+    h_scalars = torch.from_numpy(synthetic.random_scalars(n, 20 + rank, m).view(np.int64)).pin_memory()
+    d_scalars = h_scalars.cuda()
+    d_out = torch.zeros((m, 12), dtype=torch.int64, device="cuda")
+    gathered = [torch.zeros_like(d_out) for _ in range(world)] if world > 1 else None
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.check(lib.trp_dev_msm_batch(ctx.handle, hb, d_scalars.data_ptr(), n, m, d_out.data_ptr()))
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather(gathered, d_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: K steps, CUDA events on the launching stream ---------------------------------------------------
+    ctx.prof_reset(); ctx.prof_enable(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    w1 = time.time()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = ctx.launches - launches0
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
+    prof = ctx.prof_get()
+    ctx.prof_enable(False)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * m * n * args.steps / (elapsed_ms * 1e-3) / 1e6
+
+    # ---- end-to-end: host (pinned) scalars in, host results out, through the reference-facing C-ABI call -------------------
+    h_out = torch.zeros((m, 12), dtype=torch.int64).pin_memory()
+    def e2e_step():
+        ctx.check(lib.trp_msm_batch(ctx.handle, hb, h_scalars.data_ptr(), n, m, h_out.data_ptr()))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * m * n * args.steps / e2e_s / 1e6
+    same = bool(torch.equal(h_out.cuda(), d_out))
+
+    # ---- roofline of the dominant kernel (bucket accumulation, level 1) -----------------------------------------------
+    if rank == 0:
+        peaks, peak_src = _peaks()
+        int_peak_gmacs = ctx.microbench(0, 512)          # independent IMAD.WIDE.U32: 32x32+64 MACs per second (G/s), measured now
+        acc_ms, acc_launches = prof["msm_accum_l1"]
+        per_launch_ms = acc_ms / max(acc_launches, 1)
+        macs_per_launch = n * windows * FMUL_PER_MIXED_ADD * MACS_PER_FMUL
+        achieved = macs_per_launch / (per_launch_ms * 1e-3) / 1e12
+        peak = int_peak_gmacs / 1e3
+        share = {k: round(v[0] / elapsed_ms, 4) for k, v in prof.items() if v[1]}
+        roofline = {"bound": "int32-pipe", "kernel": "msm_accum_l1_kernel", "achieved": achieved, "peak": peak, "unit": "TMAC/s",
+                    "frac": achieved / peak, "traffic": _traffic_from_profiles(),
+                    "peak_source": "IMAD.WIDE.U32 issue-rate microbenchmark run in this process (MEASURED_PEAKS.json has no integer peak)",
+                    "algorithmic_macs_per_launch": macs_per_launch, "launch_ms": per_launch_ms, "launches_timed": acc_launches,
+                    "model": f"n*W*{FMUL_PER_MIXED_ADD} Fmul x {MACS_PER_FMUL} MAC, W={windows}, c={c_bits}",
+                    "hbm": {"algorithmic_bytes_per_launch": n * windows * 68, "gbs": n * windows * 68 / (per_launch_ms * 1e-3) / 1e9,
+                            "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src},
+                    "phase_share_of_step": share}
+        cpu = cpu_baseline_sample() if world == 1 else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32x8 (255-bit Montgomery)", "data": "synthetic",
+                "config": _config({"window_bits": c_bits, "windows": windows, "precomputed_bases": precomp,
+                                   "bases_load_s": round(t_load, 3), "parallelism": f"column-sharded x{world}"}),
+                "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m * n * 32, "d2h_bytes_per_step": m * 96,
+                        "matches_device_path": same},
+                "gpu_launches": launches}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

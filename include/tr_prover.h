@@ -57,6 +57,12 @@ int trp_ctx_sync(trp_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t trp_ctx_launch_count(const trp_ctx* ctx);
 const char* trp_version(void);
+/* Per-phase device timing with CUDA events on the ctx stream (off by default; a few microseconds per span).
+ * phase: 0 msm hist+scan+scatter, 1 msm bucket accumulation level 1 (the dominant kernel), 2 msm upper
+ * reduction levels, 3 msm bucket reduce + final, 4 ntt pass kernels.  trp_prof_get synchronises the stream. */
+int trp_prof_enable(trp_ctx* ctx, int on);
+int trp_prof_reset(trp_ctx* ctx);
+int trp_prof_get(trp_ctx* ctx, int phase, double* total_ms, uint64_t* count);
 
 /* ---- MSM: halo2_proofs::arithmetic::best_multiexp(coeffs, bases) -> C::Curve ---------------------------
  * and poly::commitment::Params::{commit, commit_lagrange} which append blind * w and call it.
@@ -78,6 +84,10 @@ int trp_msm_batch(trp_ctx* ctx, const trp_bases* bases, const uint64_t* scalars 
                   size_t m, uint64_t* out_jacobian /* m x 12 */);
 int trp_dev_msm_batch(trp_ctx* ctx, const trp_bases* bases, const uint64_t* d_scalars, size_t n, size_t m,
                       uint64_t* d_out_jacobian /* m x 12, device */);
+
+/* Synthetic input generator for benchmarks and large tests: d_out[i] = P0 + i*D as affine points in DEVICE
+ * memory (an arithmetic progression of random multiples of the generator). */
+int trp_dev_points_progression(trp_ctx* ctx, const uint64_t p0[8], const uint64_t d[8], size_t n, uint64_t* d_out);
 
 /* ---- NTT: halo2_proofs::arithmetic::best_fft(a, omega, log_n) (field instance) -------------------------
  * In place, natural order in and out: a[k] <- sum_j a[j] * omega^(j k); batch contiguous vectors of 2^log_n. */

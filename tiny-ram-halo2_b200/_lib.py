@@ -18,9 +18,9 @@ _ERR_NAMES = {-1: "TRP_E_INVALID", -2: "TRP_E_CUDA", -3: "TRP_E_OOM", -4: "TRP_E
 # every symbol include/tr_prover.h declares (tests check that the library exports them all)
 EXPORTED_SYMBOLS = [
     "trp_ctx_create", "trp_ctx_destroy", "trp_last_error", "trp_ctx_set_stream", "trp_ctx_sync",
-    "trp_ctx_launch_count", "trp_version",
+    "trp_ctx_launch_count", "trp_version", "trp_prof_enable", "trp_prof_reset", "trp_prof_get",
     "trp_bases_load", "trp_dev_bases_load", "trp_bases_load_ex", "trp_bases_len", "trp_bases_describe", "trp_bases_free",
-    "trp_msm", "trp_msm_batch", "trp_dev_msm_batch",
+    "trp_msm", "trp_msm_batch", "trp_dev_msm_batch", "trp_dev_points_progression",
     "trp_ntt", "trp_dev_ntt",
     "trp_domain_create", "trp_domain_free", "trp_domain_extended_k", "trp_domain_constants",
     "trp_lagrange_to_coeff", "trp_dev_lagrange_to_coeff", "trp_coeff_to_lagrange",
@@ -68,6 +68,9 @@ def load_library():
     L.trp_ctx_sync.argtypes = [vp]
     L.trp_ctx_launch_count.argtypes = [vp]; L.trp_ctx_launch_count.restype = ctypes.c_uint64
     L.trp_version.restype = ctypes.c_char_p
+    L.trp_prof_enable.argtypes = [vp, i]
+    L.trp_prof_reset.argtypes = [vp]
+    L.trp_prof_get.argtypes = [vp, i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
     L.trp_bases_load.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
     L.trp_dev_bases_load.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
     L.trp_bases_load_ex.argtypes = [vp, vp, sz, i, ctypes.POINTER(vp)]
@@ -77,6 +80,7 @@ def load_library():
     L.trp_msm.argtypes = [vp, vp, vp, sz, vp]
     L.trp_msm_batch.argtypes = [vp, vp, vp, sz, sz, vp]
     L.trp_dev_msm_batch.argtypes = [vp, vp, vp, sz, sz, vp]
+    L.trp_dev_points_progression.argtypes = [vp, vp, vp, sz, vp]
     L.trp_ntt.argtypes = [vp, vp, sz, u, vp]
     L.trp_dev_ntt.argtypes = [vp, vp, sz, u, vp]
     L.trp_domain_create.argtypes = [vp, u, u, ctypes.POINTER(vp)]
@@ -150,6 +154,23 @@ class Context:
         v = ctypes.c_double()
         self.check(self.lib.trp_microbench(self.handle, kind, iters, ctypes.byref(v)))
         return v.value
+
+    PROF_PHASES = ("msm_sort", "msm_accum_l1", "msm_levels", "msm_reduce", "ntt_pass")
+
+    def prof_enable(self, on=True):
+        self.check(self.lib.trp_prof_enable(self.handle, int(on)))
+
+    def prof_reset(self):
+        self.check(self.lib.trp_prof_reset(self.handle))
+
+    def prof_get(self):
+        """{phase: (total_ms, spans)} measured with CUDA events on the ctx stream."""
+        out = {}
+        for idx, name in enumerate(self.PROF_PHASES):
+            ms, cnt = ctypes.c_double(), ctypes.c_uint64()
+            self.check(self.lib.trp_prof_get(self.handle, idx, ctypes.byref(ms), ctypes.byref(cnt)))
+            out[name] = (ms.value, int(cnt.value))
+        return out
 
     def close(self):
         if getattr(self, "handle", None):

@@ -156,6 +156,8 @@ void trp_ctx_destroy(trp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  trp_prof_collect(ctx);
+  for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   for (auto& t : ctx->twiddles) cudaFree(t.d_tab);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -181,6 +183,29 @@ int trp_ctx_sync(trp_ctx* ctx) {
 }
 
 uint64_t trp_ctx_launch_count(const trp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int trp_prof_enable(trp_ctx* ctx, int on) {
+  if (!ctx) return TRP_E_INVALID;
+  Locked l(ctx);
+  trp_prof_collect(ctx);
+  ctx->prof_on = on != 0;
+  return TRP_OK;
+}
+int trp_prof_reset(trp_ctx* ctx) {
+  if (!ctx) return TRP_E_INVALID;
+  Locked l(ctx);
+  trp_prof_collect(ctx);
+  for (int i = 0; i < PROF_NPHASES; ++i) { ctx->prof_ms[i] = 0; ctx->prof_count[i] = 0; }
+  return TRP_OK;
+}
+int trp_prof_get(trp_ctx* ctx, int phase, double* total_ms, uint64_t* count) {
+  if (!ctx || phase < 0 || phase >= PROF_NPHASES) return TRP_E_INVALID;
+  Locked l(ctx);
+  trp_prof_collect(ctx);
+  if (total_ms) *total_ms = ctx->prof_ms[phase];
+  if (count) *count = ctx->prof_count[phase];
+  return TRP_OK;
+}
 
 // ---- MSM ---------------------------------------------------------------------------------------------------
 int trp_bases_load(trp_ctx* ctx, const uint64_t* affine_xy, size_t n, trp_bases** out) {
@@ -255,6 +280,14 @@ int trp_msm_batch(trp_ctx* ctx, const trp_bases* bases, const uint64_t* scalars,
 
 int trp_msm(trp_ctx* ctx, const trp_bases* bases, const uint64_t* scalars, size_t n, uint64_t out_jacobian[12]) {
   return trp_msm_batch(ctx, bases, scalars, n, 1, out_jacobian);
+}
+
+// synthetic bases: out[i] = P0 + i*D (affine), written to DEVICE memory
+int trp_dev_points_progression(trp_ctx* ctx, const uint64_t p0[8], const uint64_t d[8], size_t n, uint64_t* d_out) {
+  if (!ctx) return TRP_E_INVALID;
+  Locked l(ctx);
+  if (!p0 || !d || (n && !d_out)) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
+  return trp_points_progression_impl(ctx, p0, d, n, d_out);
 }
 
 // ---- NTT ---------------------------------------------------------------------------------------------------

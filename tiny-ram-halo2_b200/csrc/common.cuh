@@ -16,7 +16,16 @@ struct TwiddleTable {
   void* d_tab;
 };
 
+// optional per-phase device timing (CUDA events on the ctx stream); used by bench.py for the live roofline number
+enum ProfPhase { PROF_MSM_SORT = 0, PROF_MSM_ACCUM_L1, PROF_MSM_LEVELS, PROF_MSM_REDUCE, PROF_NTT_PASS, PROF_NPHASES };
+struct ProfSpan { int phase; cudaEvent_t e0, e1; };
+
 struct trp_ctx {
+  bool prof_on = false;
+  std::vector<ProfSpan> prof_spans;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[PROF_NPHASES] = {0, 0, 0, 0, 0};
+  uint64_t prof_count[PROF_NPHASES] = {0, 0, 0, 0, 0};
   int device = 0;
   int curve = 0;
   cudaStream_t own_stream = nullptr;
@@ -70,6 +79,33 @@ struct trp_bases {
     TRP_CUDA(ctx, cudaGetLastError());         \
   } while (0)
 
+struct ProfScope {
+  trp_ctx* ctx; int idx;
+  ProfScope(trp_ctx* c, int phase) : ctx(c), idx(-1) {
+    if (!c->prof_on) return;
+    ProfSpan s; s.phase = phase;
+    for (cudaEvent_t* e : {&s.e0, &s.e1}) {
+      if (!c->prof_pool.empty()) { *e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+      else cudaEventCreate(e);
+    }
+    cudaEventRecord(s.e0, c->stream);
+    c->prof_spans.push_back(s);
+    idx = (int)c->prof_spans.size() - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(ctx->prof_spans[idx].e1, ctx->stream); }
+};
+// fold finished spans into the per-phase totals (synchronises the stream)
+inline void trp_prof_collect(trp_ctx* ctx) {
+  if (ctx->prof_spans.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& s : ctx->prof_spans) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s.e0, s.e1) == cudaSuccess) { ctx->prof_ms[s.phase] += ms; ctx->prof_count[s.phase]++; }
+    ctx->prof_pool.push_back(s.e0); ctx->prof_pool.push_back(s.e1);
+  }
+  ctx->prof_spans.clear();
+}
+
 // grow-only scratch arena
 inline int trp_ws_reserve(trp_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->ws_bytes) return TRP_OK;
@@ -107,6 +143,7 @@ size_t trp_ntt_passes(unsigned log_n);
 int trp_msm_impl(trp_ctx* ctx, const trp_bases* bases, const void* d_scalars, size_t n, size_t m, void* d_out_jac,
                  void* ws, size_t ws_bytes);
 size_t trp_msm_ws_bytes(const trp_bases* bases, size_t n);
+int trp_points_progression_impl(trp_ctx* ctx, const uint64_t* p0, const uint64_t* d, size_t n, void* d_out);
 int trp_bases_create(trp_ctx* ctx, const void* src, bool src_on_device, size_t n, int flags, trp_bases** out);
 void trp_bases_destroy(trp_bases* b);
 int trp_bases_info(const trp_bases* b, unsigned* c, unsigned* W, unsigned* precomp);

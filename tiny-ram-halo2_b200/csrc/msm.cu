@@ -332,6 +332,24 @@ __global__ void msm_final_kernel(const uint4* set_sums, MsmGeom g, uint4* out_ja
   fe_store(out_jac, X); fe_store(out_jac + 2, Y); fe_store(out_jac + 4, Z);
 }
 
+// batch normalisation of the m results: (X, Y, Z) -> (X/Z^2, Y/Z^3, 1), identity -> (0, 0, 0).  Makes the output
+// canonical (the accumulation order inside buckets is not deterministic, the group element is).
+template <class BPR>
+__global__ void msm_normalize_kernel(uint4* out_jac, size_t m) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  uint4* o = out_jac + 6 * k;
+  Fe<BPR> X = fe_load<BPR>(o), Y = fe_load<BPR>(o + 2), Z = fe_load<BPR>(o + 4);
+  if (fe_is_zero(Z)) {
+    for (int q = 0; q < 6; ++q) o[q] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  Fe<BPR> zi = fe_inv(Z), zi2 = fe_sqr(zi);
+  fe_store(o, fe_mul(X, zi2));
+  fe_store(o + 2, fe_mul(Y, fe_mul(zi2, zi)));
+  fe_store(o + 4, fe_one<BPR>());
+}
+
 template <class BPR>
 __global__ void msm_identity_kernel(uint4* out_jac) {
   if (threadIdx.x < 6) out_jac[threadIdx.x] = make_uint4(0, 0, 0, 0);
@@ -368,6 +386,37 @@ __global__ void __launch_bounds__(128) msm_precompute_kernel(uint4* table, size_
     inv = fe_mul(inv, fe_mul(e.zz, e.zzz));
     fe_store(slot, fe_mul(e.x, fe_mul(einv, e.zzz)));       // X / ZZ
     fe_store(slot + 2, fe_mul(e.y, fe_mul(einv, e.zz)));    // Y / ZZZ
+  }
+}
+
+// ---- synthetic input generator: out[i] = P0 + i * D (affine), used by bench.py / tests to make bases on device -------
+constexpr unsigned GEN_CH = 16;
+template <class BPR>
+__global__ void __launch_bounds__(128) points_progression_kernel(Affine<BPR> p0, Affine<BPR> d, size_t n, uint4* out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t start = t * GEN_CH;
+  if (start >= n) return;
+  XYZZ<BPR> cur = xyzz_mul_small(xyzz_from_affine(d), (unsigned)start);
+  xyzz_add_mixed(cur, p0);
+  XYZZ<BPR> chain[GEN_CH];
+  Fe<BPR> pre[GEN_CH];
+  Fe<BPR> prod = fe_one<BPR>();
+  unsigned cnt = (unsigned)(n - start < GEN_CH ? n - start : GEN_CH);
+  for (unsigned k = 0; k < cnt; ++k) {
+    chain[k] = cur;
+    pre[k] = prod;
+    if (!xyzz_is_identity(cur)) prod = fe_mul(prod, fe_mul(cur.zz, cur.zzz));
+    xyzz_add_mixed(cur, d);
+  }
+  Fe<BPR> inv = fe_inv(prod);
+  for (int k = (int)cnt - 1; k >= 0; --k) {
+    uint4* slot = out + 4 * (start + k);
+    const XYZZ<BPR> e = chain[k];
+    if (xyzz_is_identity(e)) { for (int q = 0; q < 4; ++q) slot[q] = make_uint4(0, 0, 0, 0); continue; }
+    Fe<BPR> einv = fe_mul(inv, pre[k]);
+    inv = fe_mul(inv, fe_mul(e.zz, e.zzz));
+    fe_store(slot, fe_mul(e.x, fe_mul(einv, e.zzz)));
+    fe_store(slot + 2, fe_mul(e.y, fe_mul(einv, e.zz)));
   }
 }
 
@@ -434,34 +483,44 @@ int msm_one(trp_ctx* ctx, const trp_bases_impl* bs, const uint4* d_scalars, size
   uint4* set_sums = cur.take<uint4>(8 * (size_t)g.nsets);
   if (cur.off > ws_cap) TRP_FAIL(ctx, TRP_E_INVALID, "internal: MSM workspace underestimated (%zu > %zu)", cur.off, ws_cap);
 
-  TRP_CUDA(ctx, cudaMemsetAsync(counts, 0, (g.nb + 1) * sizeof(uint32_t), ctx->stream));
-  unsigned sblocks = (unsigned)((n + 127) / 128);
-  msm_hist_kernel<SPR><<<sblocks, 128, 0, ctx->stream>>>(d_scalars, n, g, counts);
-  TRP_LAUNCHED(ctx);
-  TRP_TRY(run_scan(ctx, counts, offsets, cursor, block_sums, total, g.nb, 0, 1));
-  msm_scatter_kernel<SPR><<<sblocks, 128, 0, ctx->stream>>>(d_scalars, n, g, cursor, entries);
-  TRP_LAUNCHED(ctx);
-
-  // level 1
-  TRP_TRY(run_scan(ctx, offsets, task_off[0], nullptr, block_sums, total, g.nb, 1, L1));
-  msm_accum_l1_kernel<BPR><<<(unsigned)((level_tasks[0] + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(
-      entries, offsets, task_off[0], g.nb, (const uint4*)bs->pub.d_xy, part[0]);
-  TRP_LAUNCHED(ctx);
-  int curp = 0;
-  for (size_t lv = 1; lv < level_tasks.size(); ++lv) {
-    TRP_TRY(run_scan(ctx, task_off[curp], task_off[curp ^ 1], nullptr, block_sums, total, g.nb, 1, L2));
-    msm_accum_ln_kernel<BPR><<<(unsigned)((level_tasks[lv] + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(
-        part[curp], task_off[curp], task_off[curp ^ 1], g.nb, part[curp ^ 1]);
+  {
+    ProfScope ps(ctx, PROF_MSM_SORT);
+    TRP_CUDA(ctx, cudaMemsetAsync(counts, 0, (g.nb + 1) * sizeof(uint32_t), ctx->stream));
+    unsigned sblocks = (unsigned)((n + 127) / 128);
+    msm_hist_kernel<SPR><<<sblocks, 128, 0, ctx->stream>>>(d_scalars, n, g, counts);
     TRP_LAUNCHED(ctx);
-    curp ^= 1;
+    TRP_TRY(run_scan(ctx, counts, offsets, cursor, block_sums, total, g.nb, 0, 1));
+    msm_scatter_kernel<SPR><<<sblocks, 128, 0, ctx->stream>>>(d_scalars, n, g, cursor, entries);
+    TRP_LAUNCHED(ctx);
+    TRP_TRY(run_scan(ctx, offsets, task_off[0], nullptr, block_sums, total, g.nb, 1, L1));
   }
-  unsigned nchunks = g.nsets * chunks_per_set;
-  msm_reduce_chunks_kernel<BPR><<<(nchunks + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, ctx->stream>>>(part[curp], task_off[curp], g, chunk_out);
-  TRP_LAUNCHED(ctx);
-  msm_reduce_sets_kernel<BPR><<<g.nsets, 256, 0, ctx->stream>>>(chunk_out, chunks_per_set, set_sums);
-  TRP_LAUNCHED(ctx);
-  msm_final_kernel<BPR><<<1, 32, 0, ctx->stream>>>(set_sums, g, d_out);
-  TRP_LAUNCHED(ctx);
+  {
+    ProfScope ps(ctx, PROF_MSM_ACCUM_L1);
+    msm_accum_l1_kernel<BPR><<<(unsigned)((level_tasks[0] + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(
+        entries, offsets, task_off[0], g.nb, (const uint4*)bs->pub.d_xy, part[0]);
+    TRP_LAUNCHED(ctx);
+  }
+  int curp = 0;
+  {
+    ProfScope ps(ctx, PROF_MSM_LEVELS);
+    for (size_t lv = 1; lv < level_tasks.size(); ++lv) {
+      TRP_TRY(run_scan(ctx, task_off[curp], task_off[curp ^ 1], nullptr, block_sums, total, g.nb, 1, L2));
+      msm_accum_ln_kernel<BPR><<<(unsigned)((level_tasks[lv] + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(
+          part[curp], task_off[curp], task_off[curp ^ 1], g.nb, part[curp ^ 1]);
+      TRP_LAUNCHED(ctx);
+      curp ^= 1;
+    }
+  }
+  {
+    ProfScope ps(ctx, PROF_MSM_REDUCE);
+    unsigned nchunks = g.nsets * chunks_per_set;
+    msm_reduce_chunks_kernel<BPR><<<(nchunks + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, ctx->stream>>>(part[curp], task_off[curp], g, chunk_out);
+    TRP_LAUNCHED(ctx);
+    msm_reduce_sets_kernel<BPR><<<g.nsets, 256, 0, ctx->stream>>>(chunk_out, chunks_per_set, set_sums);
+    TRP_LAUNCHED(ctx);
+    msm_final_kernel<BPR><<<1, 32, 0, ctx->stream>>>(set_sums, g, d_out);
+    TRP_LAUNCHED(ctx);
+  }
   return TRP_OK;
 }
 
@@ -535,6 +594,26 @@ int trp_bases_info(const trp_bases* b, unsigned* c, unsigned* W, unsigned* preco
   return TRP_OK;
 }
 
+int trp_points_progression_impl(trp_ctx* ctx, const uint64_t* p0, const uint64_t* d, size_t n, void* d_out) {
+  if (n == 0) return TRP_OK;
+  unsigned threads = (unsigned)((n + GEN_CH - 1) / GEN_CH);
+  unsigned blocks = (threads + 127) / 128;
+  auto launch = [&](auto tag) {
+    typedef decltype(tag) BPR;
+    Affine<BPR> a, b;
+    for (int i = 0; i < 4; ++i) {
+      a.x.v[2 * i] = (uint32_t)p0[i]; a.x.v[2 * i + 1] = (uint32_t)(p0[i] >> 32);
+      a.y.v[2 * i] = (uint32_t)p0[4 + i]; a.y.v[2 * i + 1] = (uint32_t)(p0[4 + i] >> 32);
+      b.x.v[2 * i] = (uint32_t)d[i]; b.x.v[2 * i + 1] = (uint32_t)(d[i] >> 32);
+      b.y.v[2 * i] = (uint32_t)d[4 + i]; b.y.v[2 * i + 1] = (uint32_t)(d[4 + i] >> 32);
+    }
+    points_progression_kernel<BPR><<<blocks, 128, 0, ctx->stream>>>(a, b, n, (uint4*)d_out);
+  };
+  if (base_field_of(ctx->curve) == 0) launch(FpParams()); else launch(FqParams());
+  TRP_LAUNCHED(ctx);
+  return TRP_OK;
+}
+
 size_t trp_msm_ws_bytes(const trp_bases* bases, size_t n) {
   return msm_ws_bytes(reinterpret_cast<const trp_bases_impl*>(bases)->g, n);
 }
@@ -551,6 +630,12 @@ int trp_msm_impl(trp_ctx* ctx, const trp_bases* bases, const void* d_scalars, si
     if (ctx->curve == TRP_CURVE_PALLAS) rc = msm_one<FpParams, FqParams>(ctx, bs, sc, n, out, (char*)ws, ws_bytes);
     else rc = msm_one<FqParams, FpParams>(ctx, bs, sc, n, out, (char*)ws, ws_bytes);
     if (rc != TRP_OK) return rc;
+  }
+  if (m) {
+    unsigned blocks = (unsigned)((m + 31) / 32);
+    if (ctx->curve == TRP_CURVE_PALLAS) msm_normalize_kernel<FpParams><<<blocks, 32, 0, ctx->stream>>>((uint4*)d_out_jac, m);
+    else msm_normalize_kernel<FqParams><<<blocks, 32, 0, ctx->stream>>>((uint4*)d_out_jac, m);
+    TRP_LAUNCHED(ctx);
   }
   return TRP_OK;
 }

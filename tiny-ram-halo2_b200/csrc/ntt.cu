@@ -235,8 +235,11 @@ int ntt_run(trp_ctx* ctx, const void* d_src, void* d_dst, size_t batch, unsigned
     size_t smem = (size_t)nelem * 32;
     if (smem > 48 * 1024)
       TRP_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32u << TILE_LOG_MAX)));
-    ntt_pass_kernel<PR><<<grid, threads, smem, ctx->stream>>>(p);
-    TRP_LAUNCHED(ctx);
+    {
+      ProfScope ps(ctx, PROF_NTT_PASS);
+      ntt_pass_kernel<PR><<<grid, threads, smem, ctx->stream>>>(p);
+      TRP_LAUNCHED(ctx);
+    }
   }
   return TRP_OK;
 }
