@@ -275,6 +275,8 @@ def run_gpu(args):
     e2e_s = float(t.item())
     e2e_value = world * m * n * args.steps / e2e_s / 1e6
     same = bool(torch.equal(h_out.cuda(), d_out))
+    if not same and os.environ.get("TRP_BENCH_DEBUG"):
+        print("h_out", h_out.numpy().view(np.uint64)[:2], "d_out", d_out.cpu().numpy().view(np.uint64)[:2], file=sys.stderr)
 
     # ---- roofline of the dominant kernel (bucket accumulation, level 1) -----------------------------------------------
     if rank == 0:

@@ -59,7 +59,8 @@ uint64_t trp_ctx_launch_count(const trp_ctx* ctx);
 const char* trp_version(void);
 /* Per-phase device timing with CUDA events on the ctx stream (off by default; a few microseconds per span).
  * phase: 0 msm hist+scan+scatter, 1 msm bucket accumulation level 1 (the dominant kernel), 2 msm upper
- * reduction levels, 3 msm bucket reduce + final, 4 ntt pass kernels.  trp_prof_get synchronises the stream. */
+ * reduction levels, 3 msm bucket reduce + final, 4 ntt pass kernels, 5 quotient VM kernel.
+ * trp_prof_get synchronises the stream. */
 int trp_prof_enable(trp_ctx* ctx, int on);
 int trp_prof_reset(trp_ctx* ctx);
 int trp_prof_get(trp_ctx* ctx, int phase, double* total_ms, uint64_t* count);
@@ -114,6 +115,33 @@ int trp_dev_coeff_to_extended(trp_domain* d, const uint64_t* d_coeff, uint64_t* 
 int trp_extended_to_coeff(trp_domain* d, uint64_t* ext /* 2^ext_k */, uint64_t* out_coeff /* n*(j-1) */,
                           int divide_by_vanishing);
 int trp_dev_extended_to_coeff(trp_domain* d, uint64_t* d_ext, uint64_t* d_out_coeff, int divide_by_vanishing);
+
+/* ---- quotient evaluation: halo2_proofs::poly::Evaluator::evaluate(&ast, domain) (poly/evaluator.rs) as driven by
+ * plonk::vanishing::Argument::construct in create_proof: h_ext[r] = sum_j y^j expr_j(row r) over the extended domain.
+ * The caller lowers its poly::Ast into a straight-line program over n_regs virtual registers (field elements);
+ * an instruction is 4 x uint32 { op, dst, a, b }:
+ *    0 LOAD   dst = cols[a][(row + (int32)b * step) mod rows]      (Ast::Poly(leaf).with_rotation(b))
+ *    1 CONST  dst = consts[a]                                       (Ast::ConstantTerm)
+ *    2 ADD  3 SUB  4 MUL   dst = r[a] op r[b]                       (Ast::Add / Ast::Mul)
+ *    5 NEG  6 SQR  7 DBL   dst = op r[a]
+ *    8 COSETX dst = zeta * extended_omega^row                       (Ast::LinearTerm(1): the value of X at this row)
+ *    9 STORE  out[row] = r[a]
+ *   10 MULC 11 ADDC 12 SUBC  dst = r[a] op consts[b]                (Ast::Scale and friends)
+ * coset = -1: rows = the whole extended domain; columns hold 2^extended_k values, step = 2^(extended_k - k).
+ * coset = j >= 0: rows = the j-th size-n coset (zeta * extended_omega^j * <omega>); columns hold the n values
+ *   produced by trp_dev_coeff_to_coset(.., j), step = 1, and results go to d_out[row * 2^(extended_k-k) + j], so
+ *   2^(extended_k-k) calls fill h_ext without materialising any extended column.
+ * Malformed programs are rejected with TRP_E_INVALID before anything is launched. */
+int trp_dev_quotient_eval(trp_domain* d, const uint32_t* program /* host */, size_t n_instr, unsigned n_regs,
+                          const uint64_t* consts /* host, n_consts x 4 */, size_t n_consts,
+                          const uint64_t* const* d_cols /* host array of n_cols DEVICE pointers */, size_t n_cols,
+                          int coset, uint64_t* d_out /* device, 2^extended_k x 4 */);
+int trp_quotient_eval(trp_domain* d, const uint32_t* program, size_t n_instr, unsigned n_regs, const uint64_t* consts,
+                      size_t n_consts, const uint64_t* const* cols /* n_cols HOST pointers, 2^extended_k x 4 each */,
+                      size_t n_cols, uint64_t* out_ext /* host, 2^extended_k x 4 */);
+/* out[i] = p(zeta * extended_omega^(j + i * 2^(extended_k-k))) for coefficient-form columns p (n each): row j, j + 2^(..),
+ * ... of coeff_to_extended, computed with ONE size-n NTT per column. */
+int trp_dev_coeff_to_coset(trp_domain* d, const uint64_t* d_coeff, uint64_t* d_out, size_t batch, unsigned coset);
 
 /* ---- glue / debug: elementwise field kernels over the ctx's scalar (field=0) or base (field=1) field ----
  * op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 sqr(a).  Host pointers.  Used by parity tests of K1 and by K7 callers. */

@@ -383,3 +383,81 @@ def eval_polynomial(F: Field, coeffs, x):
     for c in reversed(coeffs):
         acc = (acc * x + c) % F.p
     return acc
+
+
+# ---------------------------------------------------------------------------------------------
+# halo2_proofs::poly::Evaluator::evaluate  (poly/evaluator.rs, halo2 0.2.0) -- restated from memory, UNVERIFIED:
+# the dependency's source is not under /root/reference.  Walks an Ast (any objects whose CLASS NAMES are the
+# halo2 node names Poly / Add / Mul / Scale / DistributePowers / LinearTerm / ConstantTerm) and returns the
+# 2^extended_k values, one per point zeta * extended_omega^i of the extended coset.
+#   Poly(index, rotation)      -> polys[index] rotated by rotation * 2^(extended_k - k)   (rotate_extended)
+#   Add / Mul                  -> pointwise
+#   Scale(a, s)                -> s * a
+#   DistributePowers(ts, base) -> fold(0, |acc, t| acc * base + t)
+#   LinearTerm(s)              -> s * zeta * extended_omega^i
+#   ConstantTerm(s)            -> s
+# ---------------------------------------------------------------------------------------------
+def evaluate_ast(dom: EvaluationDomain, ast, polys):
+    p = dom.F.p
+    rows = dom.extended_len()
+    kind = type(ast).__name__
+    if kind == "Poly":
+        return dom.rotate_extended(list(polys[ast.index]), ast.rotation)
+    if kind == "Add":
+        a, b = evaluate_ast(dom, ast.a, polys), evaluate_ast(dom, ast.b, polys)
+        return [(x + y) % p for x, y in zip(a, b)]
+    if kind == "Mul":
+        a, b = evaluate_ast(dom, ast.a, polys), evaluate_ast(dom, ast.b, polys)
+        return [x * y % p for x, y in zip(a, b)]
+    if kind == "Scale":
+        s = ast.scalar % p
+        return [x * s % p for x in evaluate_ast(dom, ast.a, polys)]
+    if kind == "DistributePowers":
+        base = evaluate_ast(dom, ast.base, polys)
+        acc = [0] * rows
+        for t in ast.terms:
+            tv = evaluate_ast(dom, t, polys)
+            acc = [(x * b + y) % p for x, b, y in zip(acc, base, tv)]
+        return acc
+    if kind == "LinearTerm":
+        out, cur = [], dom.g_coset
+        for _ in range(rows):
+            out.append(cur * ast.scalar % p)
+            cur = cur * dom.extended_omega % p
+        return out
+    if kind == "ConstantTerm":
+        return [ast.scalar % p] * rows
+    raise TypeError(f"unknown Ast node {kind}")
+
+
+def run_program(dom: EvaluationDomain, code, consts, polys, coset=-1):
+    """Reference interpreter of the straight-line program format of include/tr_prover.h (trp_dev_quotient_eval),
+    used by the CPU tests to check the host-side Ast compiler without a GPU.  coset = -1: whole extended domain;
+    coset = j: rows of the j-th size-n coset, polys given on that coset, result returned for that coset only."""
+    p = dom.F.p
+    period = 1 << (dom.extended_k - dom.k)
+    rows = dom.extended_len() if coset < 0 else dom.n
+    step = period if coset < 0 else 1
+    out = [None] * rows
+    for row in range(rows):
+        g = row if coset < 0 else row * period + coset
+        regs = {}
+        for op, dst, a, b in code:
+            op, dst, a, b = int(op), int(dst), int(a), int(b)
+            if op == 0:
+                rot = b - (1 << 32) if b >= (1 << 31) else b
+                regs[dst] = polys[a][(row + rot * step) % rows]
+            elif op == 1: regs[dst] = consts[a]
+            elif op == 2: regs[dst] = (regs[a] + regs[b]) % p
+            elif op == 3: regs[dst] = (regs[a] - regs[b]) % p
+            elif op == 4: regs[dst] = regs[a] * regs[b] % p
+            elif op == 5: regs[dst] = -regs[a] % p
+            elif op == 6: regs[dst] = regs[a] * regs[a] % p
+            elif op == 7: regs[dst] = 2 * regs[a] % p
+            elif op == 8: regs[dst] = dom.g_coset * pow(dom.extended_omega, g, p) % p
+            elif op == 9: out[row] = regs[a]
+            elif op == 10: regs[dst] = regs[a] * consts[b] % p
+            elif op == 11: regs[dst] = (regs[a] + consts[b]) % p
+            elif op == 12: regs[dst] = (regs[a] - consts[b]) % p
+            else: raise ValueError(f"bad opcode {op}")
+    return out

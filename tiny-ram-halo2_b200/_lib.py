@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "trp_domain_create", "trp_domain_free", "trp_domain_extended_k", "trp_domain_constants",
     "trp_lagrange_to_coeff", "trp_dev_lagrange_to_coeff", "trp_coeff_to_lagrange",
     "trp_coeff_to_extended", "trp_dev_coeff_to_extended", "trp_extended_to_coeff", "trp_dev_extended_to_coeff",
+    "trp_dev_quotient_eval", "trp_quotient_eval", "trp_dev_coeff_to_coset",
     "trp_field_op", "trp_microbench",
 ]
 
@@ -94,6 +95,9 @@ def load_library():
     L.trp_dev_coeff_to_extended.argtypes = [vp, vp, vp, sz]
     L.trp_extended_to_coeff.argtypes = [vp, vp, vp, i]
     L.trp_dev_extended_to_coeff.argtypes = [vp, vp, vp, i]
+    L.trp_dev_quotient_eval.argtypes = [vp, vp, sz, u, vp, sz, vp, sz, i, vp]
+    L.trp_quotient_eval.argtypes = [vp, vp, sz, u, vp, sz, vp, sz, vp]
+    L.trp_dev_coeff_to_coset.argtypes = [vp, vp, vp, sz, u]
     L.trp_field_op.argtypes = [vp, i, i, vp, vp, vp, sz]
     L.trp_microbench.argtypes = [vp, i, i, ctypes.POINTER(ctypes.c_double)]
     _lib = L
@@ -155,7 +159,7 @@ class Context:
         self.check(self.lib.trp_microbench(self.handle, kind, iters, ctypes.byref(v)))
         return v.value
 
-    PROF_PHASES = ("msm_sort", "msm_accum_l1", "msm_levels", "msm_reduce", "ntt_pass")
+    PROF_PHASES = ("msm_sort", "msm_accum_l1", "msm_levels", "msm_reduce", "ntt_pass", "quotient_vm")
 
     def prof_enable(self, on=True):
         self.check(self.lib.trp_prof_enable(self.handle, int(on)))

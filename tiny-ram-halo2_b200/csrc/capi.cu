@@ -31,20 +31,6 @@ struct Locked {
 
 }  // namespace
 
-struct trp_domain {
-  trp_ctx* ctx;
-  int field;
-  unsigned k, j, ext_k;
-  uint64_t omega[4], omega_inv[4], ext_omega[4], ext_omega_inv[4], g_coset[4], g_coset_inv[4];
-  // device tables (Montgomery field elements)
-  void* d_tabs;        // one allocation holding the tables below
-  void* d_zeta_in;     // [1, zeta, zeta^2]
-  void* d_l2c_post;    // [2^-k]
-  void* d_e2c_post;    // 2^-ext_k * [1, zeta^-1, zeta^-2]
-  void* d_tinv;        // 1 / (X^n - 1) on the coset, period 2^(ext_k - k)
-  unsigned t_period;
-};
-
 namespace {
 
 template <class PR>
@@ -77,6 +63,7 @@ int domain_build(trp_ctx* ctx, trp_domain* d, const uint64_t* root_canon, const 
   Fe<PR> eninv = fe_inv(fe_to_mont(two_ek));
   tabs.push_back(eninv); tabs.push_back(fe_mul(eninv, zeta2)); tabs.push_back(fe_mul(eninv, zeta));   // e2c_post [4..7)
   d->t_period = 1u << (ext_k - k);
+  { Fe<PR> g = zeta; for (unsigned i = 0; i < d->t_period; ++i) { fe_to_u64x4(g, d->coset_gen[i]); g = fe_mul(g, ext_omega); } }
   for (unsigned i = 0; i < d->t_period; ++i) { tabs.push_back(fe_inv(fe_sub(cur, one))); cur = fe_mul(cur, step); }   // tinv [7..)
   TRP_CUDA(ctx, cudaMalloc(&d->d_tabs, tabs.size() * 32));
   TRP_CUDA(ctx, cudaMemcpy(d->d_tabs, tabs.data(), tabs.size() * 32, cudaMemcpyHostToDevice));

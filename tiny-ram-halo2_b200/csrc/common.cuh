@@ -17,15 +17,15 @@ struct TwiddleTable {
 };
 
 // optional per-phase device timing (CUDA events on the ctx stream); used by bench.py for the live roofline number
-enum ProfPhase { PROF_MSM_SORT = 0, PROF_MSM_ACCUM_L1, PROF_MSM_LEVELS, PROF_MSM_REDUCE, PROF_NTT_PASS, PROF_NPHASES };
+enum ProfPhase { PROF_MSM_SORT = 0, PROF_MSM_ACCUM_L1, PROF_MSM_LEVELS, PROF_MSM_REDUCE, PROF_NTT_PASS, PROF_QUOTIENT, PROF_NPHASES };
 struct ProfSpan { int phase; cudaEvent_t e0, e1; };
 
 struct trp_ctx {
   bool prof_on = false;
   std::vector<ProfSpan> prof_spans;
   std::vector<cudaEvent_t> prof_pool;
-  double prof_ms[PROF_NPHASES] = {0, 0, 0, 0, 0};
-  uint64_t prof_count[PROF_NPHASES] = {0, 0, 0, 0, 0};
+  double prof_ms[PROF_NPHASES] = {};
+  uint64_t prof_count[PROF_NPHASES] = {};
   int device = 0;
   int curve = 0;
   cudaStream_t own_stream = nullptr;
@@ -47,6 +47,21 @@ struct trp_bases {
   trp_ctx* ctx;
   size_t n;
   void* d_xy;   // n x 64 B affine
+};
+
+struct trp_domain {
+  trp_ctx* ctx;
+  int field;
+  unsigned k, j, ext_k;
+  uint64_t omega[4], omega_inv[4], ext_omega[4], ext_omega_inv[4], g_coset[4], g_coset_inv[4];
+  // device tables (Montgomery field elements)
+  void* d_tabs;        // one allocation holding the tables below
+  void* d_zeta_in;     // [1, zeta, zeta^2]
+  void* d_l2c_post;    // [2^-k]
+  void* d_e2c_post;    // 2^-ext_k * [1, zeta^-1, zeta^-2]
+  void* d_tinv;        // 1 / (X^n - 1) on the coset, period 2^(ext_k - k)
+  unsigned t_period;
+  uint64_t coset_gen[64][4];   // zeta * ext_omega^j, j < 2^(ext_k - k) (generator of the j-th size-n coset)
 };
 
 #define TRP_FAIL(ctx, code, ...)                              \
@@ -140,6 +155,7 @@ int trp_ntt_impl(trp_ctx* ctx, int field, const void* d_src, void* d_dst, size_t
                  const void* d_pre, unsigned pre_period, const void* d_post, unsigned post_period, unsigned n_dst,
                  void* d_tmp /* batch*2^log_n elements, needed iff src==dst and passes>1 */);
 size_t trp_ntt_passes(unsigned log_n);
+int trp_get_powers(trp_ctx* ctx, int field, unsigned log_n, const uint64_t g[4], const void** out);
 int trp_msm_impl(trp_ctx* ctx, const trp_bases* bases, const void* d_scalars, size_t n, size_t m, void* d_out_jac,
                  void* ws, size_t ws_bytes);
 size_t trp_msm_ws_bytes(const trp_bases* bases, size_t n);

@@ -246,6 +246,14 @@ int ntt_run(trp_ctx* ctx, const void* d_src, void* d_dst, size_t batch, unsigned
 
 }  // namespace
 
+// tab[i] = g^i for i < 2^(log_n-1), cached per (log_n, g) in the ctx (the NTT twiddle tables are the g = omega case)
+int trp_get_powers(trp_ctx* ctx, int field, unsigned log_n, const uint64_t g[4], const void** out) {
+  const uint4* t = nullptr;
+  int rc = field == 0 ? get_twiddles<FpParams>(ctx, log_n, g, &t) : get_twiddles<FqParams>(ctx, log_n, g, &t);
+  *out = t;
+  return rc;
+}
+
 size_t trp_ntt_passes(unsigned log_n) { return log_n == 0 ? 1 : (log_n + S_MAX - 1) / S_MAX; }
 
 int trp_ntt_impl(trp_ctx* ctx, int field, const void* d_src, void* d_dst, size_t batch, unsigned log_n,

@@ -1,0 +1,254 @@
+// K6: extended-domain evaluation of the quotient polynomial's numerator,  h_ext[r] = sum_j y^j * expr_j(row r).
+//
+// Replaces halo2_proofs::poly::Evaluator::evaluate(&ast, domain) (poly/evaluator.rs, halo2_proofs 0.2.0 @ a95945254dcc,
+// Cargo.lock:619-621) as driven by plonk::vanishing::Argument::construct inside create_proof
+// (/root/reference/src/test_utils.rs:41,96).  The CPU routine interprets an `Ast<ExtendedLagrangeCoeff>` chunk by chunk
+// on rayon threads; the expression set comes from the reference's gates and lookups (e.g.
+// /root/reference/src/circuits/sprod.rs:65-90).
+//
+// Here the host lowers the AST once into a straight-line program over a small virtual register file
+// (tiny-ram-halo2_b200/poly.py) and ONE kernel runs it for every row: a thread owns a row, the virtual registers
+// live in shared memory as two 16-byte planes ([reg][thread], conflict-free 128-bit accesses), column values are
+// read with coalesced 32-byte loads at (row + rotation * step) mod rows.  The same kernel serves two data layouts:
+//   * whole extended domain: columns hold 2^ext_k values, rotation step 2^(ext_k - k)            (what halo2 does)
+//   * one size-n coset of it: columns hold n values produced by trp_dev_coeff_to_coset, step 1; the result is
+//     written interleaved (row * 2^(ext_k-k) + coset) so that 2^(ext_k-k) calls assemble h_ext without ever
+//     materialising the extended columns (700 columns x 256 MiB at k = 20 would not fit).
+#include "common.cuh"
+
+#include <cstring>
+
+using namespace ff;
+
+namespace {
+
+enum QOp : uint32_t {
+  Q_LOAD = 0,    // dst = cols[a][(row + (int)b * step) mod rows]
+  Q_CONST = 1,   // dst = consts[a]
+  Q_ADD = 2, Q_SUB = 3, Q_MUL = 4,   // dst = a (op) b
+  Q_NEG = 5, Q_SQR = 6, Q_DBL = 7,   // dst = op(a)
+  Q_COSETX = 8,  // dst = zeta * ext_omega^(global row): the value of X on the extended coset (Ast::LinearTerm)
+  Q_STORE = 9,   // out[row] = a
+  Q_MULC = 10, Q_ADDC = 11, Q_SUBC = 12,   // dst = a (op) consts[b]
+  Q_NOPS = 13
+};
+
+struct QParams {
+  const uint4* prog;
+  unsigned n_instr, n_regs;
+  const uint4* consts;
+  const uint4* const* cols;
+  unsigned rows_log, step, out_stride, out_off, ext_log;
+  const uint4* tw_ext;   // ext_omega^i, i < 2^(ext_log-1)
+  uint4* out;
+};
+
+template <class PR>
+__global__ void __launch_bounds__(128) quotient_vm_kernel(QParams p, Fe<PR> zeta) {
+  extern __shared__ uint4 smem[];
+  uint4* plane0 = smem;
+  uint4* plane1 = smem + (size_t)p.n_regs * blockDim.x;
+  const unsigned rows = 1u << p.rows_log;
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned row = gid & (rows - 1);          // rows < blockDim: surplus threads recompute a valid row, never store
+  const bool live = gid < rows;
+  const unsigned tid = threadIdx.x, bd = blockDim.x;
+  auto rd = [&](unsigned reg) -> Fe<PR> {
+    uint4 lo = plane0[reg * bd + tid], hi = plane1[reg * bd + tid];
+    Fe<PR> r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w; r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+  };
+  auto wr = [&](unsigned reg, const Fe<PR>& a) {
+    plane0[reg * bd + tid] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    plane1[reg * bd + tid] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+  };
+  for (unsigned pc = 0; pc < p.n_instr; ++pc) {
+    const uint4 ins = __ldg(p.prog + pc);
+    switch (ins.x) {
+      case Q_LOAD: {
+        unsigned idx = (row + (unsigned)((int)ins.w * (int)p.step)) & (rows - 1);
+        const uint4* col = p.cols[ins.z];
+        wr(ins.y, fe_load<PR>(col + 2 * (size_t)idx));
+        break;
+      }
+      case Q_CONST: wr(ins.y, fe_load_ro<PR>(p.consts + 2 * (size_t)ins.z)); break;
+      case Q_ADD: wr(ins.y, fe_add(rd(ins.z), rd(ins.w))); break;
+      case Q_SUB: wr(ins.y, fe_sub(rd(ins.z), rd(ins.w))); break;
+      case Q_MUL: wr(ins.y, fe_mul(rd(ins.z), rd(ins.w))); break;
+      case Q_NEG: wr(ins.y, fe_neg(rd(ins.z))); break;
+      case Q_SQR: wr(ins.y, fe_sqr(rd(ins.z))); break;
+      case Q_DBL: wr(ins.y, fe_dbl(rd(ins.z))); break;
+      case Q_COSETX: {
+        unsigned g = row * p.out_stride + p.out_off;
+        unsigned half = 1u << (p.ext_log - 1);
+        Fe<PR> w = fe_load_ro<PR>(p.tw_ext + 2 * (size_t)(g & (half - 1)));
+        if (g & half) w = fe_neg(w);
+        wr(ins.y, fe_mul(w, zeta));
+        break;
+      }
+      case Q_STORE:
+        if (live) fe_store(p.out + 2 * ((size_t)row * p.out_stride + p.out_off), rd(ins.z));
+        break;
+      case Q_MULC: wr(ins.y, fe_mul(rd(ins.z), fe_load_ro<PR>(p.consts + 2 * (size_t)ins.w))); break;
+      case Q_ADDC: wr(ins.y, fe_add(rd(ins.z), fe_load_ro<PR>(p.consts + 2 * (size_t)ins.w))); break;
+      case Q_SUBC: wr(ins.y, fe_sub(rd(ins.z), fe_load_ro<PR>(p.consts + 2 * (size_t)ins.w))); break;
+      default: break;
+    }
+  }
+}
+
+int validate_program(trp_ctx* ctx, const uint32_t* prog, size_t n_instr, unsigned n_regs, size_t n_consts, size_t n_cols) {
+  bool stores = false;
+  for (size_t i = 0; i < n_instr; ++i) {
+    const uint32_t op = prog[4 * i], dst = prog[4 * i + 1], a = prog[4 * i + 2], b = prog[4 * i + 3];
+    bool ok = op < Q_NOPS;
+    if (ok) switch (op) {
+      case Q_LOAD: ok = dst < n_regs && a < n_cols && ((int)b > -(1 << 20) && (int)b < (1 << 20)); break;
+      case Q_CONST: ok = dst < n_regs && a < n_consts; break;
+      case Q_ADD: case Q_SUB: case Q_MUL: ok = dst < n_regs && a < n_regs && b < n_regs; break;
+      case Q_NEG: case Q_SQR: case Q_DBL: ok = dst < n_regs && a < n_regs; break;
+      case Q_COSETX: ok = dst < n_regs; break;
+      case Q_STORE: ok = a < n_regs; stores = true; break;
+      default: ok = dst < n_regs && a < n_regs && b < n_consts; break;
+    }
+    if (!ok) TRP_FAIL(ctx, TRP_E_INVALID, "quotient program: instruction %zu is malformed (op %u dst %u a %u b %u)", i, op, dst, a, b);
+  }
+  if (!stores) TRP_FAIL(ctx, TRP_E_INVALID, "quotient program never stores a result");
+  return TRP_OK;
+}
+
+// d_cols_dev: device array of column pointers; everything else already validated
+int launch_vm(trp_domain* d, const uint4* d_prog, size_t n_instr, unsigned n_regs, const uint4* d_consts,
+              const uint4* const* d_cols_dev, int coset, uint4* d_out) {
+  trp_ctx* ctx = d->ctx;
+  QParams p;
+  p.prog = d_prog; p.n_instr = (unsigned)n_instr; p.n_regs = n_regs; p.consts = d_consts; p.cols = d_cols_dev;
+  p.ext_log = d->ext_k;
+  const unsigned period = 1u << (d->ext_k - d->k);
+  if (coset < 0) { p.rows_log = d->ext_k; p.step = period; p.out_stride = 1; p.out_off = 0; }
+  else { p.rows_log = d->k; p.step = 1; p.out_stride = period; p.out_off = (unsigned)coset; }
+  const void* tw = nullptr;
+  TRP_TRY(trp_get_powers(ctx, d->field, d->ext_k, d->ext_omega, &tw));
+  p.tw_ext = (const uint4*)tw;
+  p.out = d_out;
+  unsigned threads = 128;
+  while (threads > 32 && (size_t)n_regs * threads * 32 > 200 * 1024) threads >>= 1;
+  size_t smem = (size_t)n_regs * threads * 32;
+  if (smem > 200 * 1024) TRP_FAIL(ctx, TRP_E_INVALID, "quotient program needs %u registers (max %u)", n_regs, 200 * 1024 / (32 * 32));
+  const size_t rows = (size_t)1 << p.rows_log;
+  unsigned blocks = (unsigned)((rows + threads - 1) / threads);
+  auto go = [&](auto tag) -> int {
+    typedef decltype(tag) PR;
+    Fe<PR> zeta;
+    for (int i = 0; i < 4; ++i) { zeta.v[2 * i] = (uint32_t)d->g_coset[i]; zeta.v[2 * i + 1] = (uint32_t)(d->g_coset[i] >> 32); }
+    if (smem > 48 * 1024)
+      TRP_CUDA(ctx, cudaFuncSetAttribute(quotient_vm_kernel<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ProfScope ps(ctx, PROF_QUOTIENT);
+    quotient_vm_kernel<PR><<<blocks, threads, smem, ctx->stream>>>(p, zeta);
+    TRP_LAUNCHED(ctx);
+    return TRP_OK;
+  };
+  return d->field == 0 ? go(FpParams()) : go(FqParams());
+}
+
+struct Locked {
+  std::lock_guard<std::mutex> g;
+  explicit Locked(trp_ctx* c) : g(c->mu) { cudaSetDevice(c->device); }
+};
+
+// stage program / constants / column-pointer table at the front of the arena; returns the bytes used
+int stage_tables(trp_ctx* ctx, const uint32_t* program, size_t n_instr, const uint64_t* consts, size_t n_consts,
+                 const uint64_t* const* col_ptrs, size_t n_cols, size_t extra, char** after) {
+  size_t b_prog = ws_align(n_instr * 16), b_c = ws_align((n_consts ? n_consts : 1) * 32), b_p = ws_align((n_cols ? n_cols : 1) * 8);
+  TRP_TRY(trp_ws_reserve(ctx, b_prog + b_c + b_p + extra));
+  char* w = (char*)ctx->ws;
+  TRP_CUDA(ctx, cudaMemcpyAsync(w, program, n_instr * 16, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_consts) TRP_CUDA(ctx, cudaMemcpyAsync(w + b_prog, consts, n_consts * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_cols && col_ptrs) TRP_CUDA(ctx, cudaMemcpyAsync(w + b_prog + b_c, col_ptrs, n_cols * 8, cudaMemcpyHostToDevice, ctx->stream));
+  // the host arrays may be reused by the caller as soon as we return
+  TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *after = w + b_prog + b_c + b_p;
+  return TRP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int trp_dev_quotient_eval(trp_domain* d, const uint32_t* program, size_t n_instr, unsigned n_regs, const uint64_t* consts,
+                          size_t n_consts, const uint64_t* const* d_cols, size_t n_cols, int coset, uint64_t* d_out) {
+  if (!d) return TRP_E_INVALID;
+  trp_ctx* ctx = d->ctx;
+  Locked l(ctx);
+  if (!program || !n_instr || !d_out || (n_consts && !consts) || (n_cols && !d_cols)) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
+  if (n_regs == 0 || coset >= (int)(1u << (d->ext_k - d->k))) TRP_FAIL(ctx, TRP_E_INVALID, "bad register count or coset index");
+  TRP_TRY(validate_program(ctx, program, n_instr, n_regs, n_consts, n_cols));
+  for (size_t c = 0; c < n_cols; ++c) if (!d_cols[c]) TRP_FAIL(ctx, TRP_E_INVALID, "column %zu is NULL", c);
+  char* after = nullptr;
+  TRP_TRY(stage_tables(ctx, program, n_instr, consts, n_consts, d_cols, n_cols, 0, &after));
+  char* w = (char*)ctx->ws;
+  size_t b_prog = ws_align(n_instr * 16), b_c = ws_align((n_consts ? n_consts : 1) * 32);
+  return launch_vm(d, (const uint4*)w, n_instr, n_regs, (const uint4*)(w + b_prog), (const uint4* const*)(w + b_prog + b_c), coset,
+                   (uint4*)d_out);
+}
+
+// host-pointer form over the whole extended domain (what poly::Evaluator::evaluate returns): columns are uploaded,
+// the result is downloaded.  Meant for parity tests and small domains; a prover keeps columns on the device.
+int trp_quotient_eval(trp_domain* d, const uint32_t* program, size_t n_instr, unsigned n_regs, const uint64_t* consts,
+                      size_t n_consts, const uint64_t* const* cols, size_t n_cols, uint64_t* out_ext) {
+  if (!d) return TRP_E_INVALID;
+  trp_ctx* ctx = d->ctx;
+  Locked l(ctx);
+  if (!program || !n_instr || !out_ext || (n_consts && !consts) || (n_cols && !cols)) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
+  if (n_regs == 0) TRP_FAIL(ctx, TRP_E_INVALID, "bad register count");
+  TRP_TRY(validate_program(ctx, program, n_instr, n_regs, n_consts, n_cols));
+  for (size_t c = 0; c < n_cols; ++c) if (!cols[c]) TRP_FAIL(ctx, TRP_E_INVALID, "column %zu is NULL", c);
+  const size_t EN = (size_t)1 << d->ext_k;
+  char* after = nullptr;
+  TRP_TRY(stage_tables(ctx, program, n_instr, consts, n_consts, nullptr, n_cols, (n_cols + 1) * EN * 32, &after));
+  char* w = (char*)ctx->ws;
+  size_t b_prog = ws_align(n_instr * 16), b_c = ws_align((n_consts ? n_consts : 1) * 32);
+  std::vector<const uint64_t*> dptr(n_cols);
+  for (size_t c = 0; c < n_cols; ++c) {
+    dptr[c] = (const uint64_t*)(after + c * EN * 32);
+    TRP_CUDA(ctx, cudaMemcpyAsync((void*)dptr[c], cols[c], EN * 32, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (n_cols) TRP_CUDA(ctx, cudaMemcpyAsync(w + b_prog + b_c, dptr.data(), n_cols * 8, cudaMemcpyHostToDevice, ctx->stream));
+  TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // dptr goes out of scope below
+  char* d_out = after + n_cols * EN * 32;
+  TRP_TRY(launch_vm(d, (const uint4*)w, n_instr, n_regs, (const uint4*)(w + b_prog), (const uint4* const*)(w + b_prog + b_c), -1,
+                    (uint4*)d_out));
+  TRP_CUDA(ctx, cudaMemcpyAsync(out_ext, d_out, EN * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TRP_OK;
+}
+
+// Evaluations of `batch` coefficient-form columns (n each) on the coset (zeta * ext_omega^coset) * <omega>:
+// out[i] = p(zeta * ext_omega^(coset + i * 2^(ext_k-k))), i.e. rows coset, coset + 2^(ext_k-k), ... of coeff_to_extended.
+int trp_dev_coeff_to_coset(trp_domain* d, const uint64_t* d_coeff, uint64_t* d_out, size_t batch, unsigned coset) {
+  if (!d) return TRP_E_INVALID;
+  trp_ctx* ctx = d->ctx;
+  Locked l(ctx);
+  if (batch && (!d_coeff || !d_out)) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
+  if (coset >= (1u << (d->ext_k - d->k))) TRP_FAIL(ctx, TRP_E_INVALID, "coset index %u out of range", coset);
+  const size_t n = (size_t)1 << d->k;
+  const void* pw = nullptr;   // (zeta * ext_omega^coset)^i, i < n
+  TRP_TRY(trp_get_powers(ctx, d->field, d->k + 1, d->coset_gen[coset], &pw));
+  const bool need_tmp = trp_ntt_passes(d->k) > 1 && d_coeff == d_out;
+  size_t cols = batch > 65535 ? 65535 : batch;
+  if (need_tmp) {
+    size_t fit = ((size_t)4 << 30) / (n * 32);
+    if (fit < 1) fit = 1;
+    if (cols > fit) cols = fit;
+    TRP_TRY(trp_ws_reserve(ctx, cols * n * 32));
+  }
+  for (size_t b0 = 0; b0 < batch; b0 += cols) {
+    size_t nb = batch - b0 < cols ? batch - b0 : cols;
+    TRP_TRY(trp_ntt_impl(ctx, d->field, d_coeff + 4 * b0 * n, d_out + 4 * b0 * n, nb, d->k, d->omega, n, n, (unsigned)n, pw,
+                         (unsigned)n, nullptr, 0, (unsigned)n, need_tmp ? ctx->ws : nullptr));
+  }
+  return TRP_OK;
+}
+
+}  // extern "C"
