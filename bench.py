@@ -281,7 +281,10 @@ def run_gpu(args):
     # ---- roofline of the dominant kernel (bucket accumulation, level 1) -----------------------------------------------
     if rank == 0:
         peaks, peak_src = _peaks()
-        int_peak_gmacs = ctx.microbench(0, 512)          # independent IMAD.WIDE.U32: 32x32+64 MACs per second (G/s), measured now
+        # integer-multiply peak, measured now: carry-chained 32x32+64 wide MACs (SASS: IMAD.WIDE.U32[.X] only) and,
+        # as a cross-check, the 32-bit IMAD issue rate / 2 (a wide MAC occupies two fmaheavy issue slots on sm_100a)
+        int_peak_gmacs = max(ctx.microbench(3, 512), ctx.microbench(0, 512))
+        imad32_g = ctx.microbench(1, 512)
         acc_ms, acc_launches = prof["msm_accum_l1"]
         per_launch_ms = acc_ms / max(acc_launches, 1)
         macs_per_launch = n * windows * FMUL_PER_MIXED_ADD * MACS_PER_FMUL
@@ -290,7 +293,9 @@ def run_gpu(args):
         share = {k: round(v[0] / elapsed_ms, 4) for k, v in prof.items() if v[1]}
         roofline = {"bound": "int32-pipe", "kernel": "msm_accum_l1_kernel", "achieved": achieved, "peak": peak, "unit": "TMAC/s",
                     "frac": achieved / peak, "traffic": _traffic_from_profiles(),
-                    "peak_source": "IMAD.WIDE.U32 issue-rate microbenchmark run in this process (MEASURED_PEAKS.json has no integer peak)",
+                    "peak_source": "wide-MAC (IMAD.WIDE.U32.X chain) microbenchmark run in this process; MEASURED_PEAKS.json has no "
+                                   "integer peak. Equivalent to SURVEY 8(d)'s model: 256 IMAD slots per Fmul against the 32-bit IMAD rate",
+                    "imad32_tops": imad32_g / 1e3,
                     "algorithmic_macs_per_launch": macs_per_launch, "launch_ms": per_launch_ms, "launches_timed": acc_launches,
                     "model": f"n*W*{FMUL_PER_MIXED_ADD} Fmul x {MACS_PER_FMUL} MAC, W={windows}, c={c_bits}",
                     "hbm": {"algorithmic_bytes_per_launch": n * windows * 68, "gbs": n * windows * 68 / (per_launch_ms * 1e-3) / 1e9,

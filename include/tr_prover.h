@@ -148,8 +148,10 @@ int trp_dev_coeff_to_coset(trp_domain* d, const uint64_t* d_coeff, uint64_t* d_o
 int trp_field_op(trp_ctx* ctx, int which_field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 
 /* ---- microbenchmarks used by bench.py to measure the integer-pipe roofline denominator -------------------
- * kind 0: independent IMAD.WIDE chains, 1: IMAD (32-bit), 2: IADD3, 3: mixed IMAD.WIDE + IADD3, 4: field mul.
- * Returns achieved G-ops/s in *out_gops (ops = thread-level instructions, or field muls for kind 4). */
+ * kind 0: independent 32x32+64 wide MACs with carry-out (IMAD.WIDE.U32 + carry count), 1: 32-bit IMAD,
+ * 2: IADD3.X carry chains, 3: carry-chained wide MACs as in the field multiplier (IMAD.WIDE.U32.X; the wide-MAC peak),
+ * 4: field mul, 5: field add/sub, 6-8: reduced-radix experiments, 10: IMAD.WIDE + IADD3 mix, 11: DFMA.
+ * Returns achieved G-ops/s in *out_gops (ops = wide MACs / thread-level instructions / field muls). */
 int trp_microbench(trp_ctx* ctx, int kind, int iters, double* out_gops);
 
 #ifdef __cplusplus

@@ -234,7 +234,7 @@ int trp_dev_msm_batch(trp_ctx* ctx, const trp_bases* bases, const uint64_t* d_sc
   if (!bases || bases->ctx != ctx) TRP_FAIL(ctx, TRP_E_INVALID, "bases handle does not belong to this context");
   if (m == 0) return TRP_OK;
   if ((n && !d_scalars) || !d_out_jacobian) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
-  size_t need = trp_msm_ws_bytes(bases, n);
+  size_t need = trp_msm_ws_bytes(bases, n, m);
   TRP_TRY(trp_ws_reserve(ctx, need));
   return trp_msm_impl(ctx, bases, d_scalars, n, m, d_out_jacobian, ctx->ws, ctx->ws_bytes);
 }
@@ -247,9 +247,9 @@ int trp_msm_batch(trp_ctx* ctx, const trp_bases* bases, const uint64_t* scalars,
   if ((n && !scalars) || !out_jacobian) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
   if (n > bases->n) TRP_FAIL(ctx, TRP_E_INVALID, "MSM length %zu exceeds the %zu loaded bases", n, bases->n);
   // stage up to `cols` scalar columns at a time
-  size_t msm_ws = trp_msm_ws_bytes(bases, n);
   size_t col_bytes = ws_align(n * 32 + 32);
   size_t cols = chunk_cols(m, col_bytes, SCRATCH_BUDGET);
+  size_t msm_ws = trp_msm_ws_bytes(bases, n, cols);
   size_t out_bytes = ws_align(m * 96);
   TRP_TRY(trp_ws_reserve(ctx, cols * col_bytes + out_bytes + msm_ws));
   char* ws = (char*)ctx->ws;

@@ -1,6 +1,9 @@
 // Integer-pipe microbenchmarks: establish the roofline denominator for the MSM / NTT kernels
 // (MEASURED_PEAKS.json has HBM and bf16 peaks only).  Each kernel issues long runs of one instruction
-// class from many resident warps; the result is thread-level instructions per second.
+// class from many resident warps; the result is thread-level instructions per second.  The SASS of every kernel
+// was checked with cuobjdump (profiles/int_pipe_r01.md): on sm_100a a 32x32->64 multiply-add costs TWO issue slots
+// of the fmaheavy pipe whichever way it is written (IMAD.WIDE.U32[.X] runs at 32 lanes/clk/SM, IMAD lo / IMAD.HI at
+// 64 each), so the wide-MAC peak is half the 32-bit IMAD rate: 148 x 32 x 1.965 GHz = 9.3 T MAC/s.
 #include "common.cuh"
 #include "ff29_experiment.cuh"
 
@@ -11,25 +14,9 @@ namespace {
 constexpr int MB_THREADS = 256;
 constexpr int MB_UNROLL = 16;
 
-// kind 0: independent IMAD.WIDE.U32 (32x32+64 -> 64), 8 accumulators per thread
-__global__ void mb_imad_wide(uint64_t* out, uint32_t a, uint32_t b, int iters) {
-  uint64_t acc[8];
-  uint32_t x = a + threadIdx.x, y = b | 1u;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = threadIdx.x * 7 + k;
-  for (int it = 0; it < iters; ++it) {
-#pragma unroll
-    for (int u = 0; u < MB_UNROLL; ++u) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(x), "r"(y));
-    }
-  }
-  uint64_t s = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) s ^= acc[k];
-  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
+// kind 0 is mb_wide_carryout below (independent wide MACs with carry-out).  An earlier version of kind 0 multiplied two
+// loop-invariant registers; ptxas hoisted the product and the loop became IADD3/IADD3.X pairs (no IMAD in the SASS), so
+// the 18.4 T/s it reported was an ALU-pipe number, not an integer-multiply peak.
 // kind 1: independent 32-bit IMAD
 __global__ void mb_imad(uint64_t* out, uint32_t a, uint32_t b, int iters) {
   uint32_t acc[8];
@@ -40,7 +27,7 @@ __global__ void mb_imad(uint64_t* out, uint32_t a, uint32_t b, int iters) {
 #pragma unroll
     for (int u = 0; u < MB_UNROLL; ++u) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(x), "r"(y));
+      for (int k = 0; k < 8; ++k) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(acc[(k + 3) & 7]), "r"(y));
     }
   }
   uint32_t s = 0;
@@ -157,6 +144,71 @@ __global__ void mb_mul29(uint64_t* out, uint32_t a, uint32_t b, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// kind 9: wide MAC with carry-OUT only (no carry-in), the carry counted into a separate register
+// (carry-save accumulation): expect IMAD.WIDE.U32 R, P + IADD3.X cnt.  Counts one op per wide MAC.
+__global__ void mb_wide_carryout(uint64_t* out, uint32_t a, uint32_t b, int iters) {
+  uint32_t lo[4], hi[4], cnt[4];
+  uint32_t x0 = a + threadIdx.x, x1 = x0 * 3 + 1, x2 = x0 * 5 + 2, x3 = x0 * 7 + 3, y = b | 1u;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { lo[k] = threadIdx.x * 7 + k; hi[k] = threadIdx.x * 13 + k; cnt[k] = 0; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < MB_UNROLL; ++u) {
+      asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;" : "+r"(lo[0]), "+r"(hi[0]), "+r"(cnt[0]) : "r"(x0), "r"(y));
+      asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;" : "+r"(lo[1]), "+r"(hi[1]), "+r"(cnt[1]) : "r"(x1), "r"(y));
+      asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;" : "+r"(lo[2]), "+r"(hi[2]), "+r"(cnt[2]) : "r"(x2), "r"(y));
+      asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;" : "+r"(lo[3]), "+r"(hi[3]), "+r"(cnt[3]) : "r"(x3), "r"(y));
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s ^= lo[k] ^ hi[k] ^ cnt[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// kind 10: independent IMAD.WIDE (no carry) interleaved 1:1 with independent 3-input IADD3: do the two pipes overlap?
+// counts BOTH instruction kinds (2 ops per pair)
+__global__ void mb_wide_plus_iadd3(uint64_t* out, uint32_t a, uint32_t b, int iters) {
+  uint64_t acc[4];
+  uint32_t s[4];
+  uint32_t x = a + threadIdx.x, y = b | 1u, z = a ^ b;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { acc[k] = threadIdx.x * 7 + k; s[k] = threadIdx.x + k; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < MB_UNROLL; ++u) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"((uint32_t)(acc[(k + 1) & 3] >> 32)), "r"(y));
+        asm volatile("{.reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2;}" : "+r"(s[k]) : "r"(s[(k + 1) & 3]), "r"(z));
+      }
+    }
+  }
+  uint64_t r = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r ^= acc[k] ^ s[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+// kind 11: independent DFMA (FP64 pipe rate on B200)
+__global__ void mb_dfma(uint64_t* out, uint32_t a, uint32_t b, int iters) {
+  double acc[8];
+  double x = 1.0 + 1e-9 * (a + threadIdx.x), y = 1e-3 * (b | 1u);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = threadIdx.x * 7 + k;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < MB_UNROLL; ++u) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) asm volatile("fma.rn.f64 %0, %1, %0, %2;" : "+d"(acc[k]) : "d"(x), "d"(y));
+    }
+  }
+  double r = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r += acc[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (uint64_t)__double_as_longlong(r);
+}
+
 }  // namespace
 
 int trp_microbench_impl(trp_ctx* ctx, int kind, int iters, double* out_gops) {
@@ -172,7 +224,7 @@ int trp_microbench_impl(trp_ctx* ctx, int kind, int iters, double* out_gops) {
   for (int rep = 0; rep < 4; ++rep) {
     TRP_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     switch (kind) {
-      case 0: mb_imad_wide<<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = 8.0 * MB_UNROLL; break;
+      case 0: mb_wide_carryout<<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = 4.0 * MB_UNROLL; break;
       case 1: mb_imad<<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = 8.0 * MB_UNROLL; break;
       case 2: mb_iadd_carry<<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = 8.0 * MB_UNROLL; break;
       case 3: mb_madc_chain<<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = 4.0 * MB_UNROLL; break;
@@ -181,6 +233,9 @@ int trp_microbench_impl(trp_ctx* ctx, int kind, int iters, double* out_gops) {
       case 6: mb_mul29<ff29::FqP, 0><<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = MB_UNROLL; break;
       case 7: mb_mul29<ff29::FqP, 1><<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = MB_UNROLL; break;
       case 8: mb_mul29<ff29::FqP, 2><<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = MB_UNROLL; break;
+      case 9: mb_wide_carryout<<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = 4.0 * MB_UNROLL; break;
+      case 10: mb_wide_plus_iadd3<<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = 8.0 * MB_UNROLL; break;
+      case 11: mb_dfma<<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = 8.0 * MB_UNROLL; break;
       default: TRP_FAIL(ctx, TRP_E_INVALID, "unknown microbenchmark kind %d", kind);
     }
     TRP_LAUNCHED(ctx);

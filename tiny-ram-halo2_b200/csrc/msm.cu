@@ -84,9 +84,12 @@ __device__ __forceinline__ void for_each_digit(const uint4* scalars, size_t i, s
   }
 }
 
+// Batches are processed column-concurrently: blockIdx.y is the column, its buckets are [col * nb, (col + 1) * nb).
 template <class SPR>
 __global__ void msm_hist_kernel(const uint4* scalars, size_t n, MsmGeom g, uint32_t* counts) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  scalars += 2 * (size_t)blockIdx.y * n;
+  counts += (size_t)blockIdx.y * g.nb;
   for_each_digit<SPR>(scalars, i, n, g, [&](unsigned, unsigned key, unsigned) {
     unsigned peers = __match_any_sync(0xffffffffu, key);
     if (key != 0xffffffffu && (unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(&counts[key], __popc(peers));
@@ -97,6 +100,8 @@ template <class SPR>
 __global__ void msm_scatter_kernel(const uint4* scalars, size_t n, MsmGeom g, uint32_t* cursor, uint32_t* entries) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
+  scalars += 2 * (size_t)blockIdx.y * n;
+  cursor += (size_t)blockIdx.y * g.nb;
   for_each_digit<SPR>(scalars, i, n, g, [&](unsigned w, unsigned key, unsigned neg) {
     unsigned peers = __match_any_sync(0xffffffffu, key);
     unsigned leader = __ffs(peers) - 1;
@@ -268,11 +273,11 @@ __device__ __forceinline__ XYZZ<BPR> xyzz_mul_small(const XYZZ<BPR>& p, unsigned
 
 // chunk of RED_S consecutive buckets [lo, lo+S) of one set: sum_{b} (b+1) B_b = running-sum part + lo * (sum B_b)
 template <class BPR>
-__global__ void __launch_bounds__(ACC_THREADS) msm_reduce_chunks_kernel(const uint4* part, const uint32_t* off, MsmGeom g, uint4* chunk_out) {
+__global__ void __launch_bounds__(ACC_THREADS) msm_reduce_chunks_kernel(const uint4* part, const uint32_t* off, MsmGeom g, unsigned total_sets, uint4* chunk_out) {
   unsigned chunks_per_set = g.B / RED_S ? g.B / RED_S : 1;
   unsigned S = g.B < RED_S ? g.B : RED_S;
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= g.nsets * chunks_per_set) return;
+  if (t >= total_sets * chunks_per_set) return;
   unsigned set = t / chunks_per_set, ch = t % chunks_per_set;
   unsigned lo = ch * S;
   XYZZ<BPR> run = xyzz_identity<BPR>(), acc = xyzz_identity<BPR>();
@@ -313,8 +318,11 @@ __global__ void __launch_bounds__(256) msm_reduce_sets_kernel(const uint4* chunk
 // Horner over sets (window w has weight 2^(c*w)) and conversion XYZZ -> Jacobian (X*ZZ^4... no inversion):
 // (X', Y', Z') = (X * ZZ^4, Y * ZZZ^4, ZZ * ZZZ) since Z'^2 = ZZ^5 and Z'^3 = ZZZ^5.
 template <class BPR>
-__global__ void msm_final_kernel(const uint4* set_sums, MsmGeom g, uint4* out_jac) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void msm_final_kernel(const uint4* set_sums, MsmGeom g, unsigned mcols, uint4* out_jac) {
+  unsigned col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= mcols) return;
+  set_sums += 8 * (size_t)col * g.nsets;
+  out_jac += 6 * (size_t)col;
   XYZZ<BPR> acc = load_xyzz<BPR>(set_sums + 8 * (size_t)(g.nsets - 1));
   for (int w = (int)g.nsets - 2; w >= 0; --w) {
     for (unsigned k = 0; k < g.c; ++k) xyzz_dbl(acc);
@@ -348,11 +356,6 @@ __global__ void msm_normalize_kernel(uint4* out_jac, size_t m) {
   fe_store(o, fe_mul(X, zi2));
   fe_store(o + 2, fe_mul(Y, fe_mul(zi2, zi)));
   fe_store(o + 4, fe_one<BPR>());
-}
-
-template <class BPR>
-__global__ void msm_identity_kernel(uint4* out_jac) {
-  if (threadIdx.x < 6) out_jac[threadIdx.x] = make_uint4(0, 0, 0, 0);
 }
 
 // ---- base precomputation: table[w][i] = 2^(c*w) * P_i, affine ---------------------------------------------------
@@ -443,98 +446,118 @@ int run_scan(trp_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t* out2, ui
   return TRP_OK;
 }
 
-// Worst-case task counts per level (entries may all fall into one bucket, or spread over all of them).
-std::vector<size_t> plan_levels(const MsmGeom& g, size_t n) {
-  const size_t M = n * g.W;
+// Worst-case task counts per level for mc columns processed together (entries may all fall into one bucket, or
+// spread over all of them).
+std::vector<size_t> plan_levels(const MsmGeom& g, size_t n, size_t mc) {
+  const size_t M = n * g.W * mc, NB = (size_t)g.nb * mc;
   std::vector<size_t> level_tasks;
-  size_t single = (M + L1 - 1) / L1;            // tasks if ONE bucket held every entry
-  size_t bound = single + g.nb;                 // sum_b ceil(cnt_b / L1) <= M / L1 + nb
+  size_t single = (n * g.W + L1 - 1) / L1;      // tasks if ONE bucket of a column held all its entries
+  size_t bound = (M + L1 - 1) / L1 + NB;        // sum_b ceil(cnt_b / L1) <= M / L1 + NB
   level_tasks.push_back(bound);
   while (single > 1) {
     single = (single + L2 - 1) / L2;
-    bound = (bound + L2 - 1) / L2 + g.nb;
+    bound = (bound + L2 - 1) / L2 + NB;
     level_tasks.push_back(bound);
   }
   return level_tasks;
 }
 
-template <class BPR, class SPR>
-int msm_one(trp_ctx* ctx, const trp_bases_impl* bs, const uint4* d_scalars, size_t n, uint4* d_out, char* ws, size_t ws_cap) {
-  const MsmGeom& g = bs->g;
-  if (n == 0) {
-    msm_identity_kernel<BPR><<<1, 32, 0, ctx->stream>>>(d_out);
-    TRP_LAUNCHED(ctx);
-    return TRP_OK;
-  }
-  const size_t M = n * g.W;   // upper bound on entries
-  if (M >= (size_t)1 << 31) TRP_FAIL(ctx, TRP_E_INVALID, "MSM of %zu points x %u windows exceeds the 2^31 entry limit", n, g.W);
-  std::vector<size_t> level_tasks = plan_levels(g, n);
-  WsCursor cur{ws, 0, ws_cap};
-  uint32_t* counts = cur.take<uint32_t>(g.nb + 1);
-  uint32_t* offsets = cur.take<uint32_t>(g.nb + 1);
-  uint32_t* cursor = cur.take<uint32_t>(g.nb + 1);
-  uint32_t* block_sums = cur.take<uint32_t>(SCAN_BLOCK);
-  uint32_t* total = cur.take<uint32_t>(4);
-  uint32_t* entries = cur.take<uint32_t>(M);
-  uint32_t* task_off[2] = {cur.take<uint32_t>(g.nb + 1), cur.take<uint32_t>(g.nb + 1)};
-  uint4* part[2] = {cur.take<uint4>(8 * level_tasks[0]), cur.take<uint4>(8 * (level_tasks.size() > 1 ? level_tasks[1] : 1))};
+struct MsmWs {
+  uint32_t *counts, *offsets, *cursor, *block_sums, *total, *entries, *task_off[2];
+  uint4 *part[2], *chunk_out, *set_sums;
+  size_t bytes;
+};
+MsmWs carve(const MsmGeom& g, size_t n, size_t mc, char* base) {
+  const size_t M = n * g.W * mc, NB = (size_t)g.nb * mc;
+  std::vector<size_t> lt = plan_levels(g, n, mc);
   unsigned chunks_per_set = g.B / RED_S ? g.B / RED_S : 1;
-  uint4* chunk_out = cur.take<uint4>(8 * (size_t)g.nsets * chunks_per_set);
-  uint4* set_sums = cur.take<uint4>(8 * (size_t)g.nsets);
-  if (cur.off > ws_cap) TRP_FAIL(ctx, TRP_E_INVALID, "internal: MSM workspace underestimated (%zu > %zu)", cur.off, ws_cap);
+  WsCursor cur{base, 0, 0};
+  MsmWs w;
+  w.counts = cur.take<uint32_t>(NB + 1);
+  w.offsets = cur.take<uint32_t>(NB + 1);
+  w.cursor = cur.take<uint32_t>(NB + 1);
+  w.block_sums = cur.take<uint32_t>(SCAN_BLOCK);
+  w.total = cur.take<uint32_t>(4);
+  w.entries = cur.take<uint32_t>(M ? M : 1);
+  w.task_off[0] = cur.take<uint32_t>(NB + 1);
+  w.task_off[1] = cur.take<uint32_t>(NB + 1);
+  w.part[0] = cur.take<uint4>(8 * lt[0]);
+  w.part[1] = cur.take<uint4>(8 * (lt.size() > 1 ? lt[1] : 1));
+  w.chunk_out = cur.take<uint4>(8 * (size_t)g.nsets * mc * chunks_per_set);
+  w.set_sums = cur.take<uint4>(8 * (size_t)g.nsets * mc);
+  w.bytes = cur.off + 4096;
+  return w;
+}
 
+// mc columns processed together (all on device, no host synchronisation)
+template <class BPR, class SPR>
+int msm_chunk(trp_ctx* ctx, const trp_bases_impl* bs, const uint4* d_scalars, size_t n, size_t mc, uint4* d_out, char* ws, size_t ws_cap) {
+  const MsmGeom& g = bs->g;
+  const size_t M = n * g.W * mc, NB = (size_t)g.nb * mc;
+  if (M >= ((size_t)1 << 32) - 1 || NB >= ((size_t)1 << 31)) TRP_FAIL(ctx, TRP_E_INVALID, "internal: MSM chunk of %zu columns is too large", mc);
+  std::vector<size_t> level_tasks = plan_levels(g, n, mc);
+  MsmWs w = carve(g, n, mc, ws);
+  if (w.bytes > ws_cap) TRP_FAIL(ctx, TRP_E_INVALID, "internal: MSM workspace underestimated (%zu > %zu)", w.bytes, ws_cap);
   {
     ProfScope ps(ctx, PROF_MSM_SORT);
-    TRP_CUDA(ctx, cudaMemsetAsync(counts, 0, (g.nb + 1) * sizeof(uint32_t), ctx->stream));
-    unsigned sblocks = (unsigned)((n + 127) / 128);
-    msm_hist_kernel<SPR><<<sblocks, 128, 0, ctx->stream>>>(d_scalars, n, g, counts);
+    TRP_CUDA(ctx, cudaMemsetAsync(w.counts, 0, (NB + 1) * sizeof(uint32_t), ctx->stream));
+    dim3 sgrid((unsigned)((n + 127) / 128), (unsigned)mc);
+    msm_hist_kernel<SPR><<<sgrid, 128, 0, ctx->stream>>>(d_scalars, n, g, w.counts);
     TRP_LAUNCHED(ctx);
-    TRP_TRY(run_scan(ctx, counts, offsets, cursor, block_sums, total, g.nb, 0, 1));
-    msm_scatter_kernel<SPR><<<sblocks, 128, 0, ctx->stream>>>(d_scalars, n, g, cursor, entries);
+    TRP_TRY(run_scan(ctx, w.counts, w.offsets, w.cursor, w.block_sums, w.total, NB, 0, 1));
+    msm_scatter_kernel<SPR><<<sgrid, 128, 0, ctx->stream>>>(d_scalars, n, g, w.cursor, w.entries);
     TRP_LAUNCHED(ctx);
-    TRP_TRY(run_scan(ctx, offsets, task_off[0], nullptr, block_sums, total, g.nb, 1, L1));
+    TRP_TRY(run_scan(ctx, w.offsets, w.task_off[0], nullptr, w.block_sums, w.total, NB, 1, L1));
   }
   {
     ProfScope ps(ctx, PROF_MSM_ACCUM_L1);
-    msm_accum_l1_kernel<BPR><<<(unsigned)((level_tasks[0] + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(
-        entries, offsets, task_off[0], g.nb, (const uint4*)bs->pub.d_xy, part[0]);
+    unsigned gridl1 = (unsigned)((level_tasks[0] + ACC_THREADS - 1) / ACC_THREADS);
+    msm_accum_l1_kernel<BPR><<<gridl1, ACC_THREADS, 0, ctx->stream>>>(w.entries, w.offsets, w.task_off[0], (unsigned)NB,
+                                                                     (const uint4*)bs->pub.d_xy, w.part[0]);
     TRP_LAUNCHED(ctx);
   }
   int curp = 0;
   {
     ProfScope ps(ctx, PROF_MSM_LEVELS);
     for (size_t lv = 1; lv < level_tasks.size(); ++lv) {
-      TRP_TRY(run_scan(ctx, task_off[curp], task_off[curp ^ 1], nullptr, block_sums, total, g.nb, 1, L2));
+      TRP_TRY(run_scan(ctx, w.task_off[curp], w.task_off[curp ^ 1], nullptr, w.block_sums, w.total, NB, 1, L2));
       msm_accum_ln_kernel<BPR><<<(unsigned)((level_tasks[lv] + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(
-          part[curp], task_off[curp], task_off[curp ^ 1], g.nb, part[curp ^ 1]);
+          w.part[curp], w.task_off[curp], w.task_off[curp ^ 1], (unsigned)NB, w.part[curp ^ 1]);
       TRP_LAUNCHED(ctx);
       curp ^= 1;
     }
   }
   {
     ProfScope ps(ctx, PROF_MSM_REDUCE);
-    unsigned nchunks = g.nsets * chunks_per_set;
-    msm_reduce_chunks_kernel<BPR><<<(nchunks + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, ctx->stream>>>(part[curp], task_off[curp], g, chunk_out);
+    unsigned chunks_per_set = g.B / RED_S ? g.B / RED_S : 1;
+    unsigned total_sets = (unsigned)(g.nsets * mc);
+    unsigned nchunks = total_sets * chunks_per_set;
+    msm_reduce_chunks_kernel<BPR><<<(nchunks + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, ctx->stream>>>(w.part[curp], w.task_off[curp], g, total_sets, w.chunk_out);
     TRP_LAUNCHED(ctx);
-    msm_reduce_sets_kernel<BPR><<<g.nsets, 256, 0, ctx->stream>>>(chunk_out, chunks_per_set, set_sums);
+    msm_reduce_sets_kernel<BPR><<<total_sets, 256, 0, ctx->stream>>>(w.chunk_out, chunks_per_set, w.set_sums);
     TRP_LAUNCHED(ctx);
-    msm_final_kernel<BPR><<<1, 32, 0, ctx->stream>>>(set_sums, g, d_out);
+    msm_final_kernel<BPR><<<(unsigned)((mc + 31) / 32), 32, 0, ctx->stream>>>(w.set_sums, g, (unsigned)mc, d_out);
     TRP_LAUNCHED(ctx);
   }
   return TRP_OK;
 }
 
-size_t msm_ws_bytes(const MsmGeom& g, size_t n) {
-  const size_t M = n * g.W;
-  std::vector<size_t> lt = plan_levels(g, n);
-  size_t t0 = lt[0], t1 = lt.size() > 1 ? lt[1] : 1;
-  unsigned chunks_per_set = g.B / RED_S ? g.B / RED_S : 1;
-  size_t b = 0;
-  b += 5 * ws_align((g.nb + 1) * 4) + ws_align(SCAN_BLOCK * 4) + ws_align(16);
-  b += ws_align(M * 4);
-  b += ws_align(t0 * 128) + ws_align(t1 * 128);
-  b += ws_align((size_t)g.nsets * chunks_per_set * 128) + ws_align((size_t)g.nsets * 128);
-  return b + 4096;
+// columns processed together: bounded by the 32-bit entry index and by a scratch budget
+size_t msm_cols_per_chunk(const MsmGeom& g, size_t n, size_t m) {
+  size_t budget = (size_t)6 << 30;
+  if (const char* e = getenv("TRP_MSM_BATCH_MB")) budget = (size_t)atoll(e) << 20;
+  size_t mc = m ? m : 1;
+  if (n) {
+    size_t cap = (((size_t)1 << 32) - 2) / (n * g.W);
+    if (cap < 1) cap = 1;
+    if (mc > cap) mc = cap;
+  }
+  while (mc > 1 && carve(g, n, mc, nullptr).bytes > budget) mc = (mc + 1) / 2;
+  return mc;
+}
+
+size_t msm_ws_bytes(const MsmGeom& g, size_t n, size_t m) {
+  return carve(g, n, msm_cols_per_chunk(g, n, m), nullptr).bytes;
 }
 
 }  // namespace
@@ -614,28 +637,34 @@ int trp_points_progression_impl(trp_ctx* ctx, const uint64_t* p0, const uint64_t
   return TRP_OK;
 }
 
-size_t trp_msm_ws_bytes(const trp_bases* bases, size_t n) {
-  return msm_ws_bytes(reinterpret_cast<const trp_bases_impl*>(bases)->g, n);
+size_t trp_msm_ws_bytes(const trp_bases* bases, size_t n, size_t m) {
+  return msm_ws_bytes(reinterpret_cast<const trp_bases_impl*>(bases)->g, n, m);
 }
 
 int trp_msm_impl(trp_ctx* ctx, const trp_bases* bases, const void* d_scalars, size_t n, size_t m, void* d_out_jac,
                  void* ws, size_t ws_bytes) {
   const trp_bases_impl* bs = reinterpret_cast<const trp_bases_impl*>(bases);
   if (n > bases->n) TRP_FAIL(ctx, TRP_E_INVALID, "MSM length %zu exceeds the %zu loaded bases", n, bases->n);
-  if (ws_bytes < msm_ws_bytes(bs->g, n)) TRP_FAIL(ctx, TRP_E_INVALID, "internal: MSM workspace too small");
-  for (size_t k = 0; k < m; ++k) {
+  if ((size_t)n * bs->g.W >= ((size_t)1 << 31)) TRP_FAIL(ctx, TRP_E_INVALID, "MSM of %zu points x %u windows exceeds the 2^31 entry limit", n, bs->g.W);
+  if (ws_bytes < msm_ws_bytes(bs->g, n, m)) TRP_FAIL(ctx, TRP_E_INVALID, "internal: MSM workspace too small");
+  if (m == 0) return TRP_OK;
+  const bool pallas = ctx->curve == TRP_CURVE_PALLAS;
+  if (n == 0) {
+    TRP_CUDA(ctx, cudaMemsetAsync(d_out_jac, 0, m * 96, ctx->stream));   // identity: x = y = z = 0
+    return TRP_OK;
+  }
+  const size_t mc = msm_cols_per_chunk(bs->g, n, m);
+  for (size_t k = 0; k < m; k += mc) {
+    size_t cols = m - k < mc ? m - k : mc;
     const uint4* sc = (const uint4*)d_scalars + 2 * k * n;
     uint4* out = (uint4*)d_out_jac + 6 * k;
-    int rc;
-    if (ctx->curve == TRP_CURVE_PALLAS) rc = msm_one<FpParams, FqParams>(ctx, bs, sc, n, out, (char*)ws, ws_bytes);
-    else rc = msm_one<FqParams, FpParams>(ctx, bs, sc, n, out, (char*)ws, ws_bytes);
+    int rc = pallas ? msm_chunk<FpParams, FqParams>(ctx, bs, sc, n, cols, out, (char*)ws, ws_bytes)
+                    : msm_chunk<FqParams, FpParams>(ctx, bs, sc, n, cols, out, (char*)ws, ws_bytes);
     if (rc != TRP_OK) return rc;
   }
-  if (m) {
-    unsigned blocks = (unsigned)((m + 31) / 32);
-    if (ctx->curve == TRP_CURVE_PALLAS) msm_normalize_kernel<FpParams><<<blocks, 32, 0, ctx->stream>>>((uint4*)d_out_jac, m);
-    else msm_normalize_kernel<FqParams><<<blocks, 32, 0, ctx->stream>>>((uint4*)d_out_jac, m);
-    TRP_LAUNCHED(ctx);
-  }
+  unsigned blocks = (unsigned)((m + 31) / 32);
+  if (pallas) msm_normalize_kernel<FpParams><<<blocks, 32, 0, ctx->stream>>>((uint4*)d_out_jac, m);
+  else msm_normalize_kernel<FqParams><<<blocks, 32, 0, ctx->stream>>>((uint4*)d_out_jac, m);
+  TRP_LAUNCHED(ctx);
   return TRP_OK;
 }
