@@ -86,6 +86,11 @@ int trp_msm_batch(trp_ctx* ctx, const trp_bases* bases, const uint64_t* scalars 
 int trp_dev_msm_batch(trp_ctx* ctx, const trp_bases* bases, const uint64_t* d_scalars, size_t n, size_t m,
                       uint64_t* d_out_jacobian /* m x 12, device */);
 
+/* Sum of g group elements (Jacobian in, normalised Jacobian out).  Combines the per-GPU partial sums when one MSM's point
+ * range is split across devices -- the same final step best_multiexp performs over its per-thread partial results. */
+int trp_points_sum(trp_ctx* ctx, const uint64_t* jacobian /* g x 12 */, size_t g, uint64_t out_jacobian[12]);
+int trp_dev_points_sum(trp_ctx* ctx, const uint64_t* d_jacobian, size_t g, uint64_t* d_out_jacobian);
+
 /* Synthetic input generator for benchmarks and large tests: d_out[i] = P0 + i*D as affine points in DEVICE
  * memory (an arithmetic progression of random multiples of the generator). */
 int trp_dev_points_progression(trp_ctx* ctx, const uint64_t p0[8], const uint64_t d[8], size_t n, uint64_t* d_out);

@@ -184,3 +184,33 @@ def test_commit_lagrange_linearity_2_20(pkg, ctxs):
     assert np.array_equal(O.point_add(curve, ca, cb), cab)
     want = O.msm(curve, np.concatenate([b, rb.reshape(1, 4)]), np.concatenate([pts[n:2 * n], pts[2 * n:2 * n + 1]]))
     assert np.array_equal(cb, want)
+
+
+def test_point_range_split_and_points_sum(pkg, ctxs):
+    """SURVEY 8(e)-2 on one device: the MSM over [0, n) equals trp_points_sum of the MSMs over G disjoint slices (each with
+    its own pre-sharded base handle); also the identity / single-element / cancelling cases of trp_points_sum."""
+    import ctypes
+    from tiny_ram_halo2_b200 import parallel as PL
+    from tiny_ram_halo2_b200._lib import ptr
+    curve = O.VESTA
+    ctx = ctxs[curve]
+    n, G = 3001, 4
+    pts = make_points(curve, n)
+    sc = scalars_uniform(curve, n, 12)
+    parts = np.zeros((G, 3, 4), dtype=np.uint64)
+    for r in range(G):
+        lo, hi = PL.split_point_range(n, G, r)
+        parts[r] = pkg.best_multiexp(ctx, sc[lo:hi], pkg.Bases(ctx, pts[lo:hi]))
+    out = np.zeros((3, 4), dtype=np.uint64)
+    ctx.check(ctx.lib.trp_points_sum(ctx.handle, ptr(parts), G, ptr(out)))
+    assert np.array_equal(affine_of(curve, out), O.msm(curve, sc, pts))
+    # identity inputs, P + (-P), empty sum
+    neg = parts[0].copy()
+    neg[1] = O.field_op(O.FQ, "sub", np.zeros((1, 4), dtype=np.uint64), parts[0][1].reshape(1, 4))[0]
+    for arr, want in ((np.stack([parts[0], neg]), np.zeros(8, dtype=np.uint64)),
+                      (np.stack([np.zeros((3, 4), dtype=np.uint64), parts[1]]), affine_of(curve, parts[1])),
+                      (np.stack([parts[2], parts[2]]), O.point_add(curve, affine_of(curve, parts[2]), affine_of(curve, parts[2])))):
+        ctx.check(ctx.lib.trp_points_sum(ctx.handle, ptr(np.ascontiguousarray(arr)), len(arr), ptr(out)))
+        assert np.array_equal(affine_of(curve, out), want)
+    ctx.check(ctx.lib.trp_points_sum(ctx.handle, None, 0, ptr(out)))
+    assert not out.any()

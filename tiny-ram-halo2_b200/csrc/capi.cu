@@ -269,6 +269,27 @@ int trp_msm(trp_ctx* ctx, const trp_bases* bases, const uint64_t* scalars, size_
   return trp_msm_batch(ctx, bases, scalars, n, 1, out_jacobian);
 }
 
+// sum of g group elements given as Jacobian points (normalised result): combines the partial sums of an MSM whose point
+// range was split across GPUs (mirrors how best_multiexp adds its per-thread partial results)
+int trp_points_sum(trp_ctx* ctx, const uint64_t* jacobian, size_t g, uint64_t out_jacobian[12]) {
+  if (!ctx) return TRP_E_INVALID;
+  Locked l(ctx);
+  if ((g && !jacobian) || !out_jacobian) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
+  TRP_TRY(trp_ws_reserve(ctx, ws_align(g * 96) + 256));
+  char* d_in = (char*)ctx->ws; char* d_out = d_in + ws_align(g * 96);
+  if (g) TRP_CUDA(ctx, cudaMemcpyAsync(d_in, jacobian, g * 96, cudaMemcpyHostToDevice, ctx->stream));
+  TRP_TRY(trp_points_sum_impl(ctx, d_in, g, d_out));
+  TRP_CUDA(ctx, cudaMemcpyAsync(out_jacobian, d_out, 96, cudaMemcpyDeviceToHost, ctx->stream));
+  TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return TRP_OK;
+}
+int trp_dev_points_sum(trp_ctx* ctx, const uint64_t* d_jacobian, size_t g, uint64_t* d_out_jacobian) {
+  if (!ctx) return TRP_E_INVALID;
+  Locked l(ctx);
+  if ((g && !d_jacobian) || !d_out_jacobian) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
+  return trp_points_sum_impl(ctx, d_jacobian, g, d_out_jacobian);
+}
+
 // synthetic bases: out[i] = P0 + i*D (affine), written to DEVICE memory
 int trp_dev_points_progression(trp_ctx* ctx, const uint64_t p0[8], const uint64_t d[8], size_t n, uint64_t* d_out) {
   if (!ctx) return TRP_E_INVALID;

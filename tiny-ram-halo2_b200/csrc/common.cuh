@@ -159,6 +159,7 @@ int trp_get_powers(trp_ctx* ctx, int field, unsigned log_n, const uint64_t g[4],
 int trp_msm_impl(trp_ctx* ctx, const trp_bases* bases, const void* d_scalars, size_t n, size_t m, void* d_out_jac,
                  void* ws, size_t ws_bytes);
 size_t trp_msm_ws_bytes(const trp_bases* bases, size_t n, size_t m);
+int trp_points_sum_impl(trp_ctx* ctx, const void* d_jac, size_t g, void* d_out);
 int trp_points_progression_impl(trp_ctx* ctx, const uint64_t* p0, const uint64_t* d, size_t n, void* d_out);
 int trp_bases_create(trp_ctx* ctx, const void* src, bool src_on_device, size_t n, int flags, trp_bases** out);
 void trp_bases_destroy(trp_bases* b);

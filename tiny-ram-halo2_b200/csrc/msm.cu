@@ -668,3 +668,33 @@ int trp_msm_impl(trp_ctx* ctx, const trp_bases* bases, const void* d_scalars, si
   TRP_LAUNCHED(ctx);
   return TRP_OK;
 }
+
+// ---- sum of a few group elements (combining the per-GPU partial sums of a point-range-split MSM) -----------------------
+namespace {
+template <class BPR>
+__global__ void points_sum_kernel(const uint4* jac, size_t g, uint4* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  XYZZ<BPR> acc = xyzz_identity<BPR>();
+  for (size_t i = 0; i < g; ++i) {
+    Fe<BPR> X = fe_load<BPR>(jac + 6 * i), Y = fe_load<BPR>(jac + 6 * i + 2), Z = fe_load<BPR>(jac + 6 * i + 4);
+    if (fe_is_zero(Z)) continue;
+    XYZZ<BPR> q;                                   // Jacobian (X, Y, Z) -> XYZZ (X, Y, Z^2, Z^3)
+    q.x = X; q.y = Y; q.zz = fe_sqr(Z); q.zzz = fe_mul(q.zz, Z);
+    xyzz_add(acc, q);
+  }
+  Fe<BPR> X, Y, Z;
+  if (xyzz_is_identity(acc)) { X = fe_zero<BPR>(); Y = X; Z = X; }
+  else {
+    Fe<BPR> inv = fe_inv(fe_mul(acc.zz, acc.zzz));
+    X = fe_mul(acc.x, fe_mul(inv, acc.zzz)); Y = fe_mul(acc.y, fe_mul(inv, acc.zz)); Z = fe_one<BPR>();
+  }
+  fe_store(out, X); fe_store(out + 2, Y); fe_store(out + 4, Z);
+}
+}  // namespace
+
+int trp_points_sum_impl(trp_ctx* ctx, const void* d_jac, size_t g, void* d_out) {
+  if (base_field_of(ctx->curve) == 0) points_sum_kernel<FpParams><<<1, 32, 0, ctx->stream>>>((const uint4*)d_jac, g, (uint4*)d_out);
+  else points_sum_kernel<FqParams><<<1, 32, 0, ctx->stream>>>((const uint4*)d_jac, g, (uint4*)d_out);
+  TRP_LAUNCHED(ctx);
+  return TRP_OK;
+}

@@ -1,0 +1,73 @@
+"""Multi-GPU sharding of the prover hot path: one process per GPU, torch.distributed for the plumbing.
+
+Two natural partitions, neither needs a data-path collective beyond a small gather:
+  1. column sharding   -- the ~500 per-proof columns are independent (NTT + commit): round-robin columns over ranks,
+                          all_gather the 96-byte commitments.
+  2. point-range split -- one large MSM: rank r takes points [r*n/G, (r+1)*n/G) with the matching slice of the (static,
+                          pre-sharded) bases; the G partial sums are all_gathered and added (trp_points_sum), exactly how
+                          best_multiexp combines its per-thread partial results.
+The functions take the commit / add operations as callables so the same logic runs over NCCL with the CUDA library and
+over gloo on CPU in the tests (with the oracle standing in for the device)."""
+from __future__ import annotations
+
+from typing import Callable, List, Sequence, Tuple
+
+import numpy as np
+
+
+def shard_columns(n_cols: int, world: int, rank: int) -> List[int]:
+    """round-robin: column c belongs to rank c % world"""
+    return list(range(rank, n_cols, world))
+
+
+def owner_of_column(col: int, world: int) -> Tuple[int, int]:
+    """(rank, local index) of a column under shard_columns"""
+    return col % world, col // world
+
+
+def split_point_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """[lo, hi) of rank's slice; slices differ by at most one point and cover [0, n) in rank order"""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _all_gather(t, dist):
+    import torch
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return out
+
+
+def commit_columns_sharded(columns_local, n_cols: int, commit: Callable, dist=None, device="cpu"):
+    """columns_local: this rank's columns (in shard_columns order).  Returns the (n_cols, 3, 4) uint64 commitments of ALL
+    columns in global order on every rank.  commit(cols) -> (len(cols), 3, 4) uint64."""
+    import torch
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    mine = shard_columns(n_cols, world, rank)
+    per_rank = (n_cols + world - 1) // world
+    local = np.zeros((per_rank, 3, 4), dtype=np.uint64)
+    if len(mine):
+        local[:len(mine)] = np.asarray(commit(columns_local), dtype=np.uint64).reshape(len(mine), 3, 4)
+    if world == 1:
+        return local[:n_cols]
+    t = torch.from_numpy(local.view(np.int64)).to(device)
+    parts = [p.cpu().numpy().view(np.uint64) for p in _all_gather(t, dist)]
+    out = np.zeros((n_cols, 3, 4), dtype=np.uint64)
+    for c in range(n_cols):
+        r, j = owner_of_column(c, world)
+        out[c] = parts[r][j]
+    return out
+
+
+def msm_point_split(scalars_local, msm_local: Callable, points_sum: Callable, dist=None, device="cpu"):
+    """scalars_local: this rank's slice of the scalars (split_point_range).  msm_local(scalars) -> (3, 4) partial sum over the
+    rank's slice of the bases; points_sum((G, 3, 4)) -> (3, 4).  Every rank returns the full MSM."""
+    import torch
+    part = np.asarray(msm_local(scalars_local), dtype=np.uint64).reshape(3, 4)
+    if dist is None or dist.get_world_size() == 1:
+        return points_sum(part.reshape(1, 3, 4))
+    t = torch.from_numpy(part.view(np.int64).copy()).to(device)
+    parts = np.stack([p.cpu().numpy().view(np.uint64) for p in _all_gather(t, dist)])
+    return points_sum(parts)
