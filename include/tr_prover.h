@@ -151,6 +151,9 @@ int trp_dev_coeff_to_coset(trp_domain* d, const uint64_t* d_coeff, uint64_t* d_o
 /* ---- glue / debug: elementwise field kernels over the ctx's scalar (field=0) or base (field=1) field ----
  * op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 sqr(a).  Host pointers.  Used by parity tests of K1 and by K7 callers. */
 int trp_field_op(trp_ctx* ctx, int which_field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+/* device-pointer form; op | 16 broadcasts ONE element at d_b over d_a (e.g. multiply a column by R^2 to enter
+ * Montgomery form, or by a challenge) */
+int trp_dev_field_op(trp_ctx* ctx, int which_field, int op, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, size_t n);
 
 /* ---- microbenchmarks used by bench.py to measure the integer-pipe roofline denominator -------------------
  * kind 0: independent 32x32+64 wide MACs with carry-out (IMAD.WIDE.U32 + carry count), 1: 32-bit IMAD,

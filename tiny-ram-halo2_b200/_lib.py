@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "trp_lagrange_to_coeff", "trp_dev_lagrange_to_coeff", "trp_coeff_to_lagrange",
     "trp_coeff_to_extended", "trp_dev_coeff_to_extended", "trp_extended_to_coeff", "trp_dev_extended_to_coeff",
     "trp_dev_quotient_eval", "trp_quotient_eval", "trp_dev_coeff_to_coset",
-    "trp_field_op", "trp_microbench",
+    "trp_field_op", "trp_dev_field_op", "trp_microbench",
 ]
 
 
@@ -101,6 +101,7 @@ def load_library():
     L.trp_quotient_eval.argtypes = [vp, vp, sz, u, vp, sz, vp, sz, vp]
     L.trp_dev_coeff_to_coset.argtypes = [vp, vp, vp, sz, u]
     L.trp_field_op.argtypes = [vp, i, i, vp, vp, vp, sz]
+    L.trp_dev_field_op.argtypes = [vp, i, i, vp, vp, vp, sz]
     L.trp_microbench.argtypes = [vp, i, i, ctypes.POINTER(ctypes.c_double)]
     _lib = L
     return L

@@ -459,6 +459,16 @@ int trp_field_op(trp_ctx* ctx, int which_field, int op, const uint64_t* a, const
   return TRP_OK;
 }
 
+int trp_dev_field_op(trp_ctx* ctx, int which_field, int op, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, size_t n) {
+  if (!ctx) return TRP_E_INVALID;
+  Locked l(ctx);
+  if (n == 0) return TRP_OK;
+  if (!d_a || !d_out || op < 0 || (op & 15) > 4 || op > 20) TRP_FAIL(ctx, TRP_E_INVALID, "bad argument");
+  if (((op & 15) <= 2) && !d_b) TRP_FAIL(ctx, TRP_E_INVALID, "binary op needs b");
+  int field = which_field == 0 ? scalar_field_of(ctx->curve) : base_field_of(ctx->curve);
+  return trp_field_op_impl(ctx, field, op, d_a, d_b, d_out, n);
+}
+
 int trp_microbench(trp_ctx* ctx, int kind, int iters, double* out_gops) {
   if (!ctx || !out_gops) return TRP_E_INVALID;
   Locked l(ctx);

@@ -272,7 +272,9 @@ template <class PR>
 __global__ void field_op_kernel(int op, const uint4* a, const uint4* b, uint4* out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Fe<PR> x = fe_load<PR>(a + 2 * i), y = b ? fe_load<PR>(b + 2 * i) : fe_zero<PR>(), r;
+  const bool bcast = op >= 16;          // op | 16: b is ONE element applied to every a[i]
+  op &= 15;
+  Fe<PR> x = fe_load<PR>(a + 2 * i), y = b ? fe_load<PR>(b + (bcast ? 0 : 2 * i)) : fe_zero<PR>(), r;
   switch (op) {
     case 0: r = fe_add(x, y); break;
     case 1: r = fe_sub(x, y); break;

@@ -1,0 +1,146 @@
+"""create_proof@k workload model: replays, on device-resident synthetic columns
+of the TinyRAM circuit's shape (Appendix B), every hot-path call halo2_proofs' create_proof makes for one proof --
+
+  phase 2-5  497 x commit_lagrange (MSM of n + 1 points) and 497 x lagrange_to_coeff           (instance, advice,
+             lookup A'/S', permutation Z, lookup Z columns)
+  phase 7    for each of the 2^(extended_k - k) cosets: 497 x coeff_to_coset (one size-n NTT per column; the 214 fixed /
+             sigma / selector columns are keygen-time data and enter already evaluated), then the quotient program over
+             all 711 columns; extended_to_coeff with divide_by_vanishing_poly; commit of the 5 h pieces and of the random
+             blinding polynomial (6 coefficient-basis MSMs of n points)
+
+-- and reports device time per phase.  What it does NOT contain ("next" rows): witness synthesis, lookup
+permutation / grand products, the evaluations at x, multiopen and the IPA opening.  The reference itself only runs this
+path at k <= 14 on CPU (src/test_utils.rs:20); k = 20 is BASELINE.json's target configuration.
+
+Scalars follow the distribution note of SURVEY.md 8(a): instance / advice columns are 90 % {0,1}, 8 % < 2^32, 2 % full
+width; permuted lookup columns and grand products are uniform."""
+from __future__ import annotations
+
+import ctypes
+import time
+
+import numpy as np
+
+from . import poly as P
+from . import synthetic, tinyram_shape
+from ._lib import ptr
+
+_R2 = {1: [0x8c78ecb30000000f, 0xd7d30dbd8b0de0e7, 0x7797a99bc3c95d18, 0x096d41af7b9cb714],     # Fp (ctx curve VESTA)
+       0: [0xfc9678ff0000000f, 0x67bb433d891a16e3, 0x7fae231004ccf590, 0x096d41af7ccfdaa9]}     # Fq (ctx curve PALLAS)
+
+
+class CreateProofModel:
+    def __init__(self, ctx, k: int, stream, seed: int = 40, msm_batch: int = 32, scale: float = 1.0):
+        import torch
+        self.torch, self.ctx, self.k, self.n, self.stream = torch, ctx, k, 1 << k, stream
+        self.msm_batch = msm_batch
+        lib = ctx.lib
+        from .domain import EvaluationDomain
+        self.dom = EvaluationDomain(ctx, 6, k)
+        self.cosets = 1 << (self.dom.extended_k - k)
+        self.shape = tinyram_shape.build(seed, scale=scale)
+        self.ev = P.new_evaluator(ctx)
+        self.prog = P.compile_ast(self.shape.ast, self.ev.modulus)
+        g = self.shape.groups
+        per_proof = ["advice", "instance", "permutation_z", "lookup_permuted_input", "lookup_permuted_table", "lookup_z"]
+        self.proof_cols = [c for name in per_proof for c in range(g[name][0], g[name][0] + g[name][1])]
+        self.keygen_cols = [c for c in range(self.shape.n_columns) if c not in set(self.proof_cols)]
+        self.n_proof = len(self.proof_cols)
+        n, dev = self.n, "cuda"
+        gen = torch.Generator(device=dev); gen.manual_seed(seed)
+        # ---- bases: g_lagrange ++ [w] (n + 1 points) and g (n points), synthetic progressions generated on the device ------
+        pts = torch.empty((n + 1, 8), dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        synthetic.device_points(ctx, n + 1, pts.data_ptr())
+        self.h_lagrange, self.h_g = ctypes.c_void_p(), ctypes.c_void_p()
+        ctx.check(lib.trp_dev_bases_load(ctx.handle, pts.data_ptr(), n + 1, ctypes.byref(self.h_lagrange)))
+        ctx.check(lib.trp_dev_bases_load(ctx.handle, pts.data_ptr(), n, ctypes.byref(self.h_g)))
+        ctx.sync()
+        del pts
+        # ---- per-proof Lagrange columns --------------------------------------------------------------------------------------
+        n_small = g["advice"][1] + g["instance"][1]          # TinyRAM-shaped columns come first in proof_cols
+        self.lag = torch.empty((self.n_proof, n, 4), dtype=torch.int64, device=dev)
+        r2 = torch.tensor(np.array(_R2[ctx.curve], dtype=np.uint64).view(np.int64), device=dev)
+        for c in range(self.n_proof):
+            col = self.lag[c]
+            col.random_(0, 1 << 62, generator=gen)           # uniform, already a valid Montgomery representation
+            if c < n_small:
+                kind = torch.rand(n, device=dev, generator=gen)
+                small = torch.zeros((n, 4), dtype=torch.int64, device=dev)
+                small[:, 0] = torch.where(kind < 0.9, torch.randint(0, 2, (n,), device=dev, generator=gen),
+                                          torch.randint(0, 1 << 32, (n,), device=dev, generator=gen))
+                torch.cuda.synchronize()
+                ctx.check(lib.trp_dev_field_op(ctx.handle, 0, 2 | 16, small.data_ptr(), r2.data_ptr(), small.data_ptr(), n))
+                ctx.sync()
+                col.copy_(torch.where((kind < 0.98)[:, None], small, col))
+        self.blinds = torch.randint(0, 1 << 62, (self.n_proof, 4), dtype=torch.int64, device=dev, generator=gen)
+        self.keygen_coset = torch.randint(0, 1 << 62, (len(self.keygen_cols), n, 4), dtype=torch.int64, device=dev, generator=gen)
+        self.coset_buf = torch.empty((self.n_proof, n, 4), dtype=torch.int64, device=dev)
+        self.stage = torch.empty((msm_batch, n + 1, 4), dtype=torch.int64, device=dev)
+        self.commitments = torch.zeros((self.n_proof, 12), dtype=torch.int64, device=dev)
+        self.h_ext = torch.empty((n * self.cosets, 4), dtype=torch.int64, device=dev)
+        self.h_coeff = torch.randint(0, 1 << 62, (6, n, 4), dtype=torch.int64, device=dev, generator=gen)   # [5] = random poly
+        self.h_commit = torch.zeros((6, 12), dtype=torch.int64, device=dev)
+        self.coeff = torch.empty_like(self.lag)
+        ptrs = [0] * self.shape.n_columns
+        for j, c in enumerate(self.proof_cols):
+            ptrs[c] = self.coset_buf[j].data_ptr()
+        for j, c in enumerate(self.keygen_cols):
+            ptrs[c] = self.keygen_coset[j].data_ptr()
+        self.col_ptrs = ptrs
+        torch.cuda.synchronize()
+
+    def describe(self):
+        c = self.prog.counts()
+        return {"k": self.k, "per_proof_columns": self.n_proof, "keygen_columns": len(self.keygen_cols),
+                "expressions": self.shape.n_expressions, "program": c, "vm_registers": self.prog.n_regs, "cosets": self.cosets}
+
+    def prove_once(self):
+        """One pass over the hot path; returns {phase: device milliseconds} measured with CUDA events on the ctx stream."""
+        torch, ctx, lib, n, st = self.torch, self.ctx, self.ctx.lib, self.n, self.stream
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        marks = []
+
+        def mark(name):
+            e = ev(); e.record(st); marks.append((name, e))
+
+        with torch.cuda.stream(st):
+            mark("start")
+            # phases 2-5: commitments of the Lagrange-basis columns (MSM of n + 1 points each: column ++ blind)
+            for b0 in range(0, self.n_proof, self.msm_batch):
+                nb = min(self.msm_batch, self.n_proof - b0)
+                self.stage[:nb, :n].copy_(self.lag[b0:b0 + nb])
+                self.stage[:nb, n].copy_(self.blinds[b0:b0 + nb])
+                ctx.check(lib.trp_dev_msm_batch(ctx.handle, self.h_lagrange, self.stage.data_ptr(), n + 1, nb,
+                                                self.commitments[b0].data_ptr()))
+            mark("commit_lagrange")
+            self.coeff.copy_(self.lag)
+            ctx.check(lib.trp_dev_lagrange_to_coeff(self.dom.handle, self.coeff.data_ptr(), self.n_proof))
+            mark("lagrange_to_coeff")
+            t_ntt = t_vm = 0.0
+            spans = []
+            for cs in range(self.cosets):
+                a = ev(); a.record(st)
+                ctx.check(lib.trp_dev_coeff_to_coset(self.dom.handle, self.coeff.data_ptr(), self.coset_buf.data_ptr(), self.n_proof, cs))
+                b = ev(); b.record(st)
+                self.ev.evaluate_device(self.prog, self.dom, self.col_ptrs, self.h_ext.data_ptr(), coset=cs)
+                c = ev(); c.record(st)
+                spans.append((a, b, c))
+            mark("quotient_cosets")
+            ctx.check(lib.trp_dev_extended_to_coeff(self.dom.handle, self.h_ext.data_ptr(), self.h_coeff.data_ptr(), 1))
+            mark("extended_to_coeff")
+            ctx.check(lib.trp_dev_msm_batch(ctx.handle, self.h_g, self.h_coeff.data_ptr(), n, 6, self.h_commit.data_ptr()))
+            mark("commit_h")
+        torch.cuda.synchronize()
+        out = {}
+        for (_, e_prev), (name, e) in zip(marks[:-1], marks[1:]):
+            out[name + "_ms"] = e_prev.elapsed_time(e)
+        out["coset_ntt_ms"] = sum(a.elapsed_time(b) for a, b, _ in spans)
+        out["quotient_vm_ms"] = sum(b.elapsed_time(c) for _, b, c in spans)
+        out["total_ms"] = marks[0][1].elapsed_time(marks[-1][1])
+        return out
+
+    def close(self):
+        lib = self.ctx.lib
+        lib.trp_bases_free(self.h_lagrange); lib.trp_bases_free(self.h_g)
+        self.dom.free()
