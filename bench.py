@@ -363,8 +363,8 @@ def measure_extras(pkg, ctx, stream, peaks, peak_src, int_peak_tmacs):
         best = min(runs, key=lambda r: r["total_ms"])
         out["create_proof_model"] = {"k": K_LOG, "seconds": best["total_ms"] / 1e3, "phases_ms": {k: round(v, 2) for k, v in best.items()},
                                      "shape": model.describe(),
-                                     "scope": "commit_lagrange x497, lagrange_to_coeff x497, coset NTT x497x8, quotient program x8 cosets, "
-                                              "extended_to_coeff, 6 coefficient-basis commits; excludes witness synthesis, lookup/permutation "
+                                     "scope": "commit_lagrange x497, lagrange_to_coeff x497, coset NTT x497 and quotient program on 5 of the 8 cosets "
+                                              "(deg h < 5n), cosets_to_coeff, 6 coefficient-basis commits; excludes witness synthesis, lookup/permutation "
                                               "products, evaluations, multiopen/IPA (SURVEY.md 8(f))"}
         model.close()
     except Exception as e:   # e.g. not enough free HBM next to other tenants; the headline line must still print

@@ -147,6 +147,14 @@ int trp_quotient_eval(trp_domain* d, const uint32_t* program, size_t n_instr, un
 /* out[i] = p(zeta * extended_omega^(j + i * 2^(extended_k-k))) for coefficient-form columns p (n each): row j, j + 2^(..),
  * ... of coeff_to_extended, computed with ONE size-n NTT per column. */
 int trp_dev_coeff_to_coset(trp_domain* d, const uint64_t* d_coeff, uint64_t* d_out, size_t batch, unsigned coset);
+/* OR into trp_dev_quotient_eval's coset index: write the coset's n results contiguously at d_out[row] instead of
+ * interleaving them into the extended vector (input layout of trp_dev_cosets_to_coeff). */
+#define TRP_Q_CONTIGUOUS 0x10000
+/* Coefficients of a polynomial of degree < n * ncos from its values on the first ncos cosets (d_vals: ncos x n, coset i
+ * at d_vals[i * n ..]; consumed).  With divide_by_vanishing the values are first divided by X^n - 1.  Equals
+ * extended_to_coeff(divide_by_vanishing_poly(h_ext)) while only ncos = j - 1 of the 2^(extended_k - k) cosets are ever
+ * evaluated: the quotient h(X) is unique, so commitments and proof bytes are unchanged. */
+int trp_dev_cosets_to_coeff(trp_domain* d, uint64_t* d_vals, unsigned ncos, uint64_t* d_out_coeff, int divide_by_vanishing);
 
 /* ---- glue / debug: elementwise field kernels over the ctx's scalar (field=0) or base (field=1) field ----
  * op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 sqr(a).  Host pointers.  Used by parity tests of K1 and by K7 callers. */

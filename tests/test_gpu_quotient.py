@@ -169,3 +169,76 @@ def test_malformed_programs_are_rejected(pkg, P, ctxs):
     assert run([[P.CONST, 0, 3, 0], [P.STORE, 0, 0, 0]]) == -1         # constant out of range
     assert run([[99, 0, 0, 0], [P.STORE, 0, 0, 0]]) == -1              # unknown opcode
     assert run([[P.LOAD, 0, 0, 0]]) == -1                              # never stores
+
+
+@pytest.mark.parametrize("j,k", [(3, 4), (6, 5), (6, 11), (9, 6), (2, 3), (5, 12)])
+def test_cosets_to_coeff(pkg, ctxs, j, k):
+    """values of a degree < n(j-1) polynomial on the first j-1 cosets -> its coefficients (the reduced-coset form of
+    extended_to_coeff . divide_by_vanishing_poly); the oracle's full-extended-domain evaluation supplies the coset values."""
+    import torch
+    ctx = ctxs[O.VESTA]
+    field, F = O.FP, pm.Fp
+    dom = pkg.EvaluationDomain(ctx, j, k)
+    dom_m = pm.EvaluationDomain(F, j, k)
+    n, EN, Q = 1 << k, dom.extended_len(), j - 1
+    period = EN // n
+    a = O.random_field_mont(field, Q * n, 80 + k)                         # coefficients of h, degree < Q n
+    zeta_pows = np.stack([O.to_mont(field, O.ints_to_limbs([1]))[0], dom.g_coset, dom.g_coset_inv])
+    scaled = ctx.field_op("mul", a, zeta_pows[np.arange(Q * n) % 3])
+    padded = np.zeros((EN, 4), dtype=np.uint64); padded[:Q * n] = scaled
+    h_ext = O.fft(field, padded, dom.extended_k, dom.extended_omega)      # h(zeta * ext_omega^r), oracle
+    vals = np.stack([h_ext[i::period] for i in range(Q)])                 # (Q, n, 4)
+    d_vals = torch.from_numpy(vals.view(np.int64)).cuda()
+    d_out = torch.zeros((Q * n, 4), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.check(ctx.lib.trp_dev_cosets_to_coeff(dom.handle, d_vals.data_ptr(), Q, d_out.data_ptr(), 0))
+    ctx.sync()
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64), a)
+    # numerator form: N = h * (X^n - 1), constant gamma_i - 1 on coset i; divide_by_vanishing undoes it
+    num = vals.copy()
+    for i in range(Q):
+        gamma = pow(dom_m.g_coset * pow(dom_m.extended_omega, i, F.p) % F.p, n, F.p)
+        c = np.tile(O.to_mont(field, O.ints_to_limbs([(gamma - 1) % F.p])), (n, 1))
+        num[i] = ctx.field_op("mul", vals[i], c)
+    d_vals = torch.from_numpy(num.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    ctx.check(ctx.lib.trp_dev_cosets_to_coeff(dom.handle, d_vals.data_ptr(), Q, d_out.data_ptr(), 1))
+    ctx.sync()
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64), a)
+    # and it agrees with the full-domain route through the library: extended_to_coeff(h_ext)
+    assert np.array_equal(dom.extended_to_coeff(h_ext), a)
+    assert ctx.lib.trp_dev_cosets_to_coeff(dom.handle, d_vals.data_ptr(), period + 1, d_out.data_ptr(), 0) == -1
+
+
+def test_reduced_coset_quotient_pipeline(pkg, P, ctxs):
+    """device-resident quotient, reduced form: 5 of the 8 cosets (coeff_to_coset -> program with contiguous output) and
+    cosets_to_coeff give the same h coefficients as evaluating the whole extended domain and calling extended_to_coeff."""
+    import torch
+    from tiny_ram_halo2_b200._lib import Q_CONTIGUOUS
+    ctx = ctxs[O.VESTA]
+    field, j, k = O.FP, 6, 7
+    dom = pkg.EvaluationDomain(ctx, j, k)
+    n, Q = 1 << k, j - 1
+    lag = O.random_field_mont(field, 3 * n, 5).reshape(3, n, 4)
+    lag[2] = ctx.field_op("mul", lag[0], lag[1])                          # c = a * b on every row => a*b - c vanishes on H
+    sel = O.random_field_mont(field, n, 6)
+    coeff = dom.lagrange_to_coeff(np.concatenate([lag, sel.reshape(1, n, 4)]))
+    A, B, C, S = (P.Poly(i) for i in range(4))
+    ast = S * S * S * (A * B - C) * (A.with_rotation(1) + 7)              # degree 6 numerator, divisible by X^n - 1
+    ev = P.new_evaluator(ctx)
+    ext = dom.coeff_to_extended(coeff)
+    for c in range(4):
+        ev.register_poly(ext[c])
+    want = dom.extended_to_coeff(ev.evaluate(ast, dom), divide_by_vanishing_poly=True)
+    prog = ev.compile(ast)
+    d_coeff = torch.from_numpy(coeff.view(np.int64)).cuda()
+    d_coset = torch.empty_like(d_coeff)
+    d_vals = torch.zeros((Q, n, 4), dtype=torch.int64, device="cuda")
+    d_out = torch.zeros((Q * n, 4), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    for cs in range(Q):
+        ctx.check(ctx.lib.trp_dev_coeff_to_coset(dom.handle, d_coeff.data_ptr(), d_coset.data_ptr(), 4, cs))
+        ev.evaluate_device(prog, dom, [d_coset[c].data_ptr() for c in range(4)], d_vals[cs].data_ptr(), coset=cs | Q_CONTIGUOUS)
+    ctx.check(ctx.lib.trp_dev_cosets_to_coeff(dom.handle, d_vals.data_ptr(), Q, d_out.data_ptr(), 1))
+    ctx.sync()
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64), want)

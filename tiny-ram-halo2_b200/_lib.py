@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libtrp.so")
 
 PALLAS, VESTA = 0, 1
+Q_CONTIGUOUS = 0x10000
 
 TRP_OK, TRP_E_INVALID, TRP_E_CUDA, TRP_E_OOM, TRP_E_NODEVICE = 0, -1, -2, -3, -4
 _ERR_NAMES = {-1: "TRP_E_INVALID", -2: "TRP_E_CUDA", -3: "TRP_E_OOM", -4: "TRP_E_NODEVICE"}
@@ -25,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "trp_domain_create", "trp_domain_free", "trp_domain_extended_k", "trp_domain_constants",
     "trp_lagrange_to_coeff", "trp_dev_lagrange_to_coeff", "trp_coeff_to_lagrange",
     "trp_coeff_to_extended", "trp_dev_coeff_to_extended", "trp_extended_to_coeff", "trp_dev_extended_to_coeff",
-    "trp_dev_quotient_eval", "trp_quotient_eval", "trp_dev_coeff_to_coset",
+    "trp_dev_quotient_eval", "trp_quotient_eval", "trp_dev_coeff_to_coset", "trp_dev_cosets_to_coeff",
     "trp_field_op", "trp_dev_field_op", "trp_microbench",
 ]
 
@@ -100,6 +101,7 @@ def load_library():
     L.trp_dev_quotient_eval.argtypes = [vp, vp, sz, u, vp, sz, vp, sz, i, vp]
     L.trp_quotient_eval.argtypes = [vp, vp, sz, u, vp, sz, vp, sz, vp]
     L.trp_dev_coeff_to_coset.argtypes = [vp, vp, vp, sz, u]
+    L.trp_dev_cosets_to_coeff.argtypes = [vp, vp, u, vp, i]
     L.trp_field_op.argtypes = [vp, i, i, vp, vp, vp, sz]
     L.trp_dev_field_op.argtypes = [vp, i, i, vp, vp, vp, sz]
     L.trp_microbench.argtypes = [vp, i, i, ctypes.POINTER(ctypes.c_double)]

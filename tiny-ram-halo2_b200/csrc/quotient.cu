@@ -38,7 +38,7 @@ struct QParams {
   unsigned n_instr, n_regs;
   const uint4* consts;
   const uint4* const* cols;
-  unsigned rows_log, step, out_stride, out_off, ext_log;
+  unsigned rows_log, step, out_stride, out_off, x_stride, x_off, ext_log;
   const uint4* tw_ext;   // ext_omega^i, i < 2^(ext_log-1)
   uint4* out;
 };
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) quotient_vm_kernel(QParams p, Fe<PR> zeta
       case Q_SQR: wr(ins.y, fe_sqr(rd(ins.z))); break;
       case Q_DBL: wr(ins.y, fe_dbl(rd(ins.z))); break;
       case Q_COSETX: {
-        unsigned g = row * p.out_stride + p.out_off;
+        unsigned g = row * p.x_stride + p.x_off;
         unsigned half = 1u << (p.ext_log - 1);
         Fe<PR> w = fe_load_ro<PR>(p.tw_ext + 2 * (size_t)(g & (half - 1)));
         if (g & half) w = fe_neg(w);
@@ -126,8 +126,13 @@ int launch_vm(trp_domain* d, const uint4* d_prog, size_t n_instr, unsigned n_reg
   p.prog = d_prog; p.n_instr = (unsigned)n_instr; p.n_regs = n_regs; p.consts = d_consts; p.cols = d_cols_dev;
   p.ext_log = d->ext_k;
   const unsigned period = 1u << (d->ext_k - d->k);
-  if (coset < 0) { p.rows_log = d->ext_k; p.step = period; p.out_stride = 1; p.out_off = 0; }
-  else { p.rows_log = d->k; p.step = 1; p.out_stride = period; p.out_off = (unsigned)coset; }
+  const bool contiguous = coset >= 0 && (coset & TRP_Q_CONTIGUOUS);
+  if (coset >= 0) coset &= ~TRP_Q_CONTIGUOUS;
+  if (coset < 0) { p.rows_log = d->ext_k; p.step = period; p.out_stride = 1; p.out_off = 0; p.x_stride = 1; p.x_off = 0; }
+  else {
+    p.rows_log = d->k; p.step = 1; p.x_stride = period; p.x_off = (unsigned)coset;
+    p.out_stride = contiguous ? 1 : period; p.out_off = contiguous ? 0 : (unsigned)coset;
+  }
   const void* tw = nullptr;
   TRP_TRY(trp_get_powers(ctx, d->field, d->ext_k, d->ext_omega, &tw));
   p.tw_ext = (const uint4*)tw;
@@ -150,6 +155,89 @@ int launch_vm(trp_domain* d, const uint4* d_prog, size_t n_instr, unsigned n_reg
     return TRP_OK;
   };
   return d->field == 0 ? go(FpParams()) : go(FqParams());
+}
+
+// out[q * n + t] = sum_i A[q][i] * P[i * n + t]   (Q x Q constant matrix applied to every coefficient index)
+template <class PR>
+__global__ void cosets_combine_kernel(const uint4* P, const uint4* A, unsigned Q, size_t n, uint4* out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  for (unsigned q = 0; q < Q; ++q) {
+    Fe<PR> acc = fe_mul(fe_load<PR>(P + 2 * t), fe_load_ro<PR>(A + 2 * (size_t)(q * Q)));
+    for (unsigned i = 1; i < Q; ++i)
+      acc = fe_add(acc, fe_mul(fe_load<PR>(P + 2 * (i * n + t)), fe_load_ro<PR>(A + 2 * (size_t)(q * Q + i))));
+    fe_store(out + 2 * (q * n + t), acc);
+  }
+}
+
+// A' = V^-1 * diag(1 / ((gamma_i - 1) n))  (or diag(1/n) without the vanishing division), V[i][q] = gamma_i^q,
+// gamma_i = (zeta * ext_omega^i)^n; host-side field arithmetic (ff.cuh compiles for the host)
+template <class PR>
+int build_combine_matrix(trp_domain* d, unsigned Q, int divide, std::vector<Fe<PR>>& out) {
+  auto from64 = [](const uint64_t* l) { Fe<PR> r; for (int i = 0; i < 4; ++i) { r.v[2 * i] = (uint32_t)l[i]; r.v[2 * i + 1] = (uint32_t)(l[i] >> 32); } return r; };
+  const uint64_t n = 1ULL << d->k;
+  uint32_t e[2] = {(uint32_t)n, (uint32_t)(n >> 32)};
+  const Fe<PR> one = fe_one<PR>();
+  std::vector<Fe<PR>> gamma(Q), M(Q * 2 * Q);
+  for (unsigned i = 0; i < Q; ++i) gamma[i] = fe_pow(from64(d->coset_gen[i]), e, 2);
+  // Gauss-Jordan on [V | I]
+  for (unsigned i = 0; i < Q; ++i) {
+    Fe<PR> pw = one;
+    for (unsigned q = 0; q < Q; ++q) { M[i * 2 * Q + q] = pw; pw = fe_mul(pw, gamma[i]); M[i * 2 * Q + Q + q] = (q == i) ? one : fe_zero<PR>(); }
+  }
+  for (unsigned c = 0; c < Q; ++c) {
+    unsigned piv = c;
+    while (piv < Q && fe_is_zero(M[piv * 2 * Q + c])) ++piv;
+    if (piv == Q) TRP_FAIL(d->ctx, TRP_E_INVALID, "internal: singular coset Vandermonde matrix");
+    if (piv != c) for (unsigned x = 0; x < 2 * Q; ++x) std::swap(M[piv * 2 * Q + x], M[c * 2 * Q + x]);
+    Fe<PR> inv = fe_inv(M[c * 2 * Q + c]);
+    for (unsigned x = 0; x < 2 * Q; ++x) M[c * 2 * Q + x] = fe_mul(M[c * 2 * Q + x], inv);
+    for (unsigned r = 0; r < Q; ++r) {
+      if (r == c || fe_is_zero(M[r * 2 * Q + c])) continue;
+      Fe<PR> f = M[r * 2 * Q + c];
+      for (unsigned x = 0; x < 2 * Q; ++x) M[r * 2 * Q + x] = fe_sub(M[r * 2 * Q + x], fe_mul(f, M[c * 2 * Q + x]));
+    }
+  }
+  Fe<PR> nf = fe_zero<PR>(); nf.v[d->k >> 5] = 1u << (d->k & 31);
+  const Fe<PR> ninv = fe_inv(fe_to_mont(nf));
+  out.resize(Q * Q);
+  for (unsigned i = 0; i < Q; ++i) {
+    Fe<PR> s = ninv;
+    if (divide) s = fe_mul(s, fe_inv(fe_sub(gamma[i], one)));
+    for (unsigned q = 0; q < Q; ++q) out[q * Q + i] = fe_mul(M[q * 2 * Q + Q + i], s);   // (V^-1)[q][i] * s_i
+  }
+  return TRP_OK;
+}
+
+template <class PR>
+int cosets_to_coeff_run(trp_domain* d, uint64_t* d_vals, unsigned Q, uint64_t* d_out, int divide) {
+  trp_ctx* ctx = d->ctx;
+  const size_t n = (size_t)1 << d->k;
+  std::vector<Fe<PR>> A;
+  TRP_TRY(build_combine_matrix<PR>(d, Q, divide, A));
+  const bool need_tmp = trp_ntt_passes(d->k) > 1;
+  const size_t a_bytes = ws_align((size_t)Q * Q * 32);
+  TRP_TRY(trp_ws_reserve(ctx, a_bytes + (need_tmp ? n * 32 : 0)));
+  char* w = (char*)ctx->ws;
+  TRP_CUDA(ctx, cudaMemcpyAsync(w, A.data(), (size_t)Q * Q * 32, cudaMemcpyHostToDevice, ctx->stream));
+  TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // A is a local
+  for (unsigned i = 0; i < Q; ++i) {
+    // P'_i[t] = c_i^-t * iNTT_omega(values)[t]: the coset-i remainder h mod (X^n - gamma_i), up to the factors folded into A
+    uint64_t cinv[4];
+    {
+      Fe<PR> c; for (int l = 0; l < 4; ++l) { c.v[2 * l] = (uint32_t)d->coset_gen[i][l]; c.v[2 * l + 1] = (uint32_t)(d->coset_gen[i][l] >> 32); }
+      Fe<PR> ci = fe_inv(c);
+      for (int l = 0; l < 4; ++l) cinv[l] = (uint64_t)ci.v[2 * l] | ((uint64_t)ci.v[2 * l + 1] << 32);
+    }
+    const void* post = nullptr;
+    TRP_TRY(trp_get_powers(ctx, d->field, d->k + 1, cinv, &post));
+    uint64_t* v = d_vals + 4 * (size_t)i * n;
+    TRP_TRY(trp_ntt_impl(ctx, d->field, v, v, 1, d->k, d->omega_inv, n, n, (unsigned)n, nullptr, 0, post, (unsigned)n, (unsigned)n,
+                         need_tmp ? w + a_bytes : nullptr));
+  }
+  cosets_combine_kernel<PR><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint4*)d_vals, (const uint4*)w, Q, n, (uint4*)d_out);
+  TRP_LAUNCHED(ctx);
+  return TRP_OK;
 }
 
 struct Locked {
@@ -182,7 +270,8 @@ int trp_dev_quotient_eval(trp_domain* d, const uint32_t* program, size_t n_instr
   trp_ctx* ctx = d->ctx;
   Locked l(ctx);
   if (!program || !n_instr || !d_out || (n_consts && !consts) || (n_cols && !d_cols)) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
-  if (n_regs == 0 || coset >= (int)(1u << (d->ext_k - d->k))) TRP_FAIL(ctx, TRP_E_INVALID, "bad register count or coset index");
+  if (n_regs == 0 || (coset >= 0 && (coset & ~TRP_Q_CONTIGUOUS) >= (int)(1u << (d->ext_k - d->k))))
+    TRP_FAIL(ctx, TRP_E_INVALID, "bad register count or coset index");
   TRP_TRY(validate_program(ctx, program, n_instr, n_regs, n_consts, n_cols));
   for (size_t c = 0; c < n_cols; ++c) if (!d_cols[c]) TRP_FAIL(ctx, TRP_E_INVALID, "column %zu is NULL", c);
   char* after = nullptr;
@@ -249,6 +338,22 @@ int trp_dev_coeff_to_coset(trp_domain* d, const uint64_t* d_coeff, uint64_t* d_o
                          (unsigned)n, nullptr, 0, (unsigned)n, need_tmp ? ctx->ws : nullptr));
   }
   return TRP_OK;
+}
+
+// Recover the n * ncos coefficients of a polynomial of degree < n * ncos from its values on the first ncos size-n cosets
+// (zeta * ext_omega^i) * <omega>, i < ncos: per coset an inverse NTT gives h mod (X^n - gamma_i), and one ncos x ncos
+// constant matrix (inverse Vandermonde in gamma_i = (zeta ext_omega^i)^n) applied per coefficient index undoes the
+// wrap-around.  With divide_by_vanishing the input is the quotient NUMERATOR and is divided by X^n - 1 (the constant
+// gamma_i - 1 on coset i).  Produces exactly extended_to_coeff(divide_by_vanishing_poly(.)) of the full extended
+// domain while evaluating only ncos = j - 1 of its 2^(ext_k - k) cosets (5 of 8 for the TinyRAM circuit).
+int trp_dev_cosets_to_coeff(trp_domain* d, uint64_t* d_vals, unsigned ncos, uint64_t* d_out_coeff, int divide_by_vanishing) {
+  if (!d) return TRP_E_INVALID;
+  trp_ctx* ctx = d->ctx;
+  Locked l(ctx);
+  if (!d_vals || !d_out_coeff) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
+  if (ncos == 0 || ncos > (1u << (d->ext_k - d->k))) TRP_FAIL(ctx, TRP_E_INVALID, "ncos = %u out of range", ncos);
+  return d->field == 0 ? cosets_to_coeff_run<FpParams>(d, d_vals, ncos, d_out_coeff, divide_by_vanishing)
+                       : cosets_to_coeff_run<FqParams>(d, d_vals, ncos, d_out_coeff, divide_by_vanishing);
 }
 
 }  // extern "C"

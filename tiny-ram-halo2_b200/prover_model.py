@@ -23,21 +23,24 @@ import numpy as np
 
 from . import poly as P
 from . import synthetic, tinyram_shape
-from ._lib import ptr
+from ._lib import ptr, Q_CONTIGUOUS
 
 _R2 = {1: [0x8c78ecb30000000f, 0xd7d30dbd8b0de0e7, 0x7797a99bc3c95d18, 0x096d41af7b9cb714],     # Fp (ctx curve VESTA)
        0: [0xfc9678ff0000000f, 0x67bb433d891a16e3, 0x7fae231004ccf590, 0x096d41af7ccfdaa9]}     # Fq (ctx curve PALLAS)
 
 
 class CreateProofModel:
-    def __init__(self, ctx, k: int, stream, seed: int = 40, msm_batch: int = 32, scale: float = 1.0):
+    def __init__(self, ctx, k: int, stream, seed: int = 40, msm_batch: int = 32, scale: float = 1.0, reduced_cosets: bool = True):
         import torch
         self.torch, self.ctx, self.k, self.n, self.stream = torch, ctx, k, 1 << k, stream
         self.msm_batch = msm_batch
         lib = ctx.lib
         from .domain import EvaluationDomain
         self.dom = EvaluationDomain(ctx, 6, k)
-        self.cosets = 1 << (self.dom.extended_k - k)
+        # the quotient has degree < 5n: 5 of the 8 cosets determine it (trp_dev_cosets_to_coeff); reduced_cosets=False
+        # replays halo2's own data flow (all 2^(extended_k-k) cosets, then extended_to_coeff)
+        self.reduced = reduced_cosets
+        self.cosets = (self.dom.j - 1) if reduced_cosets else 1 << (self.dom.extended_k - k)
         self.shape = tinyram_shape.build(seed, scale=scale)
         self.ev = P.new_evaluator(ctx)
         self.prog = P.compile_ast(self.shape.ast, self.ev.modulus)
@@ -78,7 +81,7 @@ class CreateProofModel:
         self.coset_buf = torch.empty((self.n_proof, n, 4), dtype=torch.int64, device=dev)
         self.stage = torch.empty((msm_batch, n + 1, 4), dtype=torch.int64, device=dev)
         self.commitments = torch.zeros((self.n_proof, 12), dtype=torch.int64, device=dev)
-        self.h_ext = torch.empty((n * self.cosets, 4), dtype=torch.int64, device=dev)
+        self.h_ext = torch.empty((self.cosets, n, 4), dtype=torch.int64, device=dev)
         self.h_coeff = torch.randint(0, 1 << 62, (6, n, 4), dtype=torch.int64, device=dev, generator=gen)   # [5] = random poly
         self.h_commit = torch.zeros((6, 12), dtype=torch.int64, device=dev)
         self.coeff = torch.empty_like(self.lag)
@@ -93,7 +96,8 @@ class CreateProofModel:
     def describe(self):
         c = self.prog.counts()
         return {"k": self.k, "per_proof_columns": self.n_proof, "keygen_columns": len(self.keygen_cols),
-                "expressions": self.shape.n_expressions, "program": c, "vm_registers": self.prog.n_regs, "cosets": self.cosets}
+                "expressions": self.shape.n_expressions, "program": c, "vm_registers": self.prog.n_regs, "cosets_evaluated": self.cosets,
+                "cosets_in_extended_domain": 1 << (self.dom.extended_k - self.k)}
 
     def prove_once(self):
         """One pass over the hot path; returns {phase: device milliseconds} measured with CUDA events on the ctx stream."""
@@ -123,11 +127,17 @@ class CreateProofModel:
                 a = ev(); a.record(st)
                 ctx.check(lib.trp_dev_coeff_to_coset(self.dom.handle, self.coeff.data_ptr(), self.coset_buf.data_ptr(), self.n_proof, cs))
                 b = ev(); b.record(st)
-                self.ev.evaluate_device(self.prog, self.dom, self.col_ptrs, self.h_ext.data_ptr(), coset=cs)
+                if self.reduced:
+                    self.ev.evaluate_device(self.prog, self.dom, self.col_ptrs, self.h_ext[cs].data_ptr(), coset=cs | Q_CONTIGUOUS)
+                else:
+                    self.ev.evaluate_device(self.prog, self.dom, self.col_ptrs, self.h_ext.data_ptr(), coset=cs)
                 c = ev(); c.record(st)
                 spans.append((a, b, c))
             mark("quotient_cosets")
-            ctx.check(lib.trp_dev_extended_to_coeff(self.dom.handle, self.h_ext.data_ptr(), self.h_coeff.data_ptr(), 1))
+            if self.reduced:
+                ctx.check(lib.trp_dev_cosets_to_coeff(self.dom.handle, self.h_ext.data_ptr(), self.cosets, self.h_coeff.data_ptr(), 1))
+            else:
+                ctx.check(lib.trp_dev_extended_to_coeff(self.dom.handle, self.h_ext.data_ptr(), self.h_coeff.data_ptr(), 1))
             mark("extended_to_coeff")
             ctx.check(lib.trp_dev_msm_batch(ctx.handle, self.h_g, self.h_coeff.data_ptr(), n, 6, self.h_commit.data_ptr()))
             mark("commit_h")
