@@ -148,6 +148,8 @@ void trp_ctx_destroy(trp_ctx* ctx) {
   for (auto& t : ctx->twiddles) cudaFree(t.d_tab);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (auto& e : ctx->copy_ev) if (e) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -255,10 +257,29 @@ int trp_msm_batch(trp_ctx* ctx, const trp_bases* bases, const uint64_t* scalars,
   char* ws = (char*)ctx->ws;
   char* d_sc = ws; char* d_out = ws + cols * col_bytes; char* d_msm = d_out + out_bytes;
   size_t msm_cap = ctx->ws_bytes - (size_t)(d_msm - ws);
+  if (!ctx->copy_stream) {
+    TRP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->copy_ev) TRP_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   for (size_t k0 = 0; k0 < m; k0 += cols) {
     size_t nk = m - k0 < cols ? m - k0 : cols;
-    if (n) TRP_CUDA(ctx, cudaMemcpyAsync(d_sc, scalars + 4 * k0 * n, nk * n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    TRP_TRY(trp_msm_impl(ctx, bases, d_sc, n, nk, d_out + 96 * k0, d_msm, msm_cap));
+    // upload on the copy stream in two parts (1 column, then the rest): the first column's kernels start as soon as it has
+    // landed and hide the upload of the others (PCIe moves a column ~5x faster than the GPU consumes it)
+    size_t part[2] = {nk >= 3 ? 1 : nk, nk >= 3 ? nk - 1 : 0};
+    TRP_CUDA(ctx, cudaEventRecord(ctx->copy_ev[2], ctx->stream));           // staging area is free once earlier work is done
+    TRP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[2], 0));
+    size_t c0 = 0;
+    for (int p = 0; p < 2 && part[p]; ++p) {
+      if (n) TRP_CUDA(ctx, cudaMemcpyAsync(d_sc + c0 * n * 32, scalars + 4 * (k0 + c0) * n, part[p] * n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+      TRP_CUDA(ctx, cudaEventRecord(ctx->copy_ev[p], ctx->copy_stream));
+      c0 += part[p];
+    }
+    c0 = 0;
+    for (int p = 0; p < 2 && part[p]; ++p) {
+      TRP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[p], 0));
+      TRP_TRY(trp_msm_impl(ctx, bases, d_sc + c0 * n * 32, n, part[p], d_out + 96 * (k0 + c0), d_msm, msm_cap));
+      c0 += part[p];
+    }
   }
   TRP_CUDA(ctx, cudaMemcpyAsync(out_jacobian, d_out, m * 96, cudaMemcpyDeviceToHost, ctx->stream));
   TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -30,6 +30,9 @@ struct trp_ctx {
   int curve = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  // host->device staging runs on its own stream so that uploads overlap the kernels of the previous chunk
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[3] = {nullptr, nullptr, nullptr};
   std::string err;
   std::mutex mu;
   uint64_t launches = 0;
