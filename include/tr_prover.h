@@ -59,7 +59,8 @@ uint64_t trp_ctx_launch_count(const trp_ctx* ctx);
 const char* trp_version(void);
 /* Per-phase device timing with CUDA events on the ctx stream (off by default; a few microseconds per span).
  * phase: 0 msm hist+scan+scatter, 1 msm bucket accumulation level 1 (the dominant kernel), 2 msm upper
- * reduction levels, 3 msm bucket reduce + final, 4 ntt pass kernels, 5 quotient VM kernel.
+ * reduction levels, 3 msm bucket reduce + final, 4 ntt pass kernels, 5 quotient VM kernel, 6 batch inversion / grand product /
+ * lookup permutation kernels, 7 lookup radix sort.
  * trp_prof_get synchronises the stream. */
 int trp_prof_enable(trp_ctx* ctx, int on);
 int trp_prof_reset(trp_ctx* ctx);
@@ -155,6 +156,42 @@ int trp_dev_coeff_to_coset(trp_domain* d, const uint64_t* d_coeff, uint64_t* d_o
  * extended_to_coeff(divide_by_vanishing_poly(h_ext)) while only ncos = j - 1 of the 2^(extended_k - k) cosets are ever
  * evaluated: the quotient h(X) is unique, so commitments and proof bytes are unchanged. */
 int trp_dev_cosets_to_coeff(trp_domain* d, uint64_t* d_vals, unsigned ncos, uint64_t* d_out_coeff, int divide_by_vanishing);
+
+/* ---- between the hot kernels: the grand products and the lookup permutation of create_proof -------
+ * halo2_proofs 0.2.0 plonk/permutation/prover.rs (Argument::commit), plonk/lookup/prover.rs (Argument::commit_permuted,
+ * Permuted::commit_product) and ff::BatchInvert.  which_field as in trp_field_op (0 = scalar field of the ctx's curve).
+ * Blinding rows are the caller's (its RNG): overwrite the tail of z / the permuted columns after the call.              */
+/* out[i] = mul[i] / a[i] (d_mul == NULL: 1 / a[i]); a[i] == 0 gives 0, as ff::BatchInvert leaves zeros alone.  out may alias a. */
+int trp_dev_batch_invert(trp_ctx* ctx, int which_field, const uint64_t* d_a, const uint64_t* d_mul, uint64_t* d_out, size_t n);
+int trp_batch_invert(trp_ctx* ctx, int which_field, uint64_t* a /* in place */, size_t n);
+/* z[0] = init (NULL: 1), z[i] = z[i-1] * v[i-1] for i < n_out <= n_in + 1.  z may alias v. */
+int trp_dev_grand_product(trp_ctx* ctx, int which_field, const uint64_t* d_v, size_t n_in, const uint64_t* d_init /* device, 1 elem */,
+                          uint64_t* d_z, size_t n_out);
+int trp_grand_product(trp_ctx* ctx, int which_field, const uint64_t* v, size_t n_in, const uint64_t init[4], uint64_t* z, size_t n_out);
+/* One chunk (m <= 16 columns; halo2 uses cs_degree - 2) of permutation::Argument::commit: z[0] = last_z (NULL: 1),
+ *   z[r+1] = z[r] * prod_c (v_c[r] + delta_beta[c] * omega^r + gamma) / prod_c (v_c[r] + beta * sigma_c[r] + gamma),  r + 1 < n,
+ * delta_beta[c] = beta * DELTA^(index of column c in the whole argument).  d_last_z is a DEVICE pointer so that chunks chain
+ * without a host round trip (pass &z_prev[n - (blinding_factors + 1)]). */
+int trp_dev_permutation_product(trp_domain* d, const uint64_t* const* d_values /* host array of m device ptrs */,
+                                const uint64_t* const* d_sigmas, size_t m, const uint64_t beta[4], const uint64_t gamma[4],
+                                const uint64_t* delta_beta /* m x 4 */, const uint64_t* d_last_z, uint64_t* d_z /* n */);
+int trp_permutation_product(trp_domain* d, const uint64_t* const* values, const uint64_t* const* sigmas, size_t m,
+                            const uint64_t beta[4], const uint64_t gamma[4], const uint64_t* delta_beta, const uint64_t last_z[4],
+                            uint64_t* z);
+/* lookup::Permuted::commit_product: z[0] = 1, z[r+1] = z[r] * (a[r] + beta)(s[r] + gamma) / ((a'[r] + beta)(s'[r] + gamma)),
+ * r + 1 < n_out <= n; a, s = compressed input / table expressions, a', s' = their permuted forms (all n values). */
+int trp_dev_lookup_product(trp_domain* d, const uint64_t* d_input, const uint64_t* d_table, const uint64_t* d_perm_input,
+                           const uint64_t* d_perm_table, const uint64_t beta[4], const uint64_t gamma[4], uint64_t* d_z, size_t n_out);
+int trp_lookup_product(trp_domain* d, const uint64_t* input, const uint64_t* table, const uint64_t* perm_input,
+                       const uint64_t* perm_table, const uint64_t beta[4], const uint64_t gamma[4], uint64_t* z, size_t n_out);
+/* lookup::prover::permute_expression_pair over the first `rows` (= usable) rows of the compressed input / table expressions
+ * (scalar field): perm_input = input sorted by canonical value; perm_table[r] = perm_input[r] at every first occurrence,
+ * the left-over table values (ascending) fill the repeated rows from the end.  *all_found = 0 when some input value is
+ * absent from the table (halo2 returns Error::ConstraintSystemFailure).  Synchronises the ctx stream. */
+int trp_dev_permute_expression_pair(trp_ctx* ctx, const uint64_t* d_input, const uint64_t* d_table, size_t rows,
+                                    uint64_t* d_perm_input, uint64_t* d_perm_table, int* all_found);
+int trp_permute_expression_pair(trp_ctx* ctx, const uint64_t* input, const uint64_t* table, size_t rows, uint64_t* perm_input,
+                                uint64_t* perm_table, int* all_found);
 
 /* ---- glue / debug: elementwise field kernels over the ctx's scalar (field=0) or base (field=1) field ----
  * op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 sqr(a).  Host pointers.  Used by parity tests of K1 and by K7 callers. */

@@ -461,3 +461,92 @@ def run_program(dom: EvaluationDomain, code, consts, polys, coset=-1):
             elif op == 12: regs[dst] = (regs[a] - consts[b]) % p
             else: raise ValueError(f"bad opcode {op}")
     return out
+
+
+# ---- the field work between the hot kernels (halo2_proofs 0.2.0, restated from the published
+# source as remembered; the reference reaches it through create_proof, src/test_utils.rs:41,96) ------------------------------
+def batch_invert(F: Field, vals):
+    """ff::BatchInvert: Montgomery's trick over the NON-ZERO entries; zeros are left untouched."""
+    acc, prefix = 1, []
+    for v in vals:
+        prefix.append(acc)
+        if v != 0:
+            acc = acc * v % F.p
+    inv = F.inv(acc)
+    out = list(vals)
+    for i in range(len(vals) - 1, -1, -1):
+        if vals[i] == 0:
+            continue
+        out[i] = inv * prefix[i] % F.p
+        inv = inv * vals[i] % F.p
+    return out
+
+
+def permutation_commit(F: Field, omega, n, values, permutations, beta, gamma, chunk_len, blinding_factors, rand):
+    """plonk::permutation::prover::Argument::commit: one grand-product column Z per chunk of `chunk_len` columns.
+    values[c] / permutations[c]: the n Lagrange values of column c and of its sigma polynomial; rand() draws a scalar
+    (blinding rows of every Z, in order).  Returns the Z columns (blind scalars / commitments are the caller's)."""
+    p = F.p
+    deltaomega, last_z, sets = 1, 1, []
+    for lo in range(0, len(values), chunk_len):
+        cols, perms = values[lo:lo + chunk_len], permutations[lo:lo + chunk_len]
+        modified = [1] * n
+        for col, perm in zip(cols, perms):
+            for i in range(n):
+                modified[i] = modified[i] * ((beta * perm[i] + gamma + col[i]) % p) % p
+        modified = batch_invert(F, modified)
+        for col in cols:
+            dw = deltaomega
+            for i in range(n):
+                modified[i] = modified[i] * ((dw * beta + gamma + col[i]) % p) % p
+                dw = dw * omega % p
+            deltaomega = deltaomega * F.DELTA % p
+        z = [last_z]
+        for row in range(1, n):
+            z.append(z[row - 1] * modified[row - 1] % p)
+        for i in range(n - blinding_factors, n):
+            z[i] = rand()
+        last_z = z[n - (blinding_factors + 1)]
+        sets.append(z)
+    return sets
+
+
+def permute_expression_pair(F: Field, input_expression, table_expression, usable_rows):
+    """plonk::lookup::prover::permute_expression_pair without the trailing blinding rows: returns
+    (permuted_input, permuted_table) over the usable rows, or None where halo2 returns ConstraintSystemFailure."""
+    permuted_input = sorted(input_expression[:usable_rows])          # Ord for Fp/Fq = canonical integer order
+    leftover = {}
+    for v in table_expression[:usable_rows]:
+        leftover[v] = leftover.get(v, 0) + 1
+    permuted_table = [0] * usable_rows
+    repeated_rows = []
+    for row, v in enumerate(permuted_input):
+        if row == 0 or v != permuted_input[row - 1]:
+            permuted_table[row] = v
+            if leftover.get(v, 0) > 0:
+                leftover[v] -= 1
+            else:
+                return None
+        else:
+            repeated_rows.append(row)
+    for coeff in sorted(leftover):                                   # BTreeMap iteration order
+        for _ in range(leftover[coeff]):
+            permuted_table[repeated_rows.pop()] = coeff
+    assert not repeated_rows
+    return permuted_input, permuted_table
+
+
+def lookup_commit_product(F: Field, n, compressed_input, compressed_table, permuted_input, permuted_table, beta, gamma,
+                          blinding_factors, rand):
+    """plonk::lookup::prover::Permuted::commit_product: the lookup grand product Z (n values, blinding tail from rand())."""
+    p = F.p
+    prod = [(beta + permuted_input[i]) * (gamma + permuted_table[i]) % p for i in range(n)]
+    prod = batch_invert(F, prod)
+    for i in range(n):
+        prod[i] = prod[i] * ((compressed_input[i] + beta) % p) % p * ((compressed_table[i] + gamma) % p) % p
+    z, state = [], 1
+    for cur in [1] + prod:
+        state = state * cur % p
+        z.append(state)
+    z = z[:n - blinding_factors] + [rand() for _ in range(blinding_factors)]
+    return z

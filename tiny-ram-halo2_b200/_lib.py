@@ -28,6 +28,9 @@ EXPORTED_SYMBOLS = [
     "trp_coeff_to_extended", "trp_dev_coeff_to_extended", "trp_extended_to_coeff", "trp_dev_extended_to_coeff",
     "trp_dev_quotient_eval", "trp_quotient_eval", "trp_dev_coeff_to_coset", "trp_dev_cosets_to_coeff",
     "trp_field_op", "trp_dev_field_op", "trp_microbench",
+    "trp_dev_batch_invert", "trp_batch_invert", "trp_dev_grand_product", "trp_grand_product",
+    "trp_dev_permutation_product", "trp_permutation_product", "trp_dev_lookup_product", "trp_lookup_product",
+    "trp_dev_permute_expression_pair", "trp_permute_expression_pair",
 ]
 
 
@@ -105,6 +108,16 @@ def load_library():
     L.trp_field_op.argtypes = [vp, i, i, vp, vp, vp, sz]
     L.trp_dev_field_op.argtypes = [vp, i, i, vp, vp, vp, sz]
     L.trp_microbench.argtypes = [vp, i, i, ctypes.POINTER(ctypes.c_double)]
+    L.trp_dev_batch_invert.argtypes = [vp, i, vp, vp, vp, sz]
+    L.trp_batch_invert.argtypes = [vp, i, vp, sz]
+    L.trp_dev_grand_product.argtypes = [vp, i, vp, sz, vp, vp, sz]
+    L.trp_grand_product.argtypes = [vp, i, vp, sz, vp, vp, sz]
+    L.trp_dev_permutation_product.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp]
+    L.trp_permutation_product.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp, vp]
+    L.trp_dev_lookup_product.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, sz]
+    L.trp_lookup_product.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, sz]
+    L.trp_dev_permute_expression_pair.argtypes = [vp, vp, vp, sz, vp, vp, ctypes.POINTER(i)]
+    L.trp_permute_expression_pair.argtypes = [vp, vp, vp, sz, vp, vp, ctypes.POINTER(i)]
     _lib = L
     return L
 
@@ -164,7 +177,7 @@ class Context:
         self.check(self.lib.trp_microbench(self.handle, kind, iters, ctypes.byref(v)))
         return v.value
 
-    PROF_PHASES = ("msm_sort", "msm_accum_l1", "msm_levels", "msm_reduce", "ntt_pass", "quotient_vm")
+    PROF_PHASES = ("msm_sort", "msm_accum_l1", "msm_levels", "msm_reduce", "ntt_pass", "quotient_vm", "products", "lookup_sort")
 
     def prof_enable(self, on=True):
         self.check(self.lib.trp_prof_enable(self.handle, int(on)))

@@ -17,7 +17,7 @@ struct TwiddleTable {
 };
 
 // optional per-phase device timing (CUDA events on the ctx stream); used by bench.py for the live roofline number
-enum ProfPhase { PROF_MSM_SORT = 0, PROF_MSM_ACCUM_L1, PROF_MSM_LEVELS, PROF_MSM_REDUCE, PROF_NTT_PASS, PROF_QUOTIENT, PROF_NPHASES };
+enum ProfPhase { PROF_MSM_SORT = 0, PROF_MSM_ACCUM_L1, PROF_MSM_LEVELS, PROF_MSM_REDUCE, PROF_NTT_PASS, PROF_QUOTIENT, PROF_PRODUCTS, PROF_LOOKUP_SORT, PROF_NPHASES };
 struct ProfSpan { int phase; cudaEvent_t e0, e1; };
 
 struct trp_ctx {
@@ -169,6 +169,19 @@ void trp_bases_destroy(trp_bases* b);
 int trp_bases_info(const trp_bases* b, unsigned* c, unsigned* W, unsigned* precomp);
 int trp_field_op_impl(trp_ctx* ctx, int field, int op, const void* d_a, const void* d_b, void* d_out, size_t n);
 int trp_microbench_impl(trp_ctx* ctx, int kind, int iters, double* out_gops);
+// products.cu (row f1): out = mul / a with zeros kept; z[0] = init, z[i] = z[i-1] * v[i-1]; fused permutation / lookup Z columns
+int trp_batch_invert_impl(trp_ctx* ctx, int field, const void* d_a, const void* d_mul, void* d_out, size_t n);
+size_t trp_grand_product_ws_bytes(size_t n_out);
+int trp_grand_product_impl(trp_ctx* ctx, int field, const void* d_v, size_t n_in, const void* d_init, void* d_z, size_t n_out, void* d_tiles);
+size_t trp_product_ws_bytes(size_t n);
+int trp_permutation_product_impl(trp_domain* d, const uint64_t* const* d_values, const uint64_t* const* d_sigmas, size_t m,
+                                 const uint64_t* consts_host, const void* d_last_z, void* d_z, void* ws);
+int trp_lookup_product_impl(trp_domain* d, const void* d_a, const void* d_s, const void* d_ap, const void* d_sp,
+                            const uint64_t* consts_host, void* d_z, size_t n_out, void* ws);
+// lookup.cu (row f1): permute_expression_pair
+size_t trp_permute_pair_ws_bytes(size_t rows);
+int trp_permute_pair_impl(trp_ctx* ctx, int field, const void* d_input, const void* d_table, size_t rows, void* d_perm_input,
+                          void* d_perm_table, void* ws, int* all_found);
 
 // field ids used internally: 0 = Fp, 1 = Fq
 inline int scalar_field_of(int curve) { return curve == TRP_CURVE_PALLAS ? 1 : 0; }
