@@ -2,14 +2,19 @@
 of the TinyRAM circuit's shape (Appendix B), every hot-path call halo2_proofs' create_proof makes for one proof --
 
   phase 2-5  497 x commit_lagrange (MSM of n + 1 points) and 497 x lagrange_to_coeff           (instance, advice,
-             lookup A'/S', permutation Z, lookup Z columns)
+             lookup A'/S', permutation Z, lookup Z columns); between them, on the device:
+             theta-compression of the 31 lookups' input / table expressions (the quotient VM over the Lagrange basis),
+             31 x permute_expression_pair, 47 x permutation grand product (chunks of 4 columns, chained), 31 x lookup
+             grand product
   phase 7    for each of the 2^(extended_k - k) cosets: 497 x coeff_to_coset (one size-n NTT per column; the 214 fixed /
              sigma / selector columns are keygen-time data and enter already evaluated), then the quotient program over
              all 711 columns; extended_to_coeff with divide_by_vanishing_poly; commit of the 5 h pieces and of the random
              blinding polynomial (6 coefficient-basis MSMs of n points)
 
--- and reports device time per phase.  What it does NOT contain ("next" rows): witness synthesis, lookup
-permutation / grand products, the evaluations at x, multiopen and the IPA opening.  The reference itself only runs this
+-- and reports device time per phase.  What it does NOT contain ("next" rows): witness synthesis, the
+evaluations at x, multiopen and the IPA opening.  The synthetic lookups use the compressed input, rotated by one row, as
+their table (so that every input value occurs in the table, as in a satisfied circuit); the table expression is still
+evaluated.  The reference itself only runs this
 path at k <= 14 on CPU (src/test_utils.rs:20); k = 20 is BASELINE.json's target configuration.
 
 Scalars follow the distribution note of SURVEY.md 8(a): instance / advice columns are 90 % {0,1}, 8 % < 2^32, 2 % full
@@ -91,6 +96,36 @@ class CreateProofModel:
         for j, c in enumerate(self.keygen_cols):
             ptrs[c] = self.keygen_coset[j].data_ptr()
         self.col_ptrs = ptrs
+        # ---- row f1: lookup permutation and grand products -----------------------------------------------------------
+        lag_ptrs = [0] * self.shape.n_columns           # Lagrange-basis view of every column (keygen columns: stand-ins)
+        self.row_of = {c: j for j, c in enumerate(self.proof_cols)}
+        for j, c in enumerate(self.proof_cols):
+            lag_ptrs[c] = self.lag[j].data_ptr()
+        for j, c in enumerate(self.keygen_cols):
+            lag_ptrs[c] = self.keygen_coset[j].data_ptr()
+        self.lag_ptrs = lag_ptrs
+        self.lookup_progs = [(P.compile_ast(a, self.ev.modulus), P.compile_ast(t, self.ev.modulus)) for a, t in self.shape.lookup_exprs]
+        self.n_lookups = len(self.lookup_progs)
+        self.compressed = torch.empty((self.n_lookups, 2, n, 4), dtype=torch.int64, device=dev)
+        self.blinding_factors = 5
+        self.usable_rows = n - (self.blinding_factors + 1)
+        p = self.ev.modulus
+        R = (1 << 256) % p
+        limbs = lambda v: np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+        import random as _random
+        rr = _random.Random(seed)
+        self.beta, self.gamma = rr.randrange(p), rr.randrange(p)
+        self.beta_m, self.gamma_m = limbs(self.beta * R % p), limbs(self.gamma * R % p)
+        delta = pow(5, 1 << 32, p)
+        self.perm_chunks = []
+        pc = self.shape.perm_cols
+        sig0 = g["permutation_sigma"][0]
+        for ch, lo in enumerate(range(0, len(pc), tinyram_shape.PERM_CHUNK)):
+            cols = pc[lo:lo + tinyram_shape.PERM_CHUNK]
+            vptr = (ctypes.c_void_p * len(cols))(*[lag_ptrs[c] for c in cols])
+            sptr = (ctypes.c_void_p * len(cols))(*[lag_ptrs[sig0 + lo + i] for i in range(len(cols))])
+            dbeta = np.stack([limbs(pow(delta, lo + i, p) * self.beta % p * R % p) for i in range(len(cols))])
+            self.perm_chunks.append((vptr, sptr, len(cols), dbeta))
         torch.cuda.synchronize()
 
     def describe(self):
@@ -108,16 +143,64 @@ class CreateProofModel:
         def mark(name):
             e = ev(); e.record(st); marks.append((name, e))
 
-        with torch.cuda.stream(st):
-            mark("start")
-            # phases 2-5: commitments of the Lagrange-basis columns (MSM of n + 1 points each: column ++ blind)
-            for b0 in range(0, self.n_proof, self.msm_batch):
-                nb = min(self.msm_batch, self.n_proof - b0)
+        g = self.shape.groups
+        rows = lambda name: range(self.row_of[g[name][0]], self.row_of[g[name][0]] + g[name][1])
+
+        def commit_rows(r):
+            for b0 in range(r.start, r.stop, self.msm_batch):
+                nb = min(self.msm_batch, r.stop - b0)
                 self.stage[:nb, :n].copy_(self.lag[b0:b0 + nb])
                 self.stage[:nb, n].copy_(self.blinds[b0:b0 + nb])
                 ctx.check(lib.trp_dev_msm_batch(ctx.handle, self.h_lagrange, self.stage.data_ptr(), n + 1, nb,
                                                 self.commitments[b0].data_ptr()))
-            mark("commit_lagrange")
+
+        la, ls, lz, pz = rows("lookup_permuted_input"), rows("lookup_permuted_table"), rows("lookup_z"), rows("permutation_z")
+        times = {}
+
+        def timed(name, fn):
+            a = ev(); a.record(st); fn(); b = ev(); b.record(st)
+            times.setdefault(name, []).append((a, b))
+
+        with torch.cuda.stream(st):
+            mark("start")
+            # phases 2-3: commitments of the instance / advice columns (MSM of n + 1 points each: column ++ blind)
+            timed("commit_lagrange_ms", lambda: commit_rows(range(0, min(la.start, pz.start))))
+            # phase 4 (theta): compress the lookups' expressions, permute them, commit A' and S'
+            def compress():
+                for i, (pi, pt) in enumerate(self.lookup_progs):
+                    self.ev.evaluate_device(pi, self.dom, self.lag_ptrs, self.compressed[i, 0].data_ptr(), coset=0 | Q_CONTIGUOUS)
+                    self.ev.evaluate_device(pt, self.dom, self.lag_ptrs, self.compressed[i, 1].data_ptr(), coset=0 | Q_CONTIGUOUS)
+                    self.compressed[i, 1].copy_(torch.roll(self.compressed[i, 0], 1, 0))      # see module docstring
+            timed("lookup_compress_ms", compress)
+            def permute():
+                ok = ctypes.c_int(1)
+                u = self.usable_rows
+                for i in range(self.n_lookups):
+                    ctx.check(lib.trp_dev_permute_expression_pair(ctx.handle, self.compressed[i, 0].data_ptr(), self.compressed[i, 1].data_ptr(),
+                                                                  u, self.lag[la.start + i].data_ptr(), self.lag[ls.start + i].data_ptr(),
+                                                                  ctypes.byref(ok)))
+                    self.lookups_ok = self.lookups_ok and bool(ok.value)
+            self.lookups_ok = True
+            timed("lookup_permute_ms", permute)
+            timed("commit_lagrange_ms", lambda: (commit_rows(la), commit_rows(ls)))
+            # phase 5 (beta, gamma): permutation and lookup grand products, commit the Z columns
+            def perm_products():
+                last = None
+                for ch, (vptr, sptr, m, dbeta) in enumerate(self.perm_chunks):
+                    z = self.lag[pz.start + ch]
+                    ctx.check(lib.trp_dev_permutation_product(self.dom.handle, vptr, sptr, m, ptr(self.beta_m), ptr(self.gamma_m), ptr(dbeta),
+                                                              last, z.data_ptr()))
+                    last = z[self.usable_rows].data_ptr()
+            timed("permutation_product_ms", perm_products)
+            def lookup_products():
+                for i in range(self.n_lookups):
+                    ctx.check(lib.trp_dev_lookup_product(self.dom.handle, self.compressed[i, 0].data_ptr(), self.compressed[i, 1].data_ptr(),
+                                                         self.lag[la.start + i].data_ptr(), self.lag[ls.start + i].data_ptr(),
+                                                         ptr(self.beta_m), ptr(self.gamma_m), self.lag[lz.start + i].data_ptr(),
+                                                         n - self.blinding_factors))
+            timed("lookup_product_ms", lookup_products)
+            timed("commit_lagrange_ms", lambda: (commit_rows(pz), commit_rows(lz)))
+            mark("commit_and_products")
             self.coeff.copy_(self.lag)
             ctx.check(lib.trp_dev_lagrange_to_coeff(self.dom.handle, self.coeff.data_ptr(), self.n_proof))
             mark("lagrange_to_coeff")
@@ -145,6 +228,8 @@ class CreateProofModel:
         out = {}
         for (_, e_prev), (name, e) in zip(marks[:-1], marks[1:]):
             out[name + "_ms"] = e_prev.elapsed_time(e)
+        for name, pairs in times.items():
+            out[name] = sum(a.elapsed_time(b) for a, b in pairs)
         out["coset_ntt_ms"] = sum(a.elapsed_time(b) for a, b, _ in spans)
         out["quotient_vm_ms"] = sum(b.elapsed_time(c) for _, b, c in spans)
         out["total_ms"] = marks[0][1].elapsed_time(marks[-1][1])

@@ -28,6 +28,8 @@ class Shape:
     n_columns: int
     n_expressions: int
     groups: dict            # name -> (first column, count)
+    lookup_exprs: list = None   # per lookup: (compressed input Ast, compressed table Ast) over the Lagrange basis
+    perm_cols: list = None      # column index of every equality-enabled column, in argument order
 
 
 def build(seed: int = 40, modulus: int = P._MODULUS[0], scale: float = 1.0) -> Shape:
@@ -95,11 +97,13 @@ def build(seed: int = 40, modulus: int = P._MODULUS[0], scale: float = 1.0) -> S
     # ---- lookups: 5 rules each; input / table expressions are theta-compressions of `width` columns --------------------
     theta = rnd()
     widths = (LOOKUP_WIDTHS * ((n_lookups + len(LOOKUP_WIDTHS) - 1) // len(LOOKUP_WIDTHS)))[:n_lookups] if scale < 1.0 else LOOKUP_WIDTHS
+    lookup_exprs = []
     for lk in range(n_lookups):
         w = widths[lk]
         sel = rng.choice(fixed)
         inp = P.DistributePowers([sel * rng.choice(advice) for _ in range(w)], P.ConstantTerm(theta))
         tab = P.DistributePowers([rng.choice(fixed + instance) for _ in range(w)], P.ConstantTerm(theta))
+        lookup_exprs.append((inp, tab))
         z, a, s = look_z[lk], look_a[lk], look_s[lk]
         exprs.append(l0 * (P.ConstantTerm(1) - z))
         exprs.append(l_last * (z * z - z))
@@ -112,4 +116,4 @@ def build(seed: int = 40, modulus: int = P._MODULUS[0], scale: float = 1.0) -> S
     h = P.ConstantTerm(0)
     for e in exprs:
         h = h * y + e
-    return Shape(h, nxt, len(exprs), groups)
+    return Shape(h, nxt, len(exprs), groups, lookup_exprs, [c.index for c in perm_cols])
