@@ -17,6 +17,15 @@ synthetic.device_points(ctx, n, d_pts.data_ptr()); ctx.sync()
 hb = ctypes.c_void_p()
 ctx.check(lib.trp_dev_bases_load(ctx.handle, d_pts.data_ptr(), n, ctypes.byref(hb))); ctx.sync()
 d_sc = torch.from_numpy(synthetic.random_scalars(n, 20, m).view(np.int64)).cuda()
+if os.environ.get("DIST", "") == "tinyram":      # 90 % {0,1}, 8 % < 2^32, 2 % uniform, Montgomery form
+    from util import O
+    kind = torch.rand((m, n), device="cuda")
+    small = torch.zeros((m, n, 4), dtype=torch.int64, device="cuda")
+    small[..., 0] = torch.where(kind < 0.9, torch.randint(0, 2, (m, n), device="cuda"), torch.randint(0, 1 << 32, (m, n), device="cuda"))
+    r2 = torch.from_numpy(O.to_mont(O.FP, O.ints_to_limbs([(1 << 256) % O.MODULUS[O.FP]])).view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    ctx.check(lib.trp_dev_field_op(ctx.handle, 0, 2 | 16, small.data_ptr(), r2.data_ptr(), small.data_ptr(), m * n)); ctx.sync()
+    d_sc = torch.where((kind < 0.98)[..., None], small, d_sc).contiguous()
 d_out = torch.zeros((m, 12), dtype=torch.int64, device="cuda"); torch.cuda.synchronize()
 fn = lambda: ctx.check(lib.trp_dev_msm_batch(ctx.handle, hb, d_sc.data_ptr(), n, m, d_out.data_ptr()))
 for _ in range(3): fn()

@@ -15,6 +15,9 @@
 // HBM traffic per transform: (#passes) x (read + write) of the vector, #passes = ceil(log_n / 10).
 #include "common.cuh"
 
+#include <cstdlib>
+#include <type_traits>
+
 using namespace ff;
 
 namespace {
@@ -130,6 +133,108 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPass p) {
   }
 }
 
+// ---- register-blocked pass ---------------------------------------------------------------------------------------------
+// Same pass geometry as ntt_pass_kernel, but the s stages run in groups of r <= R consecutive stages held in REGISTERS:
+// a thread owns the 2^r elements that differ only in index bits [q0, q0+r), runs the r stages on them (2^(r-1) independent
+// butterflies per stage: instruction-level parallelism for the multiplier) and touches shared memory and the CTA barrier
+// once per group instead of once per stage.  The first group reads global memory directly (bit reversal, zero padding and
+// pre-scaling folded in), the last group writes it directly (post-scaling, truncation).  Shared memory is XOR-swizzled so
+// that the 128-bit accesses of every group are bank-conflict free (a quarter warp covers eight distinct 16-byte bank
+// groups): slot = idx ^ (((idx >> 3) ^ (tile << (3 - c))) & 7).
+template <class PR, int R>
+__global__ void __launch_bounds__(NTT_THREADS, R >= 3 ? 2 : 3) ntt_pass_reg_kernel(NttPass p) {
+  extern __shared__ uint4 smem[];
+  const unsigned s = p.s, c = p.c, L = p.L, lo = p.lo;
+  const unsigned nelem = 1u << (s + c);
+  uint4* plane0 = smem;
+  uint4* plane1 = smem + nelem;
+  const unsigned g = blockIdx.x;
+  const uint4* src = p.src + 2 * (size_t)blockIdx.y * p.src_stride;
+  uint4* dst = p.dst + 2 * (size_t)blockIdx.y * p.dst_stride;
+  const unsigned cmask = (1u << c) - 1;
+  unsigned low_base = 0, hi = 0;
+  if (!p.first) { low_base = (g & ((1u << (lo - c)) - 1)) << c; hi = g >> (lo - c); }
+  auto pos_of = [&](unsigned t, unsigned i) -> unsigned {
+    if (p.first) return (t << (L - c)) | (g << s) | i;
+    return (hi << (lo + s)) | (i << lo) | low_base | t;
+  };
+  auto slot = [&](unsigned t, unsigned i) -> unsigned {
+    unsigned idx = (t << s) | i;
+    return idx ^ (((idx >> 3) ^ (t << (3 - c))) & 7u);
+  };
+  const unsigned ngroups = (s + R - 1) / R;
+  unsigned q0 = 0;
+  for (unsigned gi = 0; gi < ngroups; ++gi) {
+    const unsigned r = s / ngroups + (gi < s % ngroups ? 1u : 0u);
+    const bool gfirst = gi == 0, glast = gi + 1 == ngroups;
+    const unsigned units = nelem >> r, tile_units_log = s - r;
+    auto body = [&](auto rtag) {
+      constexpr int RR = decltype(rtag)::value;
+      constexpr int E = 1 << RR;
+      for (unsigned u = threadIdx.x; u < units; u += blockDim.x) {
+        unsigned t, j;
+        if (glast && p.first) { j = u & ((1u << tile_units_log) - 1); t = u >> tile_units_log; }   // contiguous stores along i
+        else { t = u & cmask; j = u >> c; }                                                        // adjacent tiles are adjacent in memory
+        if (gfirst && p.first && c) t = __brev(t) >> (32 - c);
+        const unsigned j_low = j & ((1u << q0) - 1), j_high = j >> q0;
+        const unsigned i_base = (j_high << (q0 + RR)) | j_low;
+        Fe<PR> x[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const unsigned i = i_base | ((unsigned)e << q0);
+          if (gfirst) {
+            unsigned sidx = p.first ? (L ? (__brev(pos_of(t, i)) >> (32 - L)) : 0u) : pos_of(t, i);
+            if (sidx < p.n_src) {
+              x[e] = fe_load<PR>(src + 2 * (size_t)sidx);
+              if (p.pre) x[e] = fe_mul(x[e], fe_load_ro<PR>(p.pre + 2 * (sidx % p.pre_period)));
+            } else {
+              x[e] = fe_zero<PR>();
+            }
+          } else {
+            x[e] = lds_fe<PR>(plane0, plane1, slot(t, i));
+          }
+        }
+        const unsigned low = p.first ? 0u : (low_base | t);
+#pragma unroll
+        for (int a = 0; a < RR; ++a) {
+          const unsigned tt = lo + q0 + a;
+#pragma unroll
+          for (int b = 0; b < E / 2; ++b) {
+            const int el = b & ((1 << a) - 1);                 // bits of e below a
+            const int e0 = ((b >> a) << (a + 1)) | el, e1 = e0 | (1 << a);
+            Fe<PR> y = x[e1];
+            if (tt > 0) {
+              const unsigned jl = j_low | ((unsigned)el << q0);
+              const unsigned expo = ((jl << lo) | low) << (L - tt - 1);
+              y = fe_mul(y, fe_load_ro<PR>(p.tw + 2 * (size_t)expo));
+            }
+            x[e1] = fe_sub(x[e0], y);
+            x[e0] = fe_add(x[e0], y);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const unsigned i = i_base | ((unsigned)e << q0);
+          if (glast) {
+            unsigned pos = pos_of(t, i);
+            if (p.last && pos >= p.n_dst) continue;
+            Fe<PR> v = x[e];
+            if (p.last && p.post) v = fe_mul(v, fe_load_ro<PR>(p.post + 2 * (pos % p.post_period)));
+            fe_store(dst + 2 * (size_t)pos, v);
+          } else {
+            sts_fe(plane0, plane1, slot(t, i), x[e]);
+          }
+        }
+      }
+    };
+    if (r == 1) body(std::integral_constant<int, 1>());
+    else if (r == 2) body(std::integral_constant<int, 2>());
+    else if constexpr (R >= 3) body(std::integral_constant<int, 3>());
+    if (!glast) __syncthreads();
+    q0 += r;
+  }
+}
+
 // tab[i] = omega^i, i < count
 template <class PR>
 __global__ void gen_twiddles_kernel(uint4* tab, Fe<PR> omega, unsigned count, unsigned chunk) {
@@ -233,13 +338,28 @@ int ntt_run(trp_ctx* ctx, const void* d_src, void* d_dst, size_t batch, unsigned
     if (threads < 32) threads = 32;
     dim3 grid((unsigned)(N >> (p.s + p.c)), (unsigned)batch);
     size_t smem = (size_t)nelem * 32;
-    if (smem > 48 * 1024)
-      TRP_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32u << TILE_LOG_MAX)));
-    {
-      ProfScope ps(ctx, PROF_NTT_PASS);
+    // register-blocked kernel, radix-4 groups by default (measured on B200 at 8 x 2^20: radix 4 1.53 ms, radix 8 1.61 ms --
+    // 117 registers cost a CTA per SM --, one stage per barrier 1.58 ms); TRP_NTT_RADIX=8 / 2 select the other two
+    static const int radix_log = [] { const char* e = getenv("TRP_NTT_RADIX"); int v = e ? atoi(e) : 4; return v == 2 ? 1 : v == 8 ? 3 : 2; }();
+    ProfScope ps(ctx, PROF_NTT_PASS);
+    if (p.s == 0 || radix_log == 1) {
+      if (smem > 48 * 1024)
+        TRP_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32u << TILE_LOG_MAX)));
       ntt_pass_kernel<PR><<<grid, threads, smem, ctx->stream>>>(p);
-      TRP_LAUNCHED(ctx);
+    } else if (radix_log == 2) {
+      unsigned th = nelem / 4 < NTT_THREADS ? nelem / 4 : NTT_THREADS;
+      if (th < 32) th = 32;
+      if (smem > 48 * 1024)
+        TRP_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_reg_kernel<PR, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32u << TILE_LOG_MAX)));
+      ntt_pass_reg_kernel<PR, 2><<<grid, th, smem, ctx->stream>>>(p);
+    } else {
+      unsigned th = nelem / 8 < NTT_THREADS ? nelem / 8 : NTT_THREADS;
+      if (th < 32) th = 32;
+      if (smem > 48 * 1024)
+        TRP_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_reg_kernel<PR, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32u << TILE_LOG_MAX)));
+      ntt_pass_reg_kernel<PR, 3><<<grid, th, smem, ctx->stream>>>(p);
     }
+    TRP_LAUNCHED(ctx);
   }
   return TRP_OK;
 }
