@@ -193,6 +193,29 @@ int trp_dev_permute_expression_pair(trp_ctx* ctx, const uint64_t* d_input, const
 int trp_permute_expression_pair(trp_ctx* ctx, const uint64_t* input, const uint64_t* table, size_t rows, uint64_t* perm_input,
                                 uint64_t* perm_table, int* all_found);
 
+/* ---- opening phase: halo2_proofs 0.2.0 arithmetic.rs {eval_polynomial, compute_inner_product,
+ * kate_division, parallel_generator_collapse} and the round body of poly/commitment/prover.rs create_proof (the IPA) ------- */
+/* out[j] = sum_i polys[j * stride + i] * x^i, i < n, for j < m: m evaluations at ONE point (the evaluations at x * omega^rot) */
+int trp_dev_eval_polynomials(trp_ctx* ctx, int which_field, const uint64_t* d_polys, size_t stride, size_t n, size_t m,
+                             const uint64_t x[4], uint64_t* d_out /* m x 4 */);
+int trp_eval_polynomial(trp_ctx* ctx, int which_field, const uint64_t* coeffs, size_t n, const uint64_t x[4], uint64_t out[4]);
+/* out[j] = <a_j, b_j>, vectors j at d_a + j * a_stride / d_b + j * b_stride elements (stride 0 = shared vector) */
+int trp_dev_inner_products(trp_ctx* ctx, int which_field, const uint64_t* d_a, size_t a_stride, const uint64_t* d_b, size_t b_stride,
+                           size_t n, size_t m, uint64_t* d_out);
+int trp_compute_inner_product(trp_ctx* ctx, int which_field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t out[4]);
+/* d_out[i] = x^i, i < n  (the vector b of the inner-product argument) */
+int trp_dev_powers(trp_ctx* ctx, int which_field, const uint64_t x[4], size_t n, uint64_t* d_out);
+/* kate_division: q (n - 1 coefficients) = (p(X) - p(b)) / (X - b) for the n coefficients of p */
+int trp_dev_kate_division(trp_ctx* ctx, int which_field, const uint64_t* d_coeffs, size_t n, const uint64_t b[4], uint64_t* d_q);
+int trp_kate_division(trp_ctx* ctx, int which_field, const uint64_t* coeffs, size_t n, const uint64_t b[4], uint64_t* q);
+/* IPA round: a[i] += a[i + half] * u, i < half  (p' with u^-1, b with u) */
+int trp_dev_fold(trp_ctx* ctx, int which_field, uint64_t* d_a, size_t half, const uint64_t u[4]);
+/* parallel_generator_collapse: g[i] = g[i] + [u] g[i + half], i < half, normalised affine points (identity = 0,0); u Montgomery */
+int trp_dev_generator_collapse(trp_ctx* ctx, uint64_t* d_g /* 2 * half affine points */, size_t half, const uint64_t u[4]);
+/* best_multiexp over caller-owned DEVICE bases (no precomputed table): the round MSMs over the collapsing G' */
+int trp_dev_msm_var(trp_ctx* ctx, const uint64_t* d_bases /* n x 8 */, const uint64_t* d_scalars /* m x n x 4 */, size_t n, size_t m,
+                    uint64_t* d_out_jacobian /* m x 12 */);
+
 /* ---- glue / debug: elementwise field kernels over the ctx's scalar (field=0) or base (field=1) field ----
  * op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 sqr(a).  Host pointers.  Used by parity tests of K1 and by K7 callers. */
 int trp_field_op(trp_ctx* ctx, int which_field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);

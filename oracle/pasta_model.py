@@ -550,3 +550,75 @@ def lookup_commit_product(F: Field, n, compressed_input, compressed_table, permu
         z.append(state)
     z = z[:n - blinding_factors] + [rand() for _ in range(blinding_factors)]
     return z
+
+
+# ---- the opening phase (halo2_proofs 0.2.0 arithmetic.rs / poly/commitment/prover.rs) -------------
+def compute_inner_product(F: Field, a, b):
+    assert len(a) == len(b)
+    acc = 0
+    for x, y in zip(a, b):
+        acc = (acc + x * y) % F.p
+    return acc
+
+
+def kate_division(F: Field, a, b):
+    """arithmetic::kate_division: divide a(X) by (X - b), discarding the remainder; len(a) - 1 coefficients."""
+    b = (-b) % F.p
+    q = [0] * (len(a) - 1)
+    tmp = 0
+    for i in range(len(a) - 1, 0, -1):
+        lead = (a[i] - tmp) % F.p
+        q[i - 1] = lead
+        tmp = lead * b % F.p
+    return q
+
+
+def parallel_generator_collapse(C: "Curve", g, challenge):
+    half = len(g) // 2
+    return [C.add(g[i], C.mul(challenge, g[i + half])) for i in range(half)]
+
+
+def ipa_create_proof(C: "Curve", k, g, w, u, rand, transcript, p_poly, p_blind, x_3):
+    """poly::commitment::prover::create_proof.  g: n affine points (None = identity), w, u: points; p_poly: n canonical
+    coefficients.  transcript: write_point(P), write_scalar(s), squeeze_challenge_scalar() -> int; rand() -> scalar."""
+    F = C.scalar
+    p, n = F.p, 1 << k
+    assert len(p_poly) == n
+    s_poly = [rand() for _ in range(n)]
+    s_at_x3 = eval_polynomial(F, s_poly, x_3)
+    s_poly[0] = (s_poly[0] - s_at_x3) % p
+    s_poly_blind = rand()
+    transcript.write_point(C.best_multiexp(s_poly + [s_poly_blind], g + [w]))
+    xi = transcript.squeeze_challenge_scalar()
+    z = transcript.squeeze_challenge_scalar()
+    p_prime = [(s * xi + c) % p for s, c in zip(s_poly, p_poly)]
+    v = eval_polynomial(F, p_prime, x_3)
+    p_prime[0] = (p_prime[0] - v) % p
+    f = (s_poly_blind * xi + p_blind) % p
+    b, cur = [], 1
+    for _ in range(n):
+        b.append(cur)
+        cur = cur * x_3 % p
+    g_prime = list(g)
+    for j in range(k):
+        half = 1 << (k - j - 1)
+        l_j = C.best_multiexp(p_prime[half:], g_prime[:half])
+        r_j = C.best_multiexp(p_prime[:half], g_prime[half:])
+        value_l_j = compute_inner_product(F, p_prime[half:], b[:half])
+        value_r_j = compute_inner_product(F, p_prime[:half], b[half:])
+        l_rand, r_rand = rand(), rand()
+        l_j = C.add(l_j, C.best_multiexp([value_l_j * z % p, l_rand], [u, w]))
+        r_j = C.add(r_j, C.best_multiexp([value_r_j * z % p, r_rand], [u, w]))
+        transcript.write_point(l_j)
+        transcript.write_point(r_j)
+        u_j = transcript.squeeze_challenge_scalar()
+        u_j_inv = F.inv(u_j)
+        for i in range(half):
+            p_prime[i] = (p_prime[i] + p_prime[i + half] * u_j_inv) % p
+            b[i] = (b[i] + b[i + half] * u_j) % p
+        p_prime, b = p_prime[:half], b[:half]
+        g_prime = parallel_generator_collapse(C, g_prime, u_j)
+        f = (f + l_rand * u_j_inv + r_rand * u_j) % p
+    assert len(p_prime) == 1
+    transcript.write_scalar(p_prime[0])
+    transcript.write_scalar(f)

@@ -83,3 +83,60 @@ def test_lookup_product_closes(F):
     beta, gamma = rng.randrange(F.p), rng.randrange(F.p)
     z = pm.lookup_commit_product(F, n, pad(inp), pad(table), pad(pa), pad(ps), beta, gamma, bf, lambda: rng.randrange(F.p))
     assert len(z) == n and z[0] == 1 and z[usable] == 1
+
+
+# ---- row f2: the oracle's opening phase ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F", FIELDS, ids=["Fp", "Fq"])
+def test_kate_division_identity(F):
+    rng = random.Random(5)
+    a = [rng.randrange(F.p) for _ in range(40)]
+    for b in (rng.randrange(F.p), 0, 1):
+        q = pm.kate_division(F, a, b)
+        assert len(q) == 39
+        r = rng.randrange(F.p)
+        assert ((r - b) * pm.eval_polynomial(F, q, r) + pm.eval_polynomial(F, a, b)) % F.p == pm.eval_polynomial(F, a, r)
+
+
+class _Transcript:
+    def __init__(self, seed, p):
+        self.rng, self.p, self.points, self.scalars, self.challenges = random.Random(seed), p, [], [], []
+
+    def write_point(self, P): self.points.append(P)
+    def write_scalar(self, s): self.scalars.append(s)
+
+    def squeeze_challenge_scalar(self):
+        c = self.rng.randrange(1, self.p)
+        self.challenges.append(c)
+        return c
+
+
+@pytest.mark.parametrize("C", [pm.Vesta, pm.Pallas], ids=["vesta", "pallas"])
+def test_ipa_proof_satisfies_the_verifier_equation(C):
+    """The restated prover must produce proofs the halo2 verifier accepts (poly/commitment/verifier.rs):
+    P' + sum_j [u_j^-1] L_j + [u_j] R_j = [c] G'_0 + [c * b_0 * z] U + [f] W,  P' = P - [v] G_0 + [xi] S."""
+    F = C.scalar
+    rng = random.Random(6)
+    k = 3
+    n = 1 << k
+    G = (C.base.p - 1, 2)
+    g = [C.mul(rng.randrange(1, F.p), G) for _ in range(n)]
+    w, u = C.mul(rng.randrange(1, F.p), G), C.mul(rng.randrange(1, F.p), G)
+    p_poly = [rng.randrange(F.p) for _ in range(n)]
+    p_blind, x_3 = rng.randrange(F.p), rng.randrange(F.p)
+    t = _Transcript(1, F.p)
+    pm.ipa_create_proof(C, k, g, w, u, lambda: rng.randrange(F.p), t, p_poly, p_blind, x_3)
+    s_commit, rounds = t.points[0], t.points[1:]
+    xi, z, us = t.challenges[0], t.challenges[1], t.challenges[2:]
+    c, f = t.scalars
+    assert len(rounds) == 2 * k and len(us) == k
+    P = C.best_multiexp(p_poly + [p_blind], g + [w])
+    v = pm.eval_polynomial(F, p_poly, x_3)
+    lhs = C.add(C.add(P, C.neg(C.mul(v, g[0]))), C.mul(xi, s_commit))
+    g_fold, b = list(g), [pow(x_3, i, F.p) for i in range(n)]
+    for j, u_j in enumerate(us):
+        lhs = C.add(lhs, C.add(C.mul(F.inv(u_j), rounds[2 * j]), C.mul(u_j, rounds[2 * j + 1])))
+        half = len(b) // 2
+        b = [(b[i] + b[i + half] * u_j) % F.p for i in range(half)]
+        g_fold = pm.parallel_generator_collapse(C, g_fold, u_j)
+    rhs = C.add(C.add(C.mul(c, g_fold[0]), C.mul(c * b[0] % F.p * z % F.p, u)), C.mul(f, w))
+    assert lhs == rhs

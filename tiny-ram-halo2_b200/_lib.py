@@ -31,6 +31,8 @@ EXPORTED_SYMBOLS = [
     "trp_dev_batch_invert", "trp_batch_invert", "trp_dev_grand_product", "trp_grand_product",
     "trp_dev_permutation_product", "trp_permutation_product", "trp_dev_lookup_product", "trp_lookup_product",
     "trp_dev_permute_expression_pair", "trp_permute_expression_pair",
+    "trp_dev_eval_polynomials", "trp_eval_polynomial", "trp_dev_inner_products", "trp_compute_inner_product", "trp_dev_powers",
+    "trp_dev_kate_division", "trp_kate_division", "trp_dev_fold", "trp_dev_generator_collapse", "trp_dev_msm_var",
 ]
 
 
@@ -118,6 +120,16 @@ def load_library():
     L.trp_lookup_product.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, sz]
     L.trp_dev_permute_expression_pair.argtypes = [vp, vp, vp, sz, vp, vp, ctypes.POINTER(i)]
     L.trp_permute_expression_pair.argtypes = [vp, vp, vp, sz, vp, vp, ctypes.POINTER(i)]
+    L.trp_dev_eval_polynomials.argtypes = [vp, i, vp, sz, sz, sz, vp, vp]
+    L.trp_eval_polynomial.argtypes = [vp, i, vp, sz, vp, vp]
+    L.trp_dev_inner_products.argtypes = [vp, i, vp, sz, vp, sz, sz, sz, vp]
+    L.trp_compute_inner_product.argtypes = [vp, i, vp, vp, sz, vp]
+    L.trp_dev_powers.argtypes = [vp, i, vp, sz, vp]
+    L.trp_dev_kate_division.argtypes = [vp, i, vp, sz, vp, vp]
+    L.trp_kate_division.argtypes = [vp, i, vp, sz, vp, vp]
+    L.trp_dev_fold.argtypes = [vp, i, vp, sz, vp]
+    L.trp_dev_generator_collapse.argtypes = [vp, vp, sz, vp]
+    L.trp_dev_msm_var.argtypes = [vp, vp, vp, sz, sz, vp]
     _lib = L
     return L
 

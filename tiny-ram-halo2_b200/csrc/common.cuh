@@ -178,6 +178,21 @@ int trp_permutation_product_impl(trp_domain* d, const uint64_t* const* d_values,
                                  const uint64_t* consts_host, const void* d_last_z, void* d_z, void* ws);
 int trp_lookup_product_impl(trp_domain* d, const void* d_a, const void* d_s, const void* d_ap, const void* d_sp,
                             const uint64_t* consts_host, void* d_z, size_t n_out, void* ws);
+int trp_suffix_sum_impl(trp_ctx* ctx, int field, void* d_a, size_t n, void* d_tiles);
+// ipa.cu (row f2): evaluations, inner products, Kate division, IPA round folding; msm.cu: MSM over caller-owned bases
+size_t trp_reduce_ws_bytes(trp_ctx* ctx, size_t n, size_t m);
+int trp_eval_polys_impl(trp_ctx* ctx, int field, const void* d_polys, size_t stride, size_t n, size_t m, const uint64_t x[4], void* d_out, void* ws);
+int trp_inner_products_impl(trp_ctx* ctx, int field, const void* d_a, size_t a_stride, const void* d_b, size_t b_stride, size_t n, size_t m,
+                            void* d_out, void* ws);
+int trp_fold_impl(trp_ctx* ctx, int field, void* d_a, size_t half, const uint64_t u[4]);
+int trp_powers_impl(trp_ctx* ctx, int field, const uint64_t x[4], size_t n, void* d_out);
+size_t trp_kate_ws_bytes(size_t n);
+int trp_kate_division_impl(trp_ctx* ctx, int field, const void* d_coeffs, size_t n, const uint64_t b[4], const uint64_t b_inv[4],
+                           int b_is_zero, void* d_q, void* ws);
+size_t trp_collapse_ws_bytes(size_t half);
+int trp_generator_collapse_impl(trp_ctx* ctx, void* d_g, size_t half, const uint64_t u_canonical[4], void* ws);
+size_t trp_msm_var_ws_bytes(size_t n, size_t m);
+int trp_msm_var_impl(trp_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, size_t m, void* d_out_jac, void* ws, size_t ws_bytes);
 // lookup.cu (row f1): permute_expression_pair
 size_t trp_permute_pair_ws_bytes(size_t rows);
 int trp_permute_pair_impl(trp_ctx* ctx, int field, const void* d_input, const void* d_table, size_t rows, void* d_perm_input,

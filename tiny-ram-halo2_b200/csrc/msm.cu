@@ -592,6 +592,32 @@ int trp_msm_impl(trp_ctx* ctx, const trp_bases* bases, const void* d_scalars, si
   return TRP_OK;
 }
 
+// ---- MSM over caller-owned bases (no table, one bucket set per window): the IPA rounds' <p'_hi, G'_lo> / <p'_lo, G'_hi>, whose
+// bases change every round -------------------------------------------------------------------------
+static trp_bases_impl transient_bases(trp_ctx* ctx, const void* d_xy, size_t n) {
+  trp_bases_impl b;
+  b.pub.ctx = ctx; b.pub.n = n; b.pub.d_xy = const_cast<void*>(d_xy);
+  MsmGeom& g = b.g;
+  g.c = choose_c(n ? n : 1);
+  g.W = (256 + g.c - 1) / g.c;
+  g.B = 1u << (g.c - 1);
+  g.stride = n;
+  g.precomp = 0;
+  g.nsets = g.W;
+  g.nb = g.nsets * g.B;
+  return b;
+}
+
+size_t trp_msm_var_ws_bytes(size_t n, size_t m) {
+  trp_bases_impl b = transient_bases(nullptr, nullptr, n);
+  return msm_ws_bytes(b.g, n, m);
+}
+
+int trp_msm_var_impl(trp_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, size_t m, void* d_out_jac, void* ws, size_t ws_bytes) {
+  trp_bases_impl b = transient_bases(ctx, d_bases, n);
+  return trp_msm_impl(ctx, &b.pub, d_scalars, n, m, d_out_jac, ws, ws_bytes);
+}
+
 // ---- sum of a few group elements (combining the per-GPU partial sums of a point-range-split MSM) -----------------------
 namespace {
 template <class BPR>

@@ -48,35 +48,39 @@ template <class PR> __device__ __forceinline__ Fe<PR> fe_shfl(const Fe<PR>& a, u
 
 // Products over the CTA's 256 thread values p: returns the product of the values of all LOWER threads (exclusive prefix);
 // optionally also the product of all HIGHER threads and the CTA total.  wsm: PB_WARPS field elements of shared memory.
-template <class PR>
+// ADD = false: the monoid is (field, *, 1); ADD = true: (field, +, 0) -- prefix sums for kate_division
+template <class PR, bool ADD> __device__ __forceinline__ Fe<PR> op_identity() { return ADD ? fe_zero<PR>() : fe_one<PR>(); }
+template <class PR, bool ADD> __device__ __forceinline__ Fe<PR> op_apply(const Fe<PR>& a, const Fe<PR>& b) { return ADD ? fe_add(a, b) : fe_mul(a, b); }
+
+template <class PR, bool ADD = false>
 __device__ __forceinline__ Fe<PR> block_exclusive_products(const Fe<PR>& p, uint4* wsm, Fe<PR>* suffix, Fe<PR>* total) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   Fe<PR> inc = p;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { Fe<PR> y = fe_shfl_up(inc, o); if (lane >= (unsigned)o) inc = fe_mul(inc, y); }
+  for (int o = 1; o < 32; o <<= 1) { Fe<PR> y = fe_shfl_up(inc, o); if (lane >= (unsigned)o) inc = op_apply<PR, ADD>(inc, y); }
   Fe<PR> exc = fe_shfl_up(inc, 1);
-  if (lane == 0) exc = fe_one<PR>();
-  Fe<PR> sexc = fe_one<PR>();
+  if (lane == 0) exc = op_identity<PR, ADD>();
+  Fe<PR> sexc = op_identity<PR, ADD>();
   if (suffix) {
     Fe<PR> sinc = p;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { Fe<PR> y = fe_shfl_down(sinc, o); if (lane + o < 32) sinc = fe_mul(sinc, y); }
+    for (int o = 1; o < 32; o <<= 1) { Fe<PR> y = fe_shfl_down(sinc, o); if (lane + o < 32) sinc = op_apply<PR, ADD>(sinc, y); }
     sexc = fe_shfl_down(sinc, 1);
-    if (lane == 31) sexc = fe_one<PR>();
+    if (lane == 31) sexc = op_identity<PR, ADD>();
   }
   __syncthreads();                      // wsm may still be read by a previous call
   if (lane == 31) fe_store(wsm + 2 * wid, inc);
   __syncthreads();
-  Fe<PR> before = fe_one<PR>(), after = fe_one<PR>(), all = fe_one<PR>();
+  Fe<PR> before = op_identity<PR, ADD>(), after = op_identity<PR, ADD>(), all = op_identity<PR, ADD>();
   for (unsigned w = 0; w < (unsigned)PB_WARPS; ++w) {
     Fe<PR> t = fe_load<PR>(wsm + 2 * w);
-    if (w < wid) before = fe_mul(before, t);
-    if (suffix && w > wid) after = fe_mul(after, t);
-    if (total) all = fe_mul(all, t);
+    if (w < wid) before = op_apply<PR, ADD>(before, t);
+    if (suffix && w > wid) after = op_apply<PR, ADD>(after, t);
+    if (total) all = op_apply<PR, ADD>(all, t);
   }
-  if (suffix) *suffix = fe_mul(sexc, after);
+  if (suffix) *suffix = op_apply<PR, ADD>(sexc, after);
   if (total) *total = all;
-  return fe_mul(exc, before);
+  return op_apply<PR, ADD>(exc, before);
 }
 
 // out[i] = mul[i] / a[i]  (mul == nullptr: 1 / a[i]);  a[i] == 0 -> out[i] = 0 (ff::BatchInvert skips zeros)
@@ -123,54 +127,58 @@ __global__ void __launch_bounds__(PB_THREADS) batch_invert_kernel(const uint4* a
   }
 }
 
-// ---- grand product: z[0] = init, z[i] = z[i-1] * v[i-1] for i < n_out (v[j] = 1 for j >= n_in) ---------------------
-template <class PR>
+// ---- grand product / prefix sum: z[0] = init, z[i] = z[i-1] (op) v[i-1] for i < n_out (v[j] = identity for j >= n_in) ----
+// REV: logical index i lives at physical index (len - 1 - i) of both arrays, i.e. the scan runs from the END (suffix sums).
+template <bool REV> __device__ __forceinline__ size_t phys(size_t i, size_t len) { return REV ? len - 1 - i : i; }
+
+template <class PR, bool ADD, bool REV>
 __global__ void __launch_bounds__(PB_THREADS) gp_tile_products_kernel(const uint4* v, size_t n_in, uint4* tile_prod) {
   __shared__ uint4 wsm[2 * PB_WARPS];
   const size_t base = (size_t)blockIdx.x * PB_TILE + (size_t)threadIdx.x * PB_K;
-  Fe<PR> acc = fe_one<PR>();
+  Fe<PR> acc = op_identity<PR, ADD>();
 #pragma unroll 1
   for (int k = 0; k < PB_K; ++k)
-    if (base + k < n_in) acc = fe_mul(acc, fe_load<PR>(v + 2 * (base + k)));
+    if (base + k < n_in) acc = op_apply<PR, ADD>(acc, fe_load<PR>(v + 2 * phys<REV>(base + k, n_in)));
   Fe<PR> total;
-  block_exclusive_products<PR>(acc, wsm, nullptr, &total);
+  block_exclusive_products<PR, ADD>(acc, wsm, nullptr, &total);
   if (threadIdx.x == 0) fe_store(tile_prod + 2 * (size_t)blockIdx.x, total);
 }
 
-// single CTA: tile_prod[b] <- init * prod_{b' < b} tile_prod[b']
-template <class PR>
+// single CTA: tile_prod[b] <- init (op) (op)_{b' < b} tile_prod[b']
+template <class PR, bool ADD>
 __global__ void __launch_bounds__(PB_THREADS) gp_scan_tiles_kernel(uint4* tile_prod, unsigned ntiles, const uint4* init) {
   __shared__ uint4 wsm[2 * PB_WARPS];
   const unsigned per = (ntiles + PB_THREADS - 1) / PB_THREADS;
   const unsigned lo = threadIdx.x * per, hi = min(lo + per, ntiles);
-  Fe<PR> acc = fe_one<PR>();
-  for (unsigned b = lo; b < hi; ++b) acc = fe_mul(acc, fe_load<PR>(tile_prod + 2 * (size_t)b));
-  Fe<PR> run = block_exclusive_products<PR>(acc, wsm, nullptr, nullptr);
-  if (init) run = fe_mul(run, fe_load<PR>(init));
-  __syncthreads();   // every thread has read its tiles before anyone overwrites (init may alias nothing here)
+  Fe<PR> acc = op_identity<PR, ADD>();
+  for (unsigned b = lo; b < hi; ++b) acc = op_apply<PR, ADD>(acc, fe_load<PR>(tile_prod + 2 * (size_t)b));
+  Fe<PR> run = block_exclusive_products<PR, ADD>(acc, wsm, nullptr, nullptr);
+  if (init) run = op_apply<PR, ADD>(run, fe_load<PR>(init));
+  __syncthreads();
   for (unsigned b = lo; b < hi; ++b) {
     Fe<PR> t = fe_load<PR>(tile_prod + 2 * (size_t)b);
     fe_store(tile_prod + 2 * (size_t)b, run);
-    run = fe_mul(run, t);
+    run = op_apply<PR, ADD>(run, t);
   }
 }
 
-template <class PR>
+template <class PR, bool ADD, bool REV>
 __global__ void __launch_bounds__(PB_THREADS) gp_apply_kernel(const uint4* v, size_t n_in, const uint4* tile_prefix, uint4* z, size_t n_out) {
   __shared__ uint4 wsm[2 * PB_WARPS];
   const size_t base = (size_t)blockIdx.x * PB_TILE + (size_t)threadIdx.x * PB_K;
-  Fe<PR> acc = fe_one<PR>();
+  Fe<PR> acc = op_identity<PR, ADD>();
 #pragma unroll 1
   for (int k = 0; k < PB_K; ++k)
-    if (base + k < n_in) acc = fe_mul(acc, fe_load<PR>(v + 2 * (base + k)));
-  Fe<PR> run = block_exclusive_products<PR>(acc, wsm, nullptr, nullptr);
-  run = fe_mul(run, fe_load<PR>(tile_prefix + 2 * (size_t)blockIdx.x));
+    if (base + k < n_in) acc = op_apply<PR, ADD>(acc, fe_load<PR>(v + 2 * phys<REV>(base + k, n_in)));
+  Fe<PR> run = block_exclusive_products<PR, ADD>(acc, wsm, nullptr, nullptr);
+  run = op_apply<PR, ADD>(run, fe_load<PR>(tile_prefix + 2 * (size_t)blockIdx.x));
 #pragma unroll 1
   for (int k = 0; k < PB_K; ++k) {
     if (base + k >= n_out) break;
-    Fe<PR> cur = base + k < n_in ? fe_load<PR>(v + 2 * (base + k)) : fe_one<PR>();   // read before z[i] is written: v may alias z
-    fe_store(z + 2 * (base + k), run);
-    run = fe_mul(run, cur);
+    // read before z[i] is written: v may alias z (same logical index <-> same physical index when n_in == n_out)
+    Fe<PR> cur = base + k < n_in ? fe_load<PR>(v + 2 * phys<REV>(base + k, n_in)) : op_identity<PR, ADD>();
+    fe_store(z + 2 * phys<REV>(base + k, n_out), run);
+    run = op_apply<PR, ADD>(run, cur);
   }
 }
 
@@ -236,11 +244,25 @@ int grand_product_run(trp_ctx* ctx, const void* d_v, size_t n_in, const void* d_
   if (n_out == 0) return TRP_OK;
   unsigned ntiles = (unsigned)((n_out + PB_TILE - 1) / PB_TILE);
   ProfScope ps(ctx, PROF_PRODUCTS);
-  gp_tile_products_kernel<PR><<<ntiles, PB_THREADS, 0, ctx->stream>>>((const uint4*)d_v, n_in, (uint4*)d_tiles);
+  gp_tile_products_kernel<PR, false, false><<<ntiles, PB_THREADS, 0, ctx->stream>>>((const uint4*)d_v, n_in, (uint4*)d_tiles);
   TRP_LAUNCHED(ctx);
-  gp_scan_tiles_kernel<PR><<<1, PB_THREADS, 0, ctx->stream>>>((uint4*)d_tiles, ntiles, (const uint4*)d_init);
+  gp_scan_tiles_kernel<PR, false><<<1, PB_THREADS, 0, ctx->stream>>>((uint4*)d_tiles, ntiles, (const uint4*)d_init);
   TRP_LAUNCHED(ctx);
-  gp_apply_kernel<PR><<<ntiles, PB_THREADS, 0, ctx->stream>>>((const uint4*)d_v, n_in, (const uint4*)d_tiles, (uint4*)d_z, n_out);
+  gp_apply_kernel<PR, false, false><<<ntiles, PB_THREADS, 0, ctx->stream>>>((const uint4*)d_v, n_in, (const uint4*)d_tiles, (uint4*)d_z, n_out);
+  TRP_LAUNCHED(ctx);
+  return TRP_OK;
+}
+
+// in place: a[i] <- sum_{k > i} a[k]   (exclusive suffix sums; the middle step of kate_division)
+template <class PR>
+int suffix_sum_run(trp_ctx* ctx, void* d_a, size_t n, void* d_tiles) {
+  if (n == 0) return TRP_OK;
+  unsigned ntiles = (unsigned)((n + PB_TILE - 1) / PB_TILE);
+  gp_tile_products_kernel<PR, true, true><<<ntiles, PB_THREADS, 0, ctx->stream>>>((const uint4*)d_a, n, (uint4*)d_tiles);
+  TRP_LAUNCHED(ctx);
+  gp_scan_tiles_kernel<PR, true><<<1, PB_THREADS, 0, ctx->stream>>>((uint4*)d_tiles, ntiles, nullptr);
+  TRP_LAUNCHED(ctx);
+  gp_apply_kernel<PR, true, true><<<ntiles, PB_THREADS, 0, ctx->stream>>>((const uint4*)d_a, n, (const uint4*)d_tiles, (uint4*)d_a, n);
   TRP_LAUNCHED(ctx);
   return TRP_OK;
 }
@@ -258,6 +280,10 @@ size_t trp_grand_product_ws_bytes(size_t n_out) { return gp_tiles_bytes(n_out); 
 int trp_grand_product_impl(trp_ctx* ctx, int field, const void* d_v, size_t n_in, const void* d_init, void* d_z, size_t n_out, void* d_tiles) {
   return field == 0 ? grand_product_run<FpParams>(ctx, d_v, n_in, d_init, d_z, n_out, d_tiles)
                     : grand_product_run<FqParams>(ctx, d_v, n_in, d_init, d_z, n_out, d_tiles);
+}
+
+int trp_suffix_sum_impl(trp_ctx* ctx, int field, void* d_a, size_t n, void* d_tiles) {
+  return field == 0 ? suffix_sum_run<FpParams>(ctx, d_a, n, d_tiles) : suffix_sum_run<FqParams>(ctx, d_a, n, d_tiles);
 }
 
 size_t trp_product_ws_bytes(size_t n) { return 2 * ws_align(n * 32) + gp_tiles_bytes(n) + ws_align((2 + MAX_PERM_COLS) * 32); }
