@@ -122,31 +122,33 @@ def create_proof(params: IpaParams, rand, transcript, p_poly, p_blind, x_3, rand
     set_elem(d_pp.reshape(n, 4), 0, pp0 - v)
     f = (s_poly_blind * xi + p_blind) % p
     d_b = torch.empty((n, 4), dtype=torch.int64, device="cuda")
-    d_g = params.d_g.clone()
-    d_two = torch.zeros((2, 4), dtype=torch.int64, device="cuda")
+    # G' ++ [U, W]: L_j and R_j are computed as ONE batch of two MSMs over (G'_lo | G'_hi | U | W) with the scalar columns
+    # (p'_hi | 0 | z <p'_hi, b_lo> | l_rand) and (0 | p'_lo | z <p'_lo, b_hi> | r_rand): one launch sequence per round
+    # instead of four MSMs and two point additions (zero scalars cost nothing: zero digits are never sorted into buckets)
+    d_g = torch.cat([params.d_g, params.d_uw])
+    d_sc = torch.zeros((2, n + 2, 4), dtype=torch.int64, device="cuda")
     d_ip = torch.zeros((2, 4), dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
     ctx.check(lib.trp_dev_powers(ctx.handle, 0, ptr(mont(x_3)), n, d_b.data_ptr()))
     d_pp = d_pp.reshape(n, 4)
     for j in range(k):
         half = 1 << (k - j - 1)
+        cur = 2 * half
         el = 32 * half                      # bytes per half vector of scalars
-        # L_j = <p'_hi, G'_lo> + [z <p'_hi, b_lo>] U + [l_rand] W ;  R_j likewise with the halves swapped
-        ctx.check(lib.trp_dev_msm_var(ctx.handle, d_g.data_ptr(), d_pp.data_ptr() + el, half, 1, d_pt[0].data_ptr()))
-        ctx.check(lib.trp_dev_msm_var(ctx.handle, d_g.data_ptr() + 64 * half, d_pp.data_ptr(), half, 1, d_pt[2].data_ptr()))
         ctx.check(lib.trp_dev_inner_products(ctx.handle, 0, d_pp.data_ptr() + el, 0, d_b.data_ptr(), 0, half, 1, d_ip[0].data_ptr()))
         ctx.check(lib.trp_dev_inner_products(ctx.handle, 0, d_pp.data_ptr(), 0, d_b.data_ptr() + el, 0, half, 1, d_ip[1].data_ptr()))
         ctx.sync()
         value_l, value_r = (unmont(r) for r in d_ip.cpu().numpy().view(np.uint64))
         l_rand, r_rand = rand(), rand()
-        pts = []
-        for slot, (val, rnd) in enumerate(((value_l, l_rand), (value_r, r_rand))):
-            d_two.copy_(dev(np.stack([mont(val * z), mont(rnd)])))
-            torch.cuda.synchronize()
-            ctx.check(lib.trp_dev_msm_var(ctx.handle, params.d_uw.data_ptr(), d_two.data_ptr(), 2, 1, d_pt[2 * slot + 1].data_ptr()))
-            ctx.check(lib.trp_dev_points_sum(ctx.handle, d_pt[2 * slot].data_ptr(), 2, d_pt[2 * slot].data_ptr()))
-            ctx.sync()
-            pts.append(d_pt[2 * slot].cpu().numpy().view(np.uint64)[:8].copy())
+        cols = d_sc.reshape(-1)[:2 * (cur + 2) * 4].reshape(2, cur + 2, 4)
+        cols.zero_()
+        cols[0, :half] = d_pp[half:cur]
+        cols[1, half:cur] = d_pp[:half]
+        cols[:, cur:] = dev(np.stack([mont(value_l * z), mont(l_rand), mont(value_r * z), mont(r_rand)])).reshape(2, 2, 4)
+        torch.cuda.synchronize()
+        ctx.check(lib.trp_dev_msm_var(ctx.handle, d_g.data_ptr(), cols.data_ptr(), cur + 2, 2, d_pt.data_ptr()))
+        ctx.sync()
+        pts = [r[:8].copy() for r in d_pt[:2].cpu().numpy().view(np.uint64)]
         transcript.write_point(pts[0])
         transcript.write_point(pts[1])
         u_j = transcript.squeeze_challenge_scalar()
@@ -154,6 +156,8 @@ def create_proof(params: IpaParams, rand, transcript, p_poly, p_blind, x_3, rand
         ctx.check(lib.trp_dev_fold(ctx.handle, 0, d_pp.data_ptr(), half, ptr(mont(u_j_inv))))
         ctx.check(lib.trp_dev_fold(ctx.handle, 0, d_b.data_ptr(), half, ptr(mont(u_j))))
         ctx.check(lib.trp_dev_generator_collapse(ctx.handle, d_g.data_ptr(), half, ptr(mont(u_j))))
+        ctx.sync()
+        d_g[half:half + 2] = params.d_uw    # U, W follow the collapsed generators
         f = (f + l_rand * u_j_inv + r_rand * u_j) % p
     ctx.sync()
     c = unmont(d_pp[0].cpu().numpy().view(np.uint64))

@@ -11,8 +11,12 @@ of the TinyRAM circuit's shape (Appendix B), every hot-path call halo2_proofs' c
              all 711 columns; extended_to_coeff with divide_by_vanishing_poly; commit of the 5 h pieces and of the random
              blinding polynomial (6 coefficient-basis MSMs of n points)
 
+  phase 8-9   the evaluations at x and x * omega (eval_polynomial of every coefficient-form column),
+             multiopen's three kate_divisions and one poly::commitment::prover::create_proof (k IPA rounds: two MSMs over
+             the collapsing generators, two inner products, the folds and parallel_generator_collapse per round)
+
 -- and reports device time per phase.  What it does NOT contain ("next" rows): witness synthesis, the
-evaluations at x, multiopen and the IPA opening.  The synthetic lookups use the compressed input, rotated by one row, as
+transcript hashing and multiopen's linear combinations of the opened polynomials.  The synthetic lookups use the compressed input, rotated by one row, as
 their table (so that every input value occurs in the table, as in a satisfied circuit); the table expression is still
 evaluated.  The reference itself only runs this
 path at k <= 14 on CPU (src/test_utils.rs:20); k = 20 is BASELINE.json's target configuration.
@@ -32,6 +36,22 @@ from ._lib import ptr, Q_CONTIGUOUS
 
 _R2 = {1: [0x8c78ecb30000000f, 0xd7d30dbd8b0de0e7, 0x7797a99bc3c95d18, 0x096d41af7b9cb714],     # Fp (ctx curve VESTA)
        0: [0xfc9678ff0000000f, 0x67bb433d891a16e3, 0x7fae231004ccf590, 0x096d41af7ccfdaa9]}     # Fq (ctx curve PALLAS)
+
+
+class _NullTranscript:
+    """Challenges from a seeded stream; writes are dropped (the transcript hash stays on the host side of the boundary)."""
+
+    def __init__(self, rng, p):
+        self.rng, self.p = rng, p
+
+    def write_point(self, P):
+        pass
+
+    def write_scalar(self, s):
+        pass
+
+    def squeeze_challenge_scalar(self):
+        return self.rng.randrange(1, self.p)
 
 
 class CreateProofModel:
@@ -117,6 +137,14 @@ class CreateProofModel:
         self.beta, self.gamma = rr.randrange(p), rr.randrange(p)
         self.beta_m, self.gamma_m = limbs(self.beta * R % p), limbs(self.gamma * R % p)
         delta = pow(5, 1 << 32, p)
+        # ---- row f2: opening ---------------------------------------------------------------------------------------------------
+        from . import ipa as _ipa
+        self._ipa = _ipa
+        self.open_rng = rr
+        self.evals = torch.zeros((2 * self.n_proof + 8, 4), dtype=torch.int64, device=dev)
+        self.q_poly = torch.empty((n, 4), dtype=torch.int64, device=dev)
+        self.x_m = limbs(rr.randrange(p) * R % p)
+        self.ipa_params = None
         self.perm_chunks = []
         pc = self.shape.perm_cols
         sig0 = g["permutation_sigma"][0]
@@ -224,6 +252,21 @@ class CreateProofModel:
             mark("extended_to_coeff")
             ctx.check(lib.trp_dev_msm_batch(ctx.handle, self.h_g, self.h_coeff.data_ptr(), n, 6, self.h_commit.data_ptr()))
             mark("commit_h")
+            # phase 8: evaluations at x and x * omega (every per-proof column, coefficient form); multiopen quotients
+            ctx.check(lib.trp_dev_eval_polynomials(ctx.handle, 0, self.coeff.data_ptr(), n, n, self.n_proof, ptr(self.x_m), self.evals.data_ptr()))
+            ctx.check(lib.trp_dev_eval_polynomials(ctx.handle, 0, self.coeff.data_ptr(), n, n, self.n_proof, ptr(self.beta_m),
+                                                   self.evals[self.n_proof].data_ptr()))
+            ctx.check(lib.trp_dev_eval_polynomials(ctx.handle, 0, self.h_coeff.data_ptr(), n, n, 6, ptr(self.x_m), self.evals[2 * self.n_proof].data_ptr()))
+            mark("evaluations")
+            for i in range(3):
+                ctx.check(lib.trp_dev_kate_division(ctx.handle, 0, self.coeff[i].data_ptr(), n, ptr(self.x_m), self.q_poly.data_ptr()))
+            mark("kate_division")
+            # phase 9: the IPA opening of the final polynomial
+            if self.ipa_params is None:
+                self.ipa_params = self._make_ipa_params()
+            self._ipa.create_proof(self.ipa_params, lambda: self.open_rng.randrange(self.ev.modulus), _NullTranscript(self.open_rng, self.ev.modulus),
+                                   self.coeff[0], 12345, 67890, rand_vector=lambda m: self.h_coeff[5].cpu().numpy().view(np.uint64))
+            mark("ipa_open")
         torch.cuda.synchronize()
         out = {}
         for (_, e_prev), (name, e) in zip(marks[:-1], marks[1:]):
@@ -234,6 +277,16 @@ class CreateProofModel:
         out["quotient_vm_ms"] = sum(b.elapsed_time(c) for _, b, c in spans)
         out["total_ms"] = marks[0][1].elapsed_time(marks[-1][1])
         return out
+
+    def _make_ipa_params(self):
+        """IpaParams over the model's synthetic generators (g = the first n points of the Lagrange bases' progression)."""
+        torch, ctx, n = self.torch, self.ctx, self.n
+        pts = torch.empty((n + 2, 8), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        synthetic.device_points(ctx, n + 2, pts.data_ptr())
+        ctx.sync()
+        host = pts.cpu().numpy().view(np.uint64)
+        return self._ipa.IpaParams(ctx, self.k, host[:n], host[n], host[n + 1])
 
     def close(self):
         lib = self.ctx.lib
