@@ -108,14 +108,19 @@ def _peaks():
 
 def _traffic_from_profiles():
     """dram bytes per launch of the dominant kernel from the committed ncu capture, if any (profiles/*.json)."""
-    p = os.path.join(ROOT, "profiles", "msm_accum_l1_ncu.json")
-    if os.path.exists(p):
+    import glob
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_accum_r*.json")), reverse=True):
         try:
             with open(p) as f:
-                return json.load(f).get("dram_bytes_per_launch")
+                rows = json.load(f)
+            for r in rows:
+                if "msm_accum_l1_kernel" in r.get("kernel", ""):
+                    tot = sum(float(r[k]) * scale[r[k + ".unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                    return int(tot), os.path.relpath(p, ROOT)
         except Exception:
-            return None
-    return None
+            continue
+    return None, None
 
 
 # -------------------------------------------------------------------------------------------------------------
@@ -293,7 +298,8 @@ def run_gpu(args):
         peak = int_peak_gmacs / 1e3
         share = {k: round(v[0] / elapsed_ms, 4) for k, v in prof.items() if v[1]}
         roofline = {"bound": "int32-pipe", "kernel": "msm_accum_l1_kernel", "achieved": achieved, "peak": peak, "unit": "TMAC/s",
-                    "frac": achieved / peak, "traffic": _traffic_from_profiles(),
+                    "frac": achieved / peak, "traffic": _traffic_from_profiles()[0],
+                    "traffic_unit": "dram bytes read+written per launch (ncu --set full)", "traffic_source": _traffic_from_profiles()[1],
                     "peak_source": "wide-MAC (IMAD.WIDE.U32.X chain) microbenchmark run in this process; MEASURED_PEAKS.json has no "
                                    "integer peak. Equivalent to SURVEY 8(d)'s model: 256 IMAD slots per Fmul against the 32-bit IMAD rate",
                     "imad32_tops": imad32_g / 1e3,
@@ -363,9 +369,10 @@ def measure_extras(pkg, ctx, stream, peaks, peak_src, int_peak_tmacs):
         best = min(runs, key=lambda r: r["total_ms"])
         out["create_proof_model"] = {"k": K_LOG, "seconds": best["total_ms"] / 1e3, "phases_ms": {k: round(v, 2) for k, v in best.items()},
                                      "shape": model.describe(),
-                                     "scope": "commit_lagrange x497, lagrange_to_coeff x497, coset NTT x497 and quotient program on 5 of the 8 cosets "
-                                              "(deg h < 5n), cosets_to_coeff, 6 coefficient-basis commits; excludes witness synthesis, lookup/permutation "
-                                              "products, evaluations, multiopen/IPA (SURVEY.md 8(f))"}
+                                     "scope": "commit_lagrange x497 with the lookup compression / permutation and the grand products between them, "
+                                              "lagrange_to_coeff x497, coset NTT x497 and quotient program on 5 of the 8 cosets (deg h < 5n), cosets_to_coeff, "
+                                              "6 coefficient-basis commits, evaluations at x and x*omega, kate_division x3, one IPA opening; excludes witness "
+                                              "synthesis, transcript hashing and multiopen's linear combinations"}
         model.close()
     except Exception as e:   # e.g. not enough free HBM next to other tenants; the headline line must still print
         out["create_proof_model"] = {"error": str(e)}
