@@ -216,6 +216,26 @@ int trp_dev_generator_collapse(trp_ctx* ctx, uint64_t* d_g /* 2 * half affine po
 int trp_dev_msm_var(trp_ctx* ctx, const uint64_t* d_bases /* n x 8 */, const uint64_t* d_scalars /* m x n x 4 */, size_t n, size_t m,
                     uint64_t* d_out_jacobian /* m x 12 */);
 
+/* ---- parameter generation: halo2_proofs 0.2.0 poly::commitment::Params::new(k), reached from
+ * /root/reference/src/test_utils.rs:21,89, and the pasta_curves 0.4.1 routines it calls (hashtocurve.rs, curves.rs) ----------- */
+/* CurveExt::hash_to_curve(domain_prefix) of the ctx's curve ("pallas" / "vesta") applied to n messages: expand_message_xmd over
+ * BLAKE2b-512, simplified SWU onto the iso-curve, sum of the two images, 3-isogeny.  Affine Montgomery results (identity = 0,0).
+ * Device form: message i = msg_prefix ++ (append_index ? u32_le(first_index + i) : nothing) -- Params::new hashes
+ * [0] ++ u32_le(i) for g[i], [1] for w and [2] for u.  Host form: n messages of msg_len bytes each. */
+int trp_dev_hash_to_curve(trp_ctx* ctx, const char* domain_prefix, const uint8_t* msg_prefix /* host */, size_t prefix_len,
+                          int append_index, uint64_t first_index, size_t n, uint64_t* d_out /* n x 8 */);
+int trp_hash_to_curve(trp_ctx* ctx, const char* domain_prefix, const uint8_t* messages /* n x msg_len */, size_t msg_len, size_t n,
+                      uint64_t* out /* n x 8 */);
+/* arithmetic::best_fft instantiated over curve points (the `Group` instance Params::new uses for g -> g_lagrange): in place over
+ * 2^log_n normalised affine points, natural order in and out, out[k] = sum_j [omega^(j k)] in[j]; omega (order 2^log_n) and the
+ * optional scale (every output multiplied by it; NULL = none) are Montgomery elements of the curve's SCALAR field. */
+int trp_dev_group_fft(trp_ctx* ctx, uint64_t* d_points /* 2^log_n x 8 */, unsigned log_n, const uint64_t omega[4], const uint64_t* scale);
+int trp_group_fft(trp_ctx* ctx, uint64_t* points, unsigned log_n, const uint64_t omega[4], const uint64_t* scale);
+/* Params::new(k): g[i] = hash_to_curve("Halo2-Parameters")([0] ++ u32_le(i)), g_lagrange = group iFFT of g (alpha^-1 =
+ * ROOT_OF_UNITY_INV^(2^(S-k)), then * TWO_INV^k), w = hash([1]), u = hash([2]).  n = 2^k affine points each. */
+int trp_params_new(trp_ctx* ctx, unsigned k, uint64_t* g, uint64_t* g_lagrange, uint64_t w[8], uint64_t u[8]);
+int trp_dev_params_new(trp_ctx* ctx, unsigned k, uint64_t* d_g, uint64_t* d_g_lagrange, uint64_t* d_wu /* w then u: 2 x 8 */);
+
 /* ---- glue / debug: elementwise field kernels over the ctx's scalar (field=0) or base (field=1) field ----
  * op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 sqr(a).  Host pointers.  Used by parity tests of K1 and by K7 callers. */
 int trp_field_op(trp_ctx* ctx, int which_field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);

@@ -296,6 +296,35 @@ def best_fft(F: Field, a, omega, log_n):
     return a
 
 
+def best_fft_group(C: "Curve", a, omega, log_n):
+    """best_fft instantiated over curve points (halo2_proofs::arithmetic::best_fft is generic over `Group`; Params::new uses
+    it on Vec<C::Curve>): the same butterflies, `t = a[hi] * twiddle` being a scalar multiplication.  Affine in / out."""
+    n = 1 << log_n
+    assert len(a) == n
+    p = C.scalar.p
+    a = list(a)
+    for k in range(n):
+        rk = bitreverse(k, log_n)
+        if k < rk:
+            a[k], a[rk] = a[rk], a[k]
+    tw = [1] * max(n // 2, 1)
+    for i in range(1, n // 2):
+        tw[i] = tw[i - 1] * omega % p
+    chunk, tchunk = 2, n // 2
+    for _ in range(log_n):
+        half = chunk // 2
+        for s in range(0, n, chunk):
+            for i in range(half):
+                w = tw[i * tchunk]
+                t = a[s + half + i] if w == 1 else C.mul(w, a[s + half + i])
+                u = a[s + i]
+                a[s + i] = C.add(u, t)
+                a[s + half + i] = C.add(u, C.neg(t))
+        chunk *= 2
+        tchunk //= 2
+    return a
+
+
 def naive_dft(F: Field, a, omega):
     n = len(a)
     return [sum(a[j] * pow(omega, j * k, F.p) for j in range(n)) % F.p for k in range(n)]

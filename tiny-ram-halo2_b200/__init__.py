@@ -11,11 +11,11 @@ The directory name contains '-', so import it through ``__graft_entry__.load_pac
 as ``tiny_ram_halo2_b200``) or put the repo root on sys.path and call that helper.
 """
 from ._lib import TrpError, Context, lib_path, load_library, PALLAS, VESTA, build_library  # noqa: F401
-from .arithmetic import best_multiexp, best_fft, Bases  # noqa: F401
+from .arithmetic import best_multiexp, best_fft, best_fft_group, hash_to_curve, Bases  # noqa: F401
 from .domain import EvaluationDomain  # noqa: F401
 from .commitment import Params  # noqa: F401
 from .poly import Evaluator, new_evaluator  # noqa: F401
 from . import permutation, lookup, ipa  # noqa: F401
 
-__all__ = ["TrpError", "Context", "Bases", "best_multiexp", "best_fft", "EvaluationDomain", "Params", "Evaluator", "new_evaluator",
+__all__ = ["TrpError", "Context", "Bases", "best_multiexp", "best_fft", "best_fft_group", "hash_to_curve", "EvaluationDomain", "Params", "Evaluator", "new_evaluator",
            "PALLAS", "VESTA", "lib_path", "load_library", "build_library"]

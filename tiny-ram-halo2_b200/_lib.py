@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "trp_dev_permute_expression_pair", "trp_permute_expression_pair",
     "trp_dev_eval_polynomials", "trp_eval_polynomial", "trp_dev_inner_products", "trp_compute_inner_product", "trp_dev_powers",
     "trp_dev_kate_division", "trp_kate_division", "trp_dev_fold", "trp_dev_generator_collapse", "trp_dev_msm_var",
+    "trp_dev_hash_to_curve", "trp_hash_to_curve", "trp_dev_group_fft", "trp_group_fft", "trp_params_new", "trp_dev_params_new",
 ]
 
 
@@ -130,6 +131,12 @@ def load_library():
     L.trp_dev_fold.argtypes = [vp, i, vp, sz, vp]
     L.trp_dev_generator_collapse.argtypes = [vp, vp, sz, vp]
     L.trp_dev_msm_var.argtypes = [vp, vp, vp, sz, sz, vp]
+    L.trp_dev_hash_to_curve.argtypes = [vp, ctypes.c_char_p, vp, sz, i, ctypes.c_uint64, sz, vp]
+    L.trp_hash_to_curve.argtypes = [vp, ctypes.c_char_p, vp, sz, sz, vp]
+    L.trp_dev_group_fft.argtypes = [vp, vp, u, vp, vp]
+    L.trp_group_fft.argtypes = [vp, vp, u, vp, vp]
+    L.trp_params_new.argtypes = [vp, u, vp, vp, vp, vp]
+    L.trp_dev_params_new.argtypes = [vp, u, vp, vp, vp]
     _lib = L
     return L
 

@@ -68,3 +68,34 @@ def best_fft(ctx: Context, a, omega, log_n: int):
     om = as_u64(omega).reshape(4)
     ctx.check(ctx.lib.trp_ntt(ctx.handle, ptr(arr), batch, log_n, ptr(om)))
     return arr
+
+
+def best_fft_group(ctx: Context, points, omega, log_n: int, scale=None):
+    """best_fft over curve points (the `Group` instance Params::new uses): ``points`` is (2^log_n, 8) normalised affine
+    Montgomery limbs (identity = all zero); out[k] = sum_j [omega^(jk)] points[j], every output times ``scale`` when given.
+    Returns a new array."""
+    arr = as_u64(points, copy=True)
+    if arr.size != 8 << log_n:
+        raise ValueError(f"a.len() = {arr.size // 8} != 1 << log_n = {1 << log_n}")
+    om = as_u64(omega).reshape(4)
+    sc = None if scale is None else as_u64(scale).reshape(4)
+    ctx.check(ctx.lib.trp_group_fft(ctx.handle, ptr(arr), log_n, ptr(om), ptr(sc)))
+    return arr.reshape(-1, 8)
+
+
+def hash_to_curve(ctx: Context, domain_prefix: str):
+    """CurveExt::hash_to_curve(domain_prefix) of the ctx's curve -> closure taking one message (bytes) or a list of
+    equal-length messages and returning (8,) / (n, 8) affine Montgomery limbs."""
+    prefix = domain_prefix.encode()
+
+    def hasher(message):
+        single = isinstance(message, (bytes, bytearray))
+        msgs = [bytes(message)] if single else [bytes(m) for m in message]
+        if len({len(m) for m in msgs}) > 1:
+            raise ValueError("messages of one call must have equal length")
+        buf = np.frombuffer(b"".join(msgs), dtype=np.uint8) if msgs and len(msgs[0]) else np.zeros(1, dtype=np.uint8)
+        out = np.zeros((len(msgs), 8), dtype=np.uint64)
+        ctx.check(ctx.lib.trp_hash_to_curve(ctx.handle, prefix, ptr(buf), len(msgs[0]) if msgs else 0, len(msgs), ptr(out)))
+        return out[0] if single else out
+
+    return hasher
