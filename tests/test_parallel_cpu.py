@@ -85,3 +85,61 @@ def test_partitions_cover_exactly():
             for c in range(n_cols):
                 r, j = PL.owner_of_column(c, world)
                 assert PL.shard_columns(n_cols, world, r)[j] == c
+
+
+# ---- coset split of the quotient evaluation ---------------------------------------------------------------
+def _coset_worker(rank, world, port, n_cols, q):
+    import random
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.load_package()
+    from tiny_ram_halo2_b200 import parallel as PL, poly as P
+    from util import pm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        F = pm.Fp
+        dom = pm.EvaluationDomain(F, 4, 3)                     # n = 8, 4 cosets of size 8 in the extended domain
+        n, ncos = dom.n, 1 << (dom.extended_k - dom.k)
+        rnd = random.Random(5)
+        coeff = [[rnd.randrange(F.p) for _ in range(n)] for _ in range(n_cols)]
+        leaves = [P.Poly(i % n_cols) for i in range(4)]
+        ast = leaves[0] * leaves[1].with_rotation(1) * leaves[2] - leaves[3] * 7 + P.LinearTerm(3) * leaves[0].with_rotation(-1)
+        to_t = lambda cols: (torch.from_numpy(np.stack([O.ints_to_limbs(c) for c in cols]).view(np.int64)) if len(cols)
+                             else torch.zeros((0, n, 4), dtype=torch.int64))
+        to_i = lambda t: [O.limbs_to_ints(c.numpy().view(np.uint64)) for c in t]
+
+        def eval_coset(all_coeff, cs):
+            ext = [dom.coeff_to_extended(c) for c in to_i(all_coeff)]
+            return to_t([pm.evaluate_ast(dom, ast, ext)[cs::ncos]])[0]
+
+        def combine(vals):
+            v = to_i(vals)
+            h_ext = [v[i % ncos][i // ncos] for i in range(dom.extended_len())]
+            return dom.extended_to_coeff(h_ext)
+
+        mine = PL.shard_columns(n_cols, world, rank)
+        got = PL.quotient_cosets_sharded(to_t([coeff[c] for c in mine]), n_cols, ncos, eval_coset, combine, dist)
+        want = dom.extended_to_coeff(pm.evaluate_ast(dom, ast, [dom.coeff_to_extended(c) for c in coeff]))
+        # the gather must also restore global column order
+        order_ok = to_i(PL.all_gather_columns(to_t([coeff[c] for c in mine]), n_cols, dist)) == coeff
+        q.put((rank, got == want, order_ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_cols", [5, 4, 1])
+def test_coset_split_world2_gloo(n_cols):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_coset_worker, args=(r, 2, port, n_cols, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] and r[2] for r in res), res

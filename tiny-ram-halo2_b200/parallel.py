@@ -6,6 +6,11 @@ Two natural partitions, neither needs a data-path collective beyond a small gath
   2. point-range split -- one large MSM: rank r takes points [r*n/G, (r+1)*n/G) with the matching slice of the (static,
                           pre-sharded) bases; the G partial sums are all_gathered and added (trp_points_sum), exactly how
                           best_multiexp combines its per-thread partial results.
+  3. coset split       -- the extended domain is 2^(extended_k - k) cosets of size n and deg h < (j - 1) n, so j - 1 cosets
+                          determine the quotient: after ONE all_gather of the coefficient-form columns (the path's only bulk
+                          exchange, n_cols * n * 32 B in total), rank r evaluates cosets r, r + G, ... (coset NTT of every
+                          column + the quotient program), the n-value results are all_gathered (j - 1 columns in total) and
+                          every rank recovers h(X) (trp_dev_cosets_to_coeff) for the column-sharded commits of its pieces.
 The functions take the commit / add operations as callables so the same logic runs over NCCL with the CUDA library and
 over gloo on CPU in the tests (with the oracle standing in for the device)."""
 from __future__ import annotations
@@ -71,3 +76,46 @@ def msm_point_split(scalars_local, msm_local: Callable, points_sum: Callable, di
     t = torch.from_numpy(part.view(np.int64).copy()).to(device)
     parts = np.stack([p.cpu().numpy().view(np.uint64) for p in _all_gather(t, dist)])
     return points_sum(parts)
+
+
+def shard_cosets(n_cosets: int, world: int, rank: int) -> List[int]:
+    """round-robin: coset j belongs to rank j % world"""
+    return list(range(rank, n_cosets, world))
+
+
+def all_gather_columns(local, n_cols: int, dist=None):
+    """local: torch tensor (len(shard_columns(n_cols, world, rank)), ...) of this rank's columns, on the device the process
+    group communicates from (cuda for nccl, cpu for gloo).  Returns (n_cols, ...) in GLOBAL column order on every rank."""
+    import torch
+    if dist is None or dist.get_world_size() == 1:
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per_rank = (n_cols + world - 1) // world
+    mine = len(shard_columns(n_cols, world, rank))
+    if local.shape[0] != mine:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} columns, expected {mine}")
+    padded = local
+    if mine < per_rank:
+        padded = torch.zeros((per_rank,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        padded[:mine].copy_(local)
+    gathered = torch.empty((world, per_rank) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather(list(gathered.unbind(0)), padded.contiguous())
+    # (rank, slot) -> global column slot * world + rank
+    return gathered.transpose(0, 1).reshape((per_rank * world,) + tuple(local.shape[1:]))[:n_cols]
+
+
+def quotient_cosets_sharded(coeff_local, n_cols: int, n_cosets: int, eval_coset: Callable, combine: Callable, dist=None):
+    """coeff_local: this rank's coefficient-form columns (shard_columns order), torch tensor (mine, n, 4).
+    eval_coset(all_coeff (n_cols, n, 4), coset) -> (n, 4) tensor: the quotient numerator on that coset;
+    combine(vals (n_cosets, n, 4)) -> the quotient's coefficients.  Every rank returns combine's result."""
+    import torch
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    all_coeff = all_gather_columns(coeff_local, n_cols, dist)
+    mine = shard_cosets(n_cosets, world, rank)
+    vals = [eval_coset(all_coeff, cs) for cs in mine]
+    if vals:
+        local = torch.stack(vals)
+    else:
+        local = torch.zeros((0,) + tuple(coeff_local.shape[1:]), dtype=coeff_local.dtype, device=coeff_local.device)
+    return combine(all_gather_columns(local, n_cosets, dist))
