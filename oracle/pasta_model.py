@@ -511,7 +511,7 @@ def batch_invert(F: Field, vals):
     return out
 
 
-def permutation_commit(F: Field, omega, n, values, permutations, beta, gamma, chunk_len, blinding_factors, rand):
+def permutation_commit(F: Field, omega, n, values, permutations, beta, gamma, chunk_len, blinding_factors, rand, after_chunk=None):
     """plonk::permutation::prover::Argument::commit: one grand-product column Z per chunk of `chunk_len` columns.
     values[c] / permutations[c]: the n Lagrange values of column c and of its sigma polynomial; rand() draws a scalar
     (blinding rows of every Z, in order).  Returns the Z columns (blind scalars / commitments are the caller's)."""
@@ -537,6 +537,8 @@ def permutation_commit(F: Field, omega, n, values, permutations, beta, gamma, ch
             z[i] = rand()
         last_z = z[n - (blinding_factors + 1)]
         sets.append(z)
+        if after_chunk is not None:          # create_proof draws the chunk's blind and commits before the next chunk starts
+            after_chunk(z)
     return sets
 
 

@@ -1,0 +1,104 @@
+"""CPU tests of the row-f4 host logic (tiny-ram-halo2_b200/plonk.py: ConstraintSystem, keygen, create_proof, the Blake2b
+transcript) run over the oracle's PythonBackend, against the independent verifier oracle/plonk_model.verify_proof."""
+import random
+
+import pytest
+
+from util import pm
+
+import params_model as prm
+import plonk_model as VM
+import plonk_circuits
+
+
+@pytest.fixture(scope="module")
+def PL():
+    import __graft_entry__ as ge
+    ge.load_package()
+    from tiny_ram_halo2_b200 import plonk
+    return plonk
+
+
+def _prove(PL, C, k, seed=1, mutate=None, **kw):
+    cs, fixed, copies, adv, inst = plonk_circuits.standard(PL, **kw)
+    if mutate:
+        mutate(adv, inst, fixed)
+    be = VM.PythonBackend(C, k, cs.degree())
+    pk = PL.keygen(be, cs, fixed, copies)
+    rnd = random.Random(seed)
+    tr = PL.Blake2bWrite(C.base.p, C.scalar.p)
+    proof = PL.create_proof(be, pk, inst, adv, lambda: rnd.randrange(C.scalar.p), tr)
+    return be, pk, inst, proof
+
+
+@pytest.mark.parametrize("C", [pm.Vesta, pm.Pallas], ids=["vesta", "pallas"])
+@pytest.mark.parametrize("kw", [dict(with_lookup=True), dict(with_lookup=False), dict(with_lookup=True, wide_lookup=True)],
+                         ids=["lookup", "no-lookup", "wide-lookup"])
+def test_proof_verifies(PL, C, kw):
+    be, pk, inst, proof = _prove(PL, C, 4, **kw)
+    assert VM.verify_proof(C, be.params, pk.vk, inst, proof)
+    # soundness smoke: wrong public input, flipped bytes, truncated proof are all rejected
+    assert not VM.verify_proof(C, be.params, pk.vk, [[inst[0][0] + 1]], proof)
+    for pos in (0, 40, len(proof) // 2, len(proof) - 1):
+        bad = bytearray(proof); bad[pos] ^= 1
+        assert not VM.verify_proof(C, be.params, pk.vk, inst, bytes(bad))
+    assert not VM.verify_proof(C, be.params, pk.vk, inst, proof[:-32])
+    assert not VM.verify_proof(C, be.params, pk.vk, inst, proof + bytes(32))
+
+
+def test_unsatisfied_circuits_do_not_verify(PL):
+    C = pm.Vesta
+    def break_gate(adv, inst, fixed): adv[2][0] += 1                 # a + b != c on row 0 (also breaks the copy c[0] = a[1])
+    be, pk, inst, proof = _prove(PL, C, 4, mutate=break_gate)
+    assert not VM.verify_proof(C, be.params, pk.vk, inst, proof)
+    def break_copy(adv, inst, fixed): inst[0][0] += 1                # public input differs from the copied cell
+    be, pk, inst, proof = _prove(PL, C, 4, mutate=break_copy)
+    assert not VM.verify_proof(C, be.params, pk.vk, inst, proof)
+    def break_lookup(adv, inst, fixed): adv[0][3] = 9; adv[1][3] = 9      # a = 9 is not in the table 0..7 (copy a[3] = b[3] kept)
+    with pytest.raises(ValueError):
+        _prove(PL, C, 4, mutate=break_lookup)
+
+
+def test_proof_layout_and_determinism(PL):
+    C = pm.Vesta
+    be, pk, inst, p1 = _prove(PL, C, 4, seed=7)
+    _, _, _, p2 = _prove(PL, C, 4, seed=7)
+    _, _, _, p3 = _prove(PL, C, 4, seed=8)
+    assert p1 == p2 and p1 != p3
+    cs = pk.vk.cs
+    n_sets = 2
+    points = cs.num_advice + 2 * len(cs.lookups) + n_sets + len(cs.lookups) + 1 + (pk.vk.cs_degree - 1) + 1 + 1 + 2 * be.k
+    n_q = sum(len(v) for v in cs.queries.values())
+    scalars = n_q + 1 + len(cs.permutation) + (3 * n_sets - 1) + 5 * len(cs.lookups) + 2
+    assert (len(p1) - 32 * (points + scalars)) % 32 == 0
+    n_point_sets = (len(p1) - 32 * (points + scalars)) // 32
+    assert 1 <= n_point_sets <= 5
+    assert cs.degree() == 5 and cs.blinding_factors() == 5
+
+
+def test_multiopen_point_sets(PL):
+    """construct_intermediate_sets on the pattern create_proof produces: sets are keyed by the SET of points of a commitment"""
+    qs = [("a", 10), ("a", 11), ("b", 10), ("c", 11), ("c", 10), ("d", 12), ("d", 10)]
+    cmap, point_sets = PL.construct_intermediate_sets(qs, lambda q: q[0], lambda q: q[1], lambda q: (q[0], q[1]))
+    assert [cd["set_index"] for cd in cmap] == [0, 1, 0, 2]
+    assert point_sets == [[10, 11], [10], [10, 12]]
+    assert cmap[2]["evals"] == [("c", 10), ("c", 11)]
+    F = pm.Fp
+    pts, ev = [3, 5, 11], [7, 1, 20]
+    coeffs = PL.lagrange_interpolate(pts, ev, F.p)
+    assert [pm.eval_polynomial(F, coeffs, x) for x in pts] == ev
+
+
+def test_keygen_permutation_cycles(PL):
+    cs, fixed, copies, adv, inst = plonk_circuits.standard(PL)
+    F = pm.Fp
+    n = 16
+    omega = F.root_of_unity(4)
+    sig = PL.build_sigmas(cs, n, F.p, omega, F.DELTA, copies)
+    ident = [[pow(F.DELTA, i, F.p) * pow(omega, j, F.p) % F.p for j in range(n)] for i in range(len(cs.permutation))]
+    # sigma is a permutation of the identity labels that fixes every cell outside the copy constraints
+    assert sorted(v for col in sig for v in col) == sorted(v for col in ident for v in col)
+    moved = {(i, j) for i in range(len(sig)) for j in range(n) if sig[i][j] != ident[i][j]}
+    col_of = {kc: i for i, kc in enumerate(cs.permutation)}
+    touched = {(col_of[(k_, c)], r) for pair in copies for (k_, c, r) in pair}
+    assert moved == touched

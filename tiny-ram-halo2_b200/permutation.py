@@ -23,10 +23,11 @@ def _to_int(l):
     return int(l[0]) | int(l[1]) << 64 | int(l[2]) << 128 | int(l[3]) << 192
 
 
-def commit(domain, values, permutations, beta, gamma, chunk_len, blinding_factors, rand):
+def commit(domain, values, permutations, beta, gamma, chunk_len, blinding_factors, rand, after_chunk=None):
     """values / permutations: (m, n, 4) uint64 Montgomery columns (the column's Lagrange values / its sigma polynomial);
     beta, gamma: canonical Python ints; rand() returns a canonical int (the caller's RNG, drawn for the last
-    `blinding_factors` rows of every Z in order).  Returns the list of Z columns, each (n, 4) Montgomery."""
+    `blinding_factors` rows of every Z in order); after_chunk(z), if given, runs after each Z is complete.  Returns the list
+    of Z columns, each (n, 4) Montgomery."""
     ctx = domain.ctx
     p = _MODULUS[ctx.curve]
     R = (1 << 256) % p
@@ -50,4 +51,6 @@ def commit(domain, values, permutations, beta, gamma, chunk_len, blinding_factor
             z[i] = mont(rand())
         last_z = z[n - (blinding_factors + 1)].copy()
         sets.append(z)
+        if after_chunk is not None:          # create_proof draws the chunk's blind and commits before the next chunk starts
+            after_chunk(z)
     return sets
