@@ -33,6 +33,21 @@ extern "C" {
     pub fn trp_extended_to_coeff(d: *mut trp_domain, ext: *mut u64, out_coeff: *mut u64, divide: c_int) -> c_int;
     pub fn trp_quotient_eval(d: *mut trp_domain, prog: *const u32, prog_len: usize, consts: *const u64, n_consts: usize,
                              cols: *const *const u64, n_cols: usize, out_ext: *mut u64) -> c_int;
+    // rows f1-f3 of the scope table: the callers either side of the hot kernels (host-pointer forms)
+    pub fn trp_batch_invert(ctx: *mut trp_ctx, which_field: c_int, a: *mut u64, n: usize) -> c_int;
+    pub fn trp_permutation_product(d: *mut trp_domain, values: *const *const u64, sigmas: *const *const u64, m: usize, beta: *const u64,
+                                   gamma: *const u64, delta_beta: *const u64, last_z: *const u64, z: *mut u64) -> c_int;
+    pub fn trp_lookup_product(d: *mut trp_domain, input: *const u64, table: *const u64, perm_input: *const u64, perm_table: *const u64,
+                              beta: *const u64, gamma: *const u64, z: *mut u64, n_out: usize) -> c_int;
+    pub fn trp_permute_expression_pair(ctx: *mut trp_ctx, input: *const u64, table: *const u64, rows: usize, perm_input: *mut u64,
+                                       perm_table: *mut u64, all_found: *mut c_int) -> c_int;
+    pub fn trp_eval_polynomial(ctx: *mut trp_ctx, which_field: c_int, coeffs: *const u64, n: usize, x: *const u64, out: *mut u64) -> c_int;
+    pub fn trp_compute_inner_product(ctx: *mut trp_ctx, which_field: c_int, a: *const u64, b: *const u64, n: usize, out: *mut u64) -> c_int;
+    pub fn trp_kate_division(ctx: *mut trp_ctx, which_field: c_int, coeffs: *const u64, n: usize, b: *const u64, q: *mut u64) -> c_int;
+    /// Params::new(k): g, g_lagrange (2^k affine points each, 8 x u64), w, u
+    pub fn trp_params_new(ctx: *mut trp_ctx, k: c_uint, g: *mut u64, g_lagrange: *mut u64, w: *mut u64, u: *mut u64) -> c_int;
+    pub fn trp_hash_to_curve(ctx: *mut trp_ctx, domain_prefix: *const c_char, messages: *const u8, msg_len: usize, n: usize, out: *mut u64) -> c_int;
+    pub fn trp_group_fft(ctx: *mut trp_ctx, points: *mut u64, log_n: c_uint, omega: *const u64, scale: *const u64) -> c_int;
 }
 
 /// One context per (device, curve); halo2 calls are synchronous, so a process-wide handle behind a mutex is enough.
