@@ -632,16 +632,13 @@ class GpuBackend:
     def _limbs(self, vals, mod=None, R=None):
         np = self.np
         mod, R = mod or self.p, R or self.R
-        out = np.zeros((len(vals), 4), dtype=np.uint64)
-        for i, v in enumerate(vals):
-            m = v % mod * R % mod
-            out[i] = [(m >> (64 * l)) & 0xFFFFFFFFFFFFFFFF for l in range(4)]
-        return out
+        buf = b"".join((v % mod * R % mod).to_bytes(32, "little") for v in vals)
+        return np.frombuffer(buf, dtype=np.uint64).reshape(len(vals), 4).copy()
 
     def _ints(self, arr, mod=None, Rinv=None):
         mod, Rinv = mod or self.p, Rinv or self.Rinv
-        a = self.np.asarray(arr, dtype=self.np.uint64).reshape(-1, 4)
-        return [(int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192) * Rinv % mod for r in a]
+        raw = self.np.ascontiguousarray(arr, dtype=self.np.uint64).reshape(-1, 4).tobytes()
+        return [int.from_bytes(raw[i:i + 32], "little") * Rinv % mod for i in range(0, len(raw), 32)]
 
     def _point(self, jac):
         """normalised Jacobian (3, 4) -> affine tuple / None"""
