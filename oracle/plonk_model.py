@@ -35,6 +35,46 @@ class PythonBackend:
     def rotate_omega(self, x, rotation):
         return self.dom.rotate_omega(x, rotation)
 
+    # -- vectors are plain lists of n canonical ints
+    def vec(self, values):
+        if len(values) > self.n:
+            raise ValueError("column longer than the domain")
+        return [v % self.p for v in values] + [0] * (self.n - len(values))
+
+    def set_rows(self, v, start, values):
+        v[start:start + len(values)] = [x % self.p for x in values]
+        return v
+
+    def random_vec(self, rand): return [rand() for _ in range(self.n)]
+
+    def mul_add(self, acc, s, v):
+        return list(v) if acc is None else [(a * s + c) % self.p for a, c in zip(acc, v)]
+
+    def sub_low(self, v, low):
+        out = list(v)
+        for i, r in enumerate(low):
+            out[i] = (out[i] - r) % self.p
+        return out
+
+    def sigma_vecs(self, m, moved):
+        p, n = self.p, self.n
+        om = [1] * n
+        for j in range(1, n):
+            om[j] = om[j - 1] * self.omega % p
+        dl = [pow(self.delta, i, p) for i in range(max(m, 1))]
+        out = [[dl[i] * om[j] % p for j in range(n)] for i in range(m)]
+        for (i, j), (i2, j2) in moved.items():
+            out[i][j] = dl[i2] * om[j2] % p
+        return out
+
+    def compress(self, exprs, theta, values_of):
+        p, n = self.p, self.n
+        out = [0] * n
+        for e in exprs:
+            for r in range(n):
+                out[r] = (out[r] * theta + _eval_expr(e, p, lambda q: values_of[q.kind][q.column][(r + q.rotation) % n])) % p
+        return out
+
     def commit_lagrange(self, values, blind):
         return self.C.best_multiexp(list(values) + [blind], self.params["g_lagrange"] + [self.params["w"]])
 
@@ -46,10 +86,11 @@ class PythonBackend:
 
     def quotient(self, ast, ext_polys):
         h = pm.evaluate_ast(self.dom, ast, ext_polys)
-        return self.dom.extended_to_coeff(self.dom.divide_by_vanishing_poly(h))
+        h = self.dom.extended_to_coeff(self.dom.divide_by_vanishing_poly(h))
+        return [h[i * self.n:(i + 1) * self.n] for i in range(self.j - 1)]
 
     def eval_polynomial(self, coeffs, x): return pm.eval_polynomial(self.F, coeffs, x)
-    def kate_division(self, coeffs, b): return pm.kate_division(self.F, list(coeffs), b)
+    def kate_division(self, coeffs, b): return pm.kate_division(self.F, list(coeffs), b) + [0]
 
     def permutation_commit(self, values, sigmas, beta, gamma, chunk_len, blinding_factors, rand, after_chunk):
         return pm.permutation_commit(self.F, self.omega, self.n, values, sigmas, beta, gamma, chunk_len, blinding_factors, rand, after_chunk)
@@ -58,7 +99,7 @@ class PythonBackend:
         r = pm.permute_expression_pair(self.F, inp, tab, usable_rows)
         if r is None:
             raise ValueError("ConstraintSystemFailure: lookup input value not present in the table")
-        return r
+        return r[0] + [0] * (self.n - usable_rows), r[1] + [0] * (self.n - usable_rows)
 
     def lookup_product(self, ci, ct, pi, pt, beta, gamma, blinding_factors, rand):
         return pm.lookup_commit_product(self.F, self.n, ci, ct, pi, pt, beta, gamma, blinding_factors, rand)

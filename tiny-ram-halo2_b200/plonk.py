@@ -239,53 +239,65 @@ class ProvingKey:
     l_last: object
 
 
-def build_sigmas(cs: ConstraintSystem, n: int, p: int, omega: int, delta: int, copies):
-    """permutation::keygen::Assembly (copy -> cycle merge) and build_pk's sigma values: sigma_i[j] = delta^i' * omega^j' for the
-    cell (i', j') that (i, j) maps to.  copies: ((kind, column, row), (kind, column, row)) pairs."""
-    m = len(cs.permutation)
+def permutation_mapping(cs: ConstraintSystem, n: int, copies):
+    """permutation::keygen::Assembly: cycles of the copy constraints (copy -> merge the two cycles, smaller into larger).
+    Returns {(column, row): (column', row')} for the cells whose image differs from themselves; column = index into
+    cs.permutation.  copies: ((kind, column, row), (kind, column, row)) pairs.  Cells no copy touches never enter the dict,
+    so keygen stays O(copies) however large n is."""
     col_of = {kc: i for i, kc in enumerate(cs.permutation)}
-    mapping = [[(i, j) for j in range(n)] for i in range(m)]
-    aux = [[(i, j) for j in range(n)] for i in range(m)]
-    sizes = [[1] * n for _ in range(m)]
+    mapping, aux, sizes = {}, {}, {}
     for (lk, lc, lr), (rk, rc, rr) in copies:
         if (lk, lc) not in col_of or (rk, rc) not in col_of:
             raise ValueError("copy constraint on a column without enable_equality")
         left, right = (col_of[(lk, lc)], lr), (col_of[(rk, rc)], rr)
-        lcyc, rcyc = aux[left[0]][left[1]], aux[right[0]][right[1]]
+        if not (0 <= lr < n and 0 <= rr < n):
+            raise ValueError("copy constraint outside the domain")
+        lcyc, rcyc = aux.get(left, left), aux.get(right, right)
         if lcyc == rcyc:
             continue
-        if sizes[lcyc[0]][lcyc[1]] < sizes[rcyc[0]][rcyc[1]]:
+        if sizes.get(lcyc, 1) < sizes.get(rcyc, 1):
             lcyc, rcyc = rcyc, lcyc
-        sizes[lcyc[0]][lcyc[1]] += sizes[rcyc[0]][rcyc[1]]
+        sizes[lcyc] = sizes.get(lcyc, 1) + sizes.get(rcyc, 1)
         i = rcyc
         while True:
-            aux[i[0]][i[1]] = lcyc
-            i = mapping[i[0]][i[1]]
+            aux[i] = lcyc
+            i = mapping.get(i, i)
             if i == rcyc:
                 break
-        mapping[left[0]][left[1]], mapping[right[0]][right[1]] = mapping[right[0]][right[1]], mapping[left[0]][left[1]]
+        ml, mr = mapping.get(left, left), mapping.get(right, right)
+        mapping[left], mapping[right] = mr, ml
+    return {c: t for c, t in mapping.items() if c != t}
+
+
+def build_sigmas(cs: ConstraintSystem, n: int, p: int, omega: int, delta: int, copies):
+    """build_pk's sigma values as dense int lists: sigma_i[j] = delta^i' * omega^j' for the cell (i', j') that (i, j) maps to"""
+    m = len(cs.permutation)
+    moved = permutation_mapping(cs, n, copies)
     om = [1] * n
     for j in range(1, n):
         om[j] = om[j - 1] * omega % p
     dl = [1] * max(m, 1)
     for i in range(1, m):
         dl[i] = dl[i - 1] * delta % p
-    return [[dl[mapping[i][j][0]] * om[mapping[i][j][1]] % p for j in range(n)] for i in range(m)]
+    out = [[dl[i] * om[j] % p for j in range(n)] for i in range(m)]
+    for (i, j), (i2, j2) in moved.items():
+        out[i][j] = dl[i2] * om[j2] % p
+    return out
 
 
 def keygen(backend, cs: ConstraintSystem, fixed_values, copies=()) -> ProvingKey:
-    """keygen_vk + keygen_pk.  fixed_values: one list per fixed column (padded with zeros to n)."""
+    """keygen_vk + keygen_pk.  fixed_values: one column per fixed column -- a list of at most n ints (zero-padded) or a
+    backend vector."""
     n, p = backend.n, backend.p
     if n < cs.minimum_rows():
         raise ValueError("NotEnoughRowsAvailable")
     if backend.j != cs.degree():
         raise ValueError("the backend's EvaluationDomain was built for a different constraint-system degree")
-    pad = lambda v: [x % p for x in v] + [0] * (n - len(v))
-    fixed_values = [pad(v) for v in fixed_values]
-    if len(fixed_values) != cs.num_fixed or any(len(v) != n for v in fixed_values):
-        raise ValueError("one column of at most n values per fixed column")
+    if len(fixed_values) != cs.num_fixed:
+        raise ValueError("one column per fixed column")
+    fixed_values = [backend.vec(v) for v in fixed_values]
     fixed_commitments = [backend.commit_lagrange(v, 1) for v in fixed_values]          # Blind::default() = 1
-    sigma_values = build_sigmas(cs, n, p, backend.omega, backend.delta, copies)
+    sigma_values = backend.sigma_vecs(len(cs.permutation), permutation_mapping(cs, n, copies))
     permutation_commitments = [backend.commit_lagrange(v, 1) for v in sigma_values]
     pt = lambda c: "Identity" if c is None else f"({c[0]:#066x}, {c[1]:#066x})"
     text = (f"PinnedVerificationKey {{ base_modulus: {backend.q:#066x}, scalar_modulus: {p:#066x}, domain: PinnedEvaluationDomain {{ k: {backend.k}, "
@@ -297,9 +309,9 @@ def keygen(backend, cs: ConstraintSystem, fixed_values, copies=()) -> ProvingKey
     sigma_polys = [backend.lagrange_to_coeff(v) for v in sigma_values]
     bf = cs.blinding_factors()
     ext = lambda lag: backend.coeff_to_extended(backend.lagrange_to_coeff(lag))
-    l0 = [0] * n; l0[0] = 1
-    l_blind = [0] * (n - bf) + [1] * bf
-    l_last = [0] * n; l_last[n - bf - 1] = 1
+    l0 = backend.vec([1])
+    l_blind = backend.set_rows(backend.vec([]), n - bf, [1] * bf)
+    l_last = backend.set_rows(backend.vec([]), n - bf - 1, [1])
     return ProvingKey(vk, fixed_values, fixed_polys, [backend.coeff_to_extended(c) for c in fixed_polys], sigma_values, sigma_polys,
                       [backend.coeff_to_extended(c) for c in sigma_polys], ext(l0), ext(l_blind), ext(l_last))
 
@@ -370,67 +382,57 @@ class _Opening:
 
 
 def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], int], transcript: Blake2bWrite) -> bytes:
-    """plonk::create_proof for ONE circuit instance.  instances: one list per instance column (at most usable_rows values);
-    advice: one list per advice column (values on the usable rows; the blinding rows are drawn here).  rand() draws one
-    uniformly random scalar (the caller's RNG: every draw happens in halo2's order).  Returns the proof bytes (also left in
-    `transcript`)."""
+    """plonk::create_proof for ONE circuit instance.  instances: one column per instance column, advice: one per advice column
+    -- lists of at most usable_rows ints, or backend vectors of n values whose blinding rows are overwritten here.  rand()
+    draws one uniformly random scalar (the caller's RNG: every draw happens in halo2's order).  Polynomials are opaque backend
+    vectors throughout; only scalars, points and the few interpolation coefficients live on the host.  Returns the proof
+    bytes (also left in `transcript`)."""
+    B = backend
     vk, cs = pk.vk, pk.vk.cs
-    n, p, k = backend.n, backend.p, backend.k
+    n, p, k = B.n, B.p, B.k
     bf = cs.blinding_factors()
     usable = n - (bf + 1)
-    rot = backend.rotate_omega
+    rot = B.rotate_omega
     if len(instances) != cs.num_instance or len(advice) != cs.num_advice:
         raise ValueError("InvalidInstances / wrong number of advice columns")
     transcript.common_scalar(vk.transcript_repr)
 
+    def column(col, what):
+        if isinstance(col, (list, tuple)) and len(col) > usable:
+            raise ValueError(f"{what} column longer than the usable rows")
+        return B.vec(col)
+
     # ---- instance columns: commit (not written, only absorbed) -------------------------------------------------------------
-    inst_values = []
-    for col in instances:
-        if len(col) > usable:
-            raise ValueError("InstanceTooLarge")
-        inst_values.append([v % p for v in col] + [0] * (n - len(col)))
+    inst_values = [column(c, "InstanceTooLarge: instance") for c in instances]
     for v in inst_values:
-        transcript.common_point(backend.commit_lagrange(v, 1))
-    inst_polys = [backend.lagrange_to_coeff(v) for v in inst_values]
-    inst_cosets = [backend.coeff_to_extended(c) for c in inst_polys]
+        transcript.common_point(B.commit_lagrange(v, 1))
+    inst_polys = [B.lagrange_to_coeff(v) for v in inst_values]
+    inst_cosets = [B.coeff_to_extended(c) for c in inst_polys]
 
     # ---- advice columns --------------------------------------------------------------------------------------------------------
-    adv_values = []
-    for col in advice:
-        if len(col) > usable:
-            raise ValueError("advice column longer than the usable rows")
-        adv_values.append([v % p for v in col] + [0] * (n - len(col)))
+    adv_values = [column(c, "advice") for c in advice]
     for v in adv_values:
-        for r in range(usable, n):
-            v[r] = rand()
+        B.set_rows(v, usable, [rand() for _ in range(usable, n)])
     adv_blinds = [rand() for _ in adv_values]
     for v, b in zip(adv_values, adv_blinds):
-        transcript.write_point(backend.commit_lagrange(v, b))
-    adv_polys = [backend.lagrange_to_coeff(v) for v in adv_values]
-    adv_cosets = [backend.coeff_to_extended(c) for c in adv_polys]
+        transcript.write_point(B.commit_lagrange(v, b))
+    adv_polys = [B.lagrange_to_coeff(v) for v in adv_values]
+    adv_cosets = [B.coeff_to_extended(c) for c in adv_polys]
     values_of = {ADVICE: adv_values, FIXED: pk.fixed_values, INSTANCE: inst_values}
 
     # ---- lookups: commit_permuted -------------------------------------------------------------------------------------------------
     theta = transcript.squeeze_challenge_scalar()
-
-    def compress(exprs):
-        out = [0] * n
-        for e in exprs:
-            for r in range(n):
-                out[r] = (out[r] * theta + evaluate_expression(e, p, lambda q: values_of[q.kind][q.column][(r + q.rotation) % n])) % p
-        return out
-
     lookups = []
     for inputs, tables in cs.lookups:
-        ci, ct = compress(inputs), compress(tables)
-        pi, pt = backend.permute_expression_pair(ci, ct, usable)
-        pi = list(pi) + [rand() for _ in range(bf + 1)]
-        pt = list(pt) + [rand() for _ in range(bf + 1)]
+        ci, ct = B.compress(inputs, theta, values_of), B.compress(tables, theta, values_of)
+        pi, pt = B.permute_expression_pair(ci, ct, usable)
+        B.set_rows(pi, usable, [rand() for _ in range(bf + 1)])
+        B.set_rows(pt, usable, [rand() for _ in range(bf + 1)])
         L = {"ci": ci, "ct": ct, "pi": pi, "pt": pt}
         for name in ("pi", "pt"):
-            L[name + "_poly"] = backend.lagrange_to_coeff(L[name])
+            L[name + "_poly"] = B.lagrange_to_coeff(L[name])
             L[name + "_blind"] = rand()
-            transcript.write_point(backend.commit_lagrange(L[name], L[name + "_blind"]))
+            transcript.write_point(B.commit_lagrange(L[name], L[name + "_blind"]))
         lookups.append(L)
 
     # ---- permutation and lookup grand products ----------------------------------------------------------------------------------------
@@ -441,24 +443,24 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
 
     def after_chunk(z):
         blind = rand()
-        transcript.write_point(backend.commit_lagrange(z, blind))
+        transcript.write_point(B.commit_lagrange(z, blind))
         perm_sets.append({"z": z, "blind": blind})
 
     if cs.permutation:
-        backend.permutation_commit([values_of[kk][c] for kk, c in cs.permutation], pk.sigma_values, beta, gamma, chunk_len, bf, rand, after_chunk)
+        B.permutation_commit([values_of[kk][c] for kk, c in cs.permutation], pk.sigma_values, beta, gamma, chunk_len, bf, rand, after_chunk)
     for S in perm_sets:
-        S["poly"] = backend.lagrange_to_coeff(S["z"])
-        S["coset"] = backend.coeff_to_extended(S["poly"])
+        S["poly"] = B.lagrange_to_coeff(S["z"])
+        S["coset"] = B.coeff_to_extended(S["poly"])
     for L in lookups:
-        L["z"] = backend.lookup_product(L["ci"], L["ct"], L["pi"], L["pt"], beta, gamma, bf, rand)
+        L["z"] = B.lookup_product(L["ci"], L["ct"], L["pi"], L["pt"], beta, gamma, bf, rand)
         L["z_blind"] = rand()
-        transcript.write_point(backend.commit_lagrange(L["z"], L["z_blind"]))
-        L["z_poly"] = backend.lagrange_to_coeff(L["z"])
+        transcript.write_point(B.commit_lagrange(L["z"], L["z_blind"]))
+        L["z_poly"] = B.lagrange_to_coeff(L["z"])
 
     # ---- vanishing argument: random polynomial ------------------------------------------------------------------------------------------
-    random_poly = [rand() for _ in range(n)]
+    random_poly = B.random_vec(rand)
     random_blind = rand()
-    transcript.write_point(backend.commit(random_poly, random_blind))
+    transcript.write_point(B.commit(random_poly, random_blind))
 
     # ---- quotient --------------------------------------------------------------------------------------------------------------------
     y = transcript.squeeze_challenge_scalar()
@@ -493,18 +495,18 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
         for i, z in enumerate(zs):
             cols = cs.permutation[i * chunk_len:(i + 1) * chunk_len]
             left, right = z.with_rotation(1), z
-            cur_delta = beta * pow(backend.delta, i * chunk_len, p) % p
+            cur_delta = beta * pow(B.delta, i * chunk_len, p) % p
             for off, (kk, c) in enumerate(cols):
                 col = leaf((kk, c), cos_of[kk][c])
                 sig = leaf(("sigma", i * chunk_len + off), pk.sigma_cosets[i * chunk_len + off])
                 left = left * (col + sig * beta + gamma)
                 right = right * (col + P.LinearTerm(cur_delta) + gamma)
-                cur_delta = cur_delta * backend.delta % p
+                cur_delta = cur_delta * B.delta % p
             exprs.append((left - right) * active)
     for li, (L, (inputs, tables)) in enumerate(zip(lookups, cs.lookups)):
-        z = leaf(("lookup_z", li), backend.coeff_to_extended(L["z_poly"]))
-        a = leaf(("lookup_a", li), backend.coeff_to_extended(L["pi_poly"]))
-        s = leaf(("lookup_s", li), backend.coeff_to_extended(L["pt_poly"]))
+        z = leaf(("lookup_z", li), B.coeff_to_extended(L["z_poly"]))
+        a = leaf(("lookup_a", li), B.coeff_to_extended(L["pi_poly"]))
+        s = leaf(("lookup_s", li), B.coeff_to_extended(L["pt_poly"]))
         comp = lambda es: P.DistributePowers([to_ast(e) for e in es], P.ConstantTerm(theta)) if len(es) > 1 else to_ast(es[0])
         exprs.append(l0 * (one - z))
         exprs.append(l_last * (z * z - z))
@@ -514,35 +516,42 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     h_ast = P.ConstantTerm(0)
     for e in exprs:
         h_ast = h_ast * y + e
-    h_coeffs = backend.quotient(h_ast, ext_polys)                       # n * (j - 1) coefficients of h(X)
-    pieces = [h_coeffs[i * n:(i + 1) * n] for i in range(vk.cs_degree - 1)]
+    pieces = B.quotient(h_ast, ext_polys)                       # the j - 1 pieces (n coefficients each) of h(X)
     h_blinds = [rand() for _ in pieces]
     for piece, b in zip(pieces, h_blinds):
-        transcript.write_point(backend.commit(piece, b))
+        transcript.write_point(B.commit(piece, b))
 
     # ---- evaluations -----------------------------------------------------------------------------------------------------------------
     x = transcript.squeeze_challenge_scalar()
     xn = pow(x, n, p)
     polys_of = {ADVICE: adv_polys, FIXED: pk.fixed_polys, INSTANCE: inst_polys}
+    cache = {}
+
+    def ev(poly, point):                       # every opened value is computed once (transcript and multiopen share them)
+        key = (id(poly), point)
+        if key not in cache:
+            cache[key] = B.eval_polynomial(poly, point)
+        return cache[key]
+
     for kind in (INSTANCE, ADVICE, FIXED):
         for c, r in cs.queries[kind]:
-            transcript.write_scalar(backend.eval_polynomial(polys_of[kind][c], rot(x, r)))
-    h_poly, h_blind = [0] * n, 0
+            transcript.write_scalar(ev(polys_of[kind][c], rot(x, r)))
+    h_poly, h_blind = None, 0
     for piece, b in zip(reversed(pieces), reversed(h_blinds)):
-        h_poly = [(a * xn + c) % p for a, c in zip(h_poly, piece)]
+        h_poly = B.mul_add(h_poly, xn, piece)
         h_blind = (h_blind * xn + b) % p
-    transcript.write_scalar(backend.eval_polynomial(random_poly, x))
+    transcript.write_scalar(ev(random_poly, x))
     for sp in pk.sigma_polys:
-        transcript.write_scalar(backend.eval_polynomial(sp, x))
+        transcript.write_scalar(ev(sp, x))
     x_next, x_inv, x_last = rot(x, 1), rot(x, -1), rot(x, -(bf + 1))
     for i, S in enumerate(perm_sets):
-        transcript.write_scalar(backend.eval_polynomial(S["poly"], x))
-        transcript.write_scalar(backend.eval_polynomial(S["poly"], x_next))
+        transcript.write_scalar(ev(S["poly"], x))
+        transcript.write_scalar(ev(S["poly"], x_next))
         if i + 1 < len(perm_sets):
-            transcript.write_scalar(backend.eval_polynomial(S["poly"], x_last))
+            transcript.write_scalar(ev(S["poly"], x_last))
     for L in lookups:
         for poly, pt_ in ((L["z_poly"], x), (L["z_poly"], x_next), (L["pi_poly"], x), (L["pi_poly"], x_inv), (L["pt_poly"], x)):
-            transcript.write_scalar(backend.eval_polynomial(poly, pt_))
+            transcript.write_scalar(ev(poly, pt_))
 
     # ---- multiopen ---------------------------------------------------------------------------------------------------------------------
     qs: List[_Opening] = []
@@ -568,7 +577,7 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     qs.append(_Opening(h_poly, h_blind, x))
     qs.append(_Opening(random_poly, random_blind, x))
     for q in qs:
-        q.eval = backend.eval_polynomial(q.poly, q.point)
+        q.eval = ev(q.poly, q.point)
 
     x_1 = transcript.squeeze_challenge_scalar()
     x_2 = transcript.squeeze_challenge_scalar()
@@ -578,44 +587,45 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     q_eval_sets = [[0] * len(ps) for ps in point_sets]
     for cd in cmap:
         s, o = cd["set_index"], cd["commitment"]
-        q_polys[s] = list(o.poly) if q_polys[s] is None else [(a * x_1 + c) % p for a, c in zip(q_polys[s], o.poly)]
+        q_polys[s] = B.mul_add(q_polys[s], x_1, o.poly)
         q_blinds[s] = (q_blinds[s] * x_1 + o.blind) % p
         q_eval_sets[s] = [(a * x_1 + e) % p for a, e in zip(q_eval_sets[s], cd["evals"])]
     q_prime = None
     for points, evals, poly in zip(point_sets, q_eval_sets, q_polys):
-        r_poly = lagrange_interpolate(points, evals, p)
-        cur = list(poly)
-        for i, r in enumerate(r_poly):
-            cur[i] = (cur[i] - r) % p
+        cur = B.sub_low(poly, lagrange_interpolate(points, evals, p))
         for pt_ in points:
-            cur = backend.kate_division(cur, pt_)
-        cur = list(cur) + [0] * (n - len(cur))
-        q_prime = cur if q_prime is None else [(a * x_2 + c) % p for a, c in zip(q_prime, cur)]
+            cur = B.kate_division(cur, pt_)
+        q_prime = B.mul_add(q_prime, x_2, cur)
     q_prime_blind = rand()
-    transcript.write_point(backend.commit(q_prime, q_prime_blind))
+    transcript.write_point(B.commit(q_prime, q_prime_blind))
     x_3 = transcript.squeeze_challenge_scalar()
     for qp in q_polys:
-        transcript.write_scalar(backend.eval_polynomial(qp, x_3))
+        transcript.write_scalar(B.eval_polynomial(qp, x_3))
     x_4 = transcript.squeeze_challenge_scalar()
     p_poly, p_blind = q_prime, q_prime_blind
     for qp, qb in zip(q_polys, q_blinds):
-        p_poly = [(a * x_4 + c) % p for a, c in zip(p_poly, qp)]
+        p_poly = B.mul_add(p_poly, x_4, qp)
         p_blind = (p_blind * x_4 + qb) % p
-    backend.ipa_create_proof(rand, transcript, p_poly, p_blind, x_3)
+    B.ipa_create_proof(rand, transcript, p_poly, p_blind, x_3)
     return transcript.finalize()
 
 
-# ---- the product backend: libtrp.so ---------------------------------------------------------------------------------------------------
+# ---- the product backend: libtrp.so, device resident ----------------------------------------------------------------------------------
 class GpuBackend:
-    """Backend of create_proof / keygen over the CUDA library (host-array entry points of include/tr_prover.h)."""
+    """Backend of keygen / create_proof over the CUDA library.  Every polynomial is a torch int64 tensor (n, 4) of Montgomery
+    limbs in HBM and every operation is a trp_dev_* entry point of include/tr_prover.h; the host sees scalars and points only.
+    The quotient is evaluated coset by coset from coefficient form (j - 1 cosets, trp_dev_cosets_to_coeff), so no
+    extended-domain column is ever materialised.  No CPU fallback: constructing it without a GPU raises TrpError."""
 
     def __init__(self, ctx, k: int, cs_degree: int, params=None):
+        import ctypes
         import numpy as np
-        from . import ipa as _ipa, lookup as _lookup, permutation as _perm
+        import torch
+        from . import ipa as _ipa, permutation as _perm
         from .commitment import Params
         from .domain import EvaluationDomain
-        self.np, self._ipa, self._lookup, self._perm = np, _ipa, _lookup, _perm
-        self.ctx, self.k, self.n, self.j = ctx, k, 1 << k, cs_degree
+        self.np, self.torch, self.ct, self._ipa = np, torch, ctypes, _ipa
+        self.ctx, self.lib, self.k, self.n, self.j = ctx, ctx.lib, k, 1 << k, cs_degree
         self.p = _perm._MODULUS[ctx.curve]
         self.q = _perm._MODULUS[1 - ctx.curve]
         self.R, self.Rq = (1 << 256) % self.p, (1 << 256) % self.q
@@ -627,8 +637,10 @@ class GpuBackend:
         self.omega_inv = pow(self.omega, -1, self.p)
         self.delta = pow(5, 1 << 32, self.p)
         self.ipa_params = _ipa.IpaParams(ctx, k, self.params.g_points, self.params.w, self.params.u)
+        self.ev = P.new_evaluator(ctx)
+        self.launch_log = {}
 
-    # -- conversions between canonical ints and Montgomery limb arrays
+    # -- conversions between canonical ints and Montgomery limb arrays (host side: scalars, points, short lists)
     def _limbs(self, vals, mod=None, R=None):
         np = self.np
         mod, R = mod or self.p, R or self.R
@@ -640,8 +652,23 @@ class GpuBackend:
         raw = self.np.ascontiguousarray(arr, dtype=self.np.uint64).reshape(-1, 4).tobytes()
         return [int.from_bytes(raw[i:i + 32], "little") * Rinv % mod for i in range(0, len(raw), 32)]
 
-    def _point(self, jac):
-        """normalised Jacobian (3, 4) -> affine tuple / None"""
+    def _m(self, v):                      # one scalar -> host limbs pointer argument
+        from ._lib import ptr
+        return ptr(self._limbs([v])[0])
+
+    def _dev(self, limbs):
+        return self.torch.from_numpy(self.np.ascontiguousarray(limbs).view(self.np.int64)).cuda()
+
+    def _new(self, rows=None, zero=False):
+        f = self.torch.zeros if zero else self.torch.empty
+        return f((self.n if rows is None else rows, 4), dtype=self.torch.int64, device="cuda")
+
+    def _sync(self):
+        self.torch.cuda.synchronize()     # device-wide: orders torch's stream and the ctx stream
+
+    def _point(self, d_jac):
+        self._sync()
+        jac = d_jac.cpu().numpy().view(self.np.uint64).reshape(3, 4)
         if not jac[2].any():
             return None
         x, y = self._ints(jac[:2], self.q, self.Rqinv)
@@ -650,43 +677,185 @@ class GpuBackend:
     def rotate_omega(self, x, rotation):
         return x * pow(self.omega if rotation >= 0 else self.omega_inv, abs(rotation), self.p) % self.p
 
-    def commit_lagrange(self, values, blind):
-        return self._point(self.params.commit_lagrange(self._limbs(values), self._limbs([blind])[0]))
+    # -- vectors
+    def vec(self, values):
+        if hasattr(values, "data_ptr"):
+            if tuple(values.shape) != (self.n, 4) or values.dtype != self.torch.int64 or not values.is_cuda:
+                raise ValueError("device columns must be (n, 4) int64 cuda tensors of Montgomery limbs")
+            return values
+        if len(values) > self.n:
+            raise ValueError("column longer than the domain")
+        v = self._new(zero=True)
+        if len(values):
+            v[:len(values)] = self._dev(self._limbs(values))
+        return v
 
-    def commit(self, coeffs, blind):
-        return self._point(self.params.commit(self._limbs(coeffs), self._limbs([blind])[0]))
+    def set_rows(self, v, start, values):
+        if len(values):
+            v[start:start + len(values)] = self._dev(self._limbs(values))
+        return v
 
-    def lagrange_to_coeff(self, values):
-        return self._ints(self.dom.lagrange_to_coeff(self._limbs(values)))
+    def random_vec(self, rand):
+        bulk = getattr(rand, "vector", None)           # optional bulk draw: (n, 4) Montgomery limbs
+        return self._dev(bulk(self.n)) if bulk else self._dev(self._limbs([rand() for _ in range(self.n)]))
 
-    def coeff_to_extended(self, coeffs):
-        return self.dom.coeff_to_extended(self._limbs(coeffs))            # opaque: (2^extended_k, 4) Montgomery array
+    def mul_add(self, acc, s, v):
+        if acc is None:
+            return v.clone()
+        out = self._new()
+        d_s = self._dev(self._limbs([s]))
+        self._sync()
+        self.ctx.check(self.lib.trp_dev_field_op(self.ctx.handle, 0, 2 | 16, acc.data_ptr(), d_s.data_ptr(), out.data_ptr(), self.n))
+        self.ctx.check(self.lib.trp_dev_field_op(self.ctx.handle, 0, 0, out.data_ptr(), v.data_ptr(), out.data_ptr(), self.n))
+        self._sync()
+        return out
+
+    def sub_low(self, v, low):
+        out = v.clone()
+        self._sync()
+        cur = self._ints(out[:len(low)].cpu().numpy().view(self.np.uint64))
+        return self.set_rows(out, 0, [(c - r) % self.p for c, r in zip(cur, low)])
+
+    def sigma_vecs(self, m, moved):
+        base = self._new()
+        self._sync()
+        self.ctx.check(self.lib.trp_dev_powers(self.ctx.handle, 0, self._m(self.omega), self.n, base.data_ptr()))
+        out, dl = [], 1
+        for i in range(m):
+            v = self._new()
+            d_s = self._dev(self._limbs([dl]))
+            self._sync()
+            self.ctx.check(self.lib.trp_dev_field_op(self.ctx.handle, 0, 2 | 16, base.data_ptr(), d_s.data_ptr(), v.data_ptr(), self.n))
+            out.append(v)
+            dl = dl * self.delta % self.p
+        self._sync()
+        for (i, j), (i2, j2) in moved.items():
+            self.set_rows(out[i], j, [pow(self.delta, i2, self.p) * pow(self.omega, j2, self.p) % self.p])
+        return out
+
+    # -- commitments and transforms
+    def _commit(self, bases, v, blind):
+        t = self.torch
+        stage = t.cat([v, self._dev(self._limbs([blind]))])
+        out = t.zeros(12, dtype=t.int64, device="cuda")
+        self._sync()
+        self.ctx.check(self.lib.trp_dev_msm_batch(self.ctx.handle, bases.handle, stage.data_ptr(), self.n + 1, 1, out.data_ptr()))
+        return self._point(out)
+
+    def commit_lagrange(self, v, blind): return self._commit(self.params.g_lagrange, v, blind)
+    def commit(self, v, blind): return self._commit(self.params.g, v, blind)
+
+    def lagrange_to_coeff(self, v):
+        c = v.clone()
+        self._sync()
+        self.ctx.check(self.lib.trp_dev_lagrange_to_coeff(self.dom.handle, c.data_ptr(), 1))
+        self._sync()
+        return c
+
+    def coeff_to_extended(self, c):
+        return c                          # lazy: the quotient evaluates cosets straight from coefficient form
+
+    def _run_program(self, ast, columns, out, coset):
+        from ._lib import Q_CONTIGUOUS
+        prog = P.compile_ast(ast, self.p)
+        self.ev.evaluate_device(prog, self.dom, [c.data_ptr() for c in columns], out.data_ptr(), coset=coset | Q_CONTIGUOUS)
 
     def quotient(self, ast, ext_polys):
-        ev = P.new_evaluator(self.ctx)
-        for e in ext_polys:
-            ev.register_poly(e)
-        h_ext = ev.evaluate(ast, self.dom)
-        return self._ints(self.dom.extended_to_coeff(h_ext, divide_by_vanishing_poly=True))
+        from ._lib import Q_CONTIGUOUS
+        t, n, ncos = self.torch, self.n, self.j - 1
+        prog = P.compile_ast(ast, self.p)
+        coeff = t.stack(ext_polys)                                     # (cols, n, 4), contiguous for the batched coset NTT
+        buf = t.empty_like(coeff)
+        vals = t.empty((ncos, n, 4), dtype=t.int64, device="cuda")
+        ptrs = [buf[i].data_ptr() for i in range(len(ext_polys))]
+        self._sync()
+        for cs in range(ncos):
+            self.ctx.check(self.lib.trp_dev_coeff_to_coset(self.dom.handle, coeff.data_ptr(), buf.data_ptr(), len(ext_polys), cs))
+            self.ev.evaluate_device(prog, self.dom, ptrs, vals[cs].data_ptr(), coset=cs | Q_CONTIGUOUS)
+        h = t.empty((ncos, n, 4), dtype=t.int64, device="cuda")
+        self.ctx.check(self.lib.trp_dev_cosets_to_coeff(self.dom.handle, vals.data_ptr(), ncos, h.data_ptr(), 1))
+        self._sync()
+        return [h[i] for i in range(ncos)]
 
-    def eval_polynomial(self, coeffs, x):
-        return self._ints(self._ipa.eval_polynomial(self.ctx, self._limbs(coeffs), self._limbs([x])[0]).reshape(1, 4))[0]
+    def eval_polynomial(self, v, x):
+        out = self._new(1)
+        self._sync()
+        self.ctx.check(self.lib.trp_dev_eval_polynomials(self.ctx.handle, 0, v.data_ptr(), self.n, self.n, 1, self._m(x), out.data_ptr()))
+        self._sync()
+        return self._ints(out.cpu().numpy().view(self.np.uint64))[0]
 
-    def kate_division(self, coeffs, b):
-        return self._ints(self._ipa.kate_division(self.ctx, self._limbs(coeffs), self._limbs([b])[0]))
+    def kate_division(self, v, b):
+        q = self._new(zero=True)
+        self._sync()
+        self.ctx.check(self.lib.trp_dev_kate_division(self.ctx.handle, 0, v.data_ptr(), self.n, self._m(b), q.data_ptr()))
+        self._sync()
+        return q
 
-    def permutation_commit(self, values, sigmas, beta, gamma, chunk_len, blinding_factors, rand, after_chunk):
-        np = self.np
-        v = np.stack([self._limbs(c) for c in values]); s = np.stack([self._limbs(c) for c in sigmas])
-        return self._perm.commit(self.dom, v, s, beta, gamma, chunk_len, blinding_factors, rand, lambda z: after_chunk(self._ints(z)))
+    # -- lookups and permutation
+    def compress(self, exprs, theta, values_of):
+        leaves, cols = {}, []
+
+        def to_ast(e):
+            if isinstance(e, Constant): return P.ConstantTerm(e.value % self.p)
+            if isinstance(e, Query):
+                key = (e.kind, e.column)
+                if key not in leaves:
+                    leaves[key] = len(cols); cols.append(values_of[e.kind][e.column])
+                return P.Poly(leaves[key], e.rotation)
+            if isinstance(e, Negated): return -to_ast(e.a)
+            if isinstance(e, Sum): return to_ast(e.a) + to_ast(e.b)
+            if isinstance(e, Product): return to_ast(e.a) * to_ast(e.b)
+            return to_ast(e.a) * (e.scalar % self.p)
+
+        ast = P.ConstantTerm(0)
+        for e in exprs:
+            ast = ast * theta + to_ast(e)
+        out = self._new()
+        self._sync()
+        self._run_program(ast, cols, out, 0)          # coset 0, contiguous: rows = n, rotations step by one row
+        self._sync()
+        return out
 
     def permute_expression_pair(self, inp, tab, usable_rows):
-        a, s = self._lookup.permute_expression_pair(self.ctx, self._limbs(inp), self._limbs(tab), usable_rows)
-        return self._ints(a), self._ints(s)
+        from .lookup import ConstraintSystemFailure
+        pa, ps = self._new(zero=True), self._new(zero=True)
+        ok = self.ct.c_int(1)
+        self._sync()
+        self.ctx.check(self.lib.trp_dev_permute_expression_pair(self.ctx.handle, inp.data_ptr(), tab.data_ptr(), usable_rows, pa.data_ptr(),
+                                                                ps.data_ptr(), self.ct.byref(ok)))
+        self._sync()
+        if not ok.value:
+            raise ConstraintSystemFailure("lookup input value not present in the table")
+        return pa, ps
 
-    def lookup_product(self, ci, ct, pi, pt, beta, gamma, blinding_factors, rand):
-        return self._ints(self._lookup.commit_product(self.dom, self._limbs(ci), self._limbs(ct), self._limbs(pi), self._limbs(pt),
-                                                      beta, gamma, blinding_factors, rand))
+    def permutation_commit(self, values, sigmas, beta, gamma, chunk_len, blinding_factors, rand, after_chunk):
+        from ._lib import ptr
+        n, p, ct = self.n, self.p, self.ct
+        deltaomega, last, sets = 1, None, []
+        for lo in range(0, len(values), chunk_len):
+            cols = list(range(lo, min(lo + chunk_len, len(values))))
+            dbeta = self._limbs([deltaomega * pow(self.delta, c - lo, p) % p * beta % p for c in cols])
+            deltaomega = deltaomega * pow(self.delta, len(cols), p) % p
+            vptr = (ct.c_void_p * len(cols))(*[values[c].data_ptr() for c in cols])
+            sptr = (ct.c_void_p * len(cols))(*[sigmas[c].data_ptr() for c in cols])
+            z = self._new()
+            self._sync()
+            self.ctx.check(self.lib.trp_dev_permutation_product(self.dom.handle, vptr, sptr, len(cols), self._m(beta), self._m(gamma), ptr(dbeta),
+                                                                None if last is None else last[n - (blinding_factors + 1)].data_ptr(), z.data_ptr()))
+            self._sync()
+            self.set_rows(z, n - blinding_factors, [rand() for _ in range(blinding_factors)])
+            last = z
+            sets.append(z)
+            after_chunk(z)
+        return sets
+
+    def lookup_product(self, ci, ct_, pi, pt, beta, gamma, blinding_factors, rand):
+        z = self._new()
+        self._sync()
+        self.ctx.check(self.lib.trp_dev_lookup_product(self.dom.handle, ci.data_ptr(), ct_.data_ptr(), pi.data_ptr(), pt.data_ptr(), self._m(beta),
+                                                       self._m(gamma), z.data_ptr(), self.n - blinding_factors))
+        self._sync()
+        return self.set_rows(z, self.n - blinding_factors, [rand() for _ in range(blinding_factors)])
 
     def ipa_create_proof(self, rand, transcript, p_poly, p_blind, x_3):
         outer = self
@@ -698,4 +867,5 @@ class GpuBackend:
             def write_scalar(self, s): transcript.write_scalar(s)
             def squeeze_challenge_scalar(self): return transcript.squeeze_challenge_scalar()
 
-        self._ipa.create_proof(self.ipa_params, rand, _Adapter(), self._limbs(p_poly), p_blind, x_3)
+        self._sync()
+        self._ipa.create_proof(self.ipa_params, rand, _Adapter(), p_poly, p_blind, x_3, rand_vector=getattr(rand, "vector", None))
