@@ -192,8 +192,12 @@ def verify_proof(curve: pm.Curve, params: dict, vk, instances, proof: bytes) -> 
     try:
         _verify(curve, params, vk, instances, proof)
         return True
-    except VerifyError:
+    except VerifyError as e:
+        verify_proof.last_error = str(e)
         return False
+
+
+verify_proof.last_error = None
 
 
 def _verify(C, params, vk, instances, proof):

@@ -114,8 +114,11 @@ def create_proof(params: IpaParams, rand, transcript, p_poly, p_blind, x_3, rand
     z = transcript.squeeze_challenge_scalar()
     # P' = P - [v] G_0 + [xi] S
     d_pp = torch.empty_like(d_s)
-    ctx.check(lib.trp_dev_field_op(ctx.handle, 0, 2 | 16, d_s.data_ptr(), dev(mont(xi)).data_ptr(), d_pp.data_ptr(), n))
+    d_xi = dev(mont(xi))          # must outlive the kernel that reads it: the library's stream is invisible to torch's allocator
+    torch.cuda.synchronize()
+    ctx.check(lib.trp_dev_field_op(ctx.handle, 0, 2 | 16, d_s.data_ptr(), d_xi.data_ptr(), d_pp.data_ptr(), n))
     ctx.check(lib.trp_dev_field_op(ctx.handle, 0, 0, d_pp.data_ptr(), d_p.data_ptr(), d_pp.data_ptr(), n))
+    ctx.sync()
     v = evaluate(d_pp, x_3)
     ctx.sync()
     pp0 = unmont(d_pp.reshape(n, 4)[0].cpu().numpy().view(np.uint64))

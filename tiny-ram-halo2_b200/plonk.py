@@ -381,7 +381,39 @@ class _Opening:
     eval: int = 0
 
 
-def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], int], transcript: Blake2bWrite) -> bytes:
+def eval_ast_at_point(B, ast, polys, x):
+    """value at X = x of an Ast whose leaves are coefficient-form polynomials (debug aid: the vanishing identity at one point)"""
+    p = B.p
+    memo = {}
+
+    def go(a):
+        if isinstance(a, P.Poly):
+            key = (a.index, a.rotation)
+            if key not in memo:
+                memo[key] = B.eval_polynomial(polys[a.index], B.rotate_omega(x, a.rotation))
+            return memo[key]
+        if isinstance(a, P.Add): return (go(a.a) + go(a.b)) % p
+        if isinstance(a, P.Mul): return go(a.a) * go(a.b) % p
+        if isinstance(a, P.Scale): return go(a.a) * a.scalar % p
+        if isinstance(a, P.LinearTerm): return a.scalar * x % p
+        if isinstance(a, P.ConstantTerm): return a.scalar % p
+        if isinstance(a, P.DistributePowers):
+            base, acc = go(a.base), 0
+            for t in a.terms:
+                acc = (acc * base + go(t)) % p
+            return acc
+        raise TypeError(type(a))
+
+    import sys
+    old = sys.getrecursionlimit(); sys.setrecursionlimit(max(old, 100000))
+    try:
+        return go(ast)
+    finally:
+        sys.setrecursionlimit(old)
+
+
+def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], int], transcript: Blake2bWrite, debug: bool = False,
+                 timings: Optional[dict] = None) -> bytes:
     """plonk::create_proof for ONE circuit instance.  instances: one column per instance column, advice: one per advice column
     -- lists of at most usable_rows ints, or backend vectors of n values whose blinding rows are overwritten here.  rand()
     draws one uniformly random scalar (the caller's RNG: every draw happens in halo2's order).  Polynomials are opaque backend
@@ -396,6 +428,14 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     if len(instances) != cs.num_instance or len(advice) != cs.num_advice:
         raise ValueError("InvalidInstances / wrong number of advice columns")
     transcript.common_scalar(vk.transcript_repr)
+    import time as _time
+    _t = [_time.perf_counter()]
+
+    def tick(name):                            # wall-clock per phase (the backend's work is synchronous at this level)
+        if timings is not None:
+            now = _time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + now - _t[0]
+            _t[0] = now
 
     def column(col, what):
         if isinstance(col, (list, tuple)) and len(col) > usable:
@@ -408,6 +448,7 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
         transcript.common_point(B.commit_lagrange(v, 1))
     inst_polys = [B.lagrange_to_coeff(v) for v in inst_values]
     inst_cosets = [B.coeff_to_extended(c) for c in inst_polys]
+    tick("instance")
 
     # ---- advice columns --------------------------------------------------------------------------------------------------------
     adv_values = [column(c, "advice") for c in advice]
@@ -419,6 +460,7 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     adv_polys = [B.lagrange_to_coeff(v) for v in adv_values]
     adv_cosets = [B.coeff_to_extended(c) for c in adv_polys]
     values_of = {ADVICE: adv_values, FIXED: pk.fixed_values, INSTANCE: inst_values}
+    tick("advice")
 
     # ---- lookups: commit_permuted -------------------------------------------------------------------------------------------------
     theta = transcript.squeeze_challenge_scalar()
@@ -434,6 +476,7 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
             L[name + "_blind"] = rand()
             transcript.write_point(B.commit_lagrange(L[name], L[name + "_blind"]))
         lookups.append(L)
+    tick("lookups_permuted")
 
     # ---- permutation and lookup grand products ----------------------------------------------------------------------------------------
     beta = transcript.squeeze_challenge_scalar()
@@ -456,6 +499,7 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
         L["z_blind"] = rand()
         transcript.write_point(B.commit_lagrange(L["z"], L["z_blind"]))
         L["z_poly"] = B.lagrange_to_coeff(L["z"])
+    tick("grand_products")
 
     # ---- vanishing argument: random polynomial ------------------------------------------------------------------------------------------
     random_poly = B.random_vec(rand)
@@ -517,9 +561,19 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     for e in exprs:
         h_ast = h_ast * y + e
     pieces = B.quotient(h_ast, ext_polys)                       # the j - 1 pieces (n coefficients each) of h(X)
+    if debug:        # h(X) (X^n - 1) must equal the folded constraint polynomial: checked at a point outside the domain
+        xd = 0x1234567890abcdef1234567890abcdef % p
+        lhs = eval_ast_at_point(B, h_ast, ext_polys, xd)
+        hx, xdn = 0, pow(xd, n, p)
+        for piece in reversed(pieces):
+            hx = (hx * xdn + B.eval_polynomial(piece, xd)) % p
+        if lhs != hx * (xdn - 1) % p:
+            raise AssertionError("the quotient does not satisfy h(X) (X^n - 1) = sum_i y^i expr_i(X): unsatisfied circuit or a "
+                                 "fault in the quotient phase")
     h_blinds = [rand() for _ in pieces]
     for piece, b in zip(pieces, h_blinds):
         transcript.write_point(B.commit(piece, b))
+    tick("quotient")
 
     # ---- evaluations -----------------------------------------------------------------------------------------------------------------
     x = transcript.squeeze_challenge_scalar()
@@ -552,6 +606,7 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     for L in lookups:
         for poly, pt_ in ((L["z_poly"], x), (L["z_poly"], x_next), (L["pi_poly"], x), (L["pi_poly"], x_inv), (L["pt_poly"], x)):
             transcript.write_scalar(ev(poly, pt_))
+    tick("evaluations")
 
     # ---- multiopen ---------------------------------------------------------------------------------------------------------------------
     qs: List[_Opening] = []
@@ -606,7 +661,9 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     for qp, qb in zip(q_polys, q_blinds):
         p_poly = B.mul_add(p_poly, x_4, qp)
         p_blind = (p_blind * x_4 + qb) % p
+    tick("multiopen")
     B.ipa_create_proof(rand, transcript, p_poly, p_blind, x_3)
+    tick("ipa")
     return transcript.finalize()
 
 
@@ -726,11 +783,24 @@ class GpuBackend:
             d_s = self._dev(self._limbs([dl]))
             self._sync()
             self.ctx.check(self.lib.trp_dev_field_op(self.ctx.handle, 0, 2 | 16, base.data_ptr(), d_s.data_ptr(), v.data_ptr(), self.n))
+            self._sync()                               # d_s is released below: the kernel reading it must have finished
             out.append(v)
             dl = dl * self.delta % self.p
         self._sync()
-        for (i, j), (i2, j2) in moved.items():
-            self.set_rows(out[i], j, [pow(self.delta, i2, self.p) * pow(self.omega, j2, self.p) % self.p])
+        if moved:                                      # patch the cells the copy constraints move: one scatter per column
+            top = max(j2 for _, (_, j2) in moved.items())
+            om = [1] * (top + 1)
+            for j in range(1, top + 1):
+                om[j] = om[j - 1] * self.omega % self.p
+            dls = [pow(self.delta, i, self.p) for i in range(m)]
+            per_col = {}
+            for (i, j), (i2, j2) in moved.items():
+                per_col.setdefault(i, ([], []))
+                per_col[i][0].append(j); per_col[i][1].append(dls[i2] * om[j2] % self.p)
+            for i, (rws, vals) in per_col.items():
+                idx = self.torch.tensor(rws, dtype=self.torch.int64, device="cuda")
+                out[i][idx] = self._dev(self._limbs(vals))
+            self._sync()
         return out
 
     # -- commitments and transforms
