@@ -81,6 +81,9 @@ class PythonBackend:
     def commit(self, coeffs, blind):
         return self.C.best_multiexp(list(coeffs) + [blind], self.params["g"] + [self.params["w"]])
 
+    def commit_lagrange_many(self, vecs, blinds): return [self.commit_lagrange(v, b) for v, b in zip(vecs, blinds)]
+    def commit_many(self, vecs, blinds): return [self.commit(v, b) for v, b in zip(vecs, blinds)]
+
     def lagrange_to_coeff(self, values): return self.dom.lagrange_to_coeff(list(values))
     def coeff_to_extended(self, coeffs): return self.dom.coeff_to_extended(list(coeffs))
 

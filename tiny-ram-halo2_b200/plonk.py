@@ -296,9 +296,9 @@ def keygen(backend, cs: ConstraintSystem, fixed_values, copies=()) -> ProvingKey
     if len(fixed_values) != cs.num_fixed:
         raise ValueError("one column per fixed column")
     fixed_values = [backend.vec(v) for v in fixed_values]
-    fixed_commitments = [backend.commit_lagrange(v, 1) for v in fixed_values]          # Blind::default() = 1
+    fixed_commitments = backend.commit_lagrange_many(fixed_values, [1] * len(fixed_values))          # Blind::default() = 1
     sigma_values = backend.sigma_vecs(len(cs.permutation), permutation_mapping(cs, n, copies))
-    permutation_commitments = [backend.commit_lagrange(v, 1) for v in sigma_values]
+    permutation_commitments = backend.commit_lagrange_many(sigma_values, [1] * len(sigma_values))
     pt = lambda c: "Identity" if c is None else f"({c[0]:#066x}, {c[1]:#066x})"
     text = (f"PinnedVerificationKey {{ base_modulus: {backend.q:#066x}, scalar_modulus: {p:#066x}, domain: PinnedEvaluationDomain {{ k: {backend.k}, "
             f"extended_k: {backend.extended_k}, omega: {backend.omega:#066x} }}, cs: {cs.pinned_text()}, "
@@ -308,12 +308,13 @@ def keygen(backend, cs: ConstraintSystem, fixed_values, copies=()) -> ProvingKey
     fixed_polys = [backend.lagrange_to_coeff(v) for v in fixed_values]
     sigma_polys = [backend.lagrange_to_coeff(v) for v in sigma_values]
     bf = cs.blinding_factors()
-    ext = lambda lag: backend.coeff_to_extended(backend.lagrange_to_coeff(lag))
+    static = getattr(backend, "coeff_to_extended_static", backend.coeff_to_extended)   # key material: cosets may be cached
+    ext = lambda lag: static(backend.lagrange_to_coeff(lag))
     l0 = backend.vec([1])
     l_blind = backend.set_rows(backend.vec([]), n - bf, [1] * bf)
     l_last = backend.set_rows(backend.vec([]), n - bf - 1, [1])
-    return ProvingKey(vk, fixed_values, fixed_polys, [backend.coeff_to_extended(c) for c in fixed_polys], sigma_values, sigma_polys,
-                      [backend.coeff_to_extended(c) for c in sigma_polys], ext(l0), ext(l_blind), ext(l_last))
+    return ProvingKey(vk, fixed_values, fixed_polys, [static(c) for c in fixed_polys], sigma_values, sigma_polys,
+                      [static(c) for c in sigma_polys], ext(l0), ext(l_blind), ext(l_last))
 
 
 # ---- poly/multiopen: construct_intermediate_sets -----------------------------------------------------------------------------------
@@ -444,8 +445,8 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
 
     # ---- instance columns: commit (not written, only absorbed) -------------------------------------------------------------
     inst_values = [column(c, "InstanceTooLarge: instance") for c in instances]
-    for v in inst_values:
-        transcript.common_point(B.commit_lagrange(v, 1))
+    for cm in B.commit_lagrange_many(inst_values, [1] * len(inst_values)):
+        transcript.common_point(cm)
     inst_polys = [B.lagrange_to_coeff(v) for v in inst_values]
     inst_cosets = [B.coeff_to_extended(c) for c in inst_polys]
     tick("instance")
@@ -455,8 +456,8 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     for v in adv_values:
         B.set_rows(v, usable, [rand() for _ in range(usable, n)])
     adv_blinds = [rand() for _ in adv_values]
-    for v, b in zip(adv_values, adv_blinds):
-        transcript.write_point(B.commit_lagrange(v, b))
+    for cm in B.commit_lagrange_many(adv_values, adv_blinds):
+        transcript.write_point(cm)
     adv_polys = [B.lagrange_to_coeff(v) for v in adv_values]
     adv_cosets = [B.coeff_to_extended(c) for c in adv_polys]
     values_of = {ADVICE: adv_values, FIXED: pk.fixed_values, INSTANCE: inst_values}
@@ -474,8 +475,10 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
         for name in ("pi", "pt"):
             L[name + "_poly"] = B.lagrange_to_coeff(L[name])
             L[name + "_blind"] = rand()
-            transcript.write_point(B.commit_lagrange(L[name], L[name + "_blind"]))
         lookups.append(L)
+    # the commitments do not feed the RNG, so they are computed as one batch and written in halo2's order
+    for cm in B.commit_lagrange_many([L[nm] for L in lookups for nm in ("pi", "pt")], [L[nm + "_blind"] for L in lookups for nm in ("pi", "pt")]):
+        transcript.write_point(cm)
     tick("lookups_permuted")
 
     # ---- permutation and lookup grand products ----------------------------------------------------------------------------------------
@@ -484,20 +487,22 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     chunk_len = vk.cs_degree - 2
     perm_sets = []
 
-    def after_chunk(z):
-        blind = rand()
-        transcript.write_point(B.commit_lagrange(z, blind))
-        perm_sets.append({"z": z, "blind": blind})
+    def after_chunk(z):                        # halo2 draws the chunk's blind right after its blinding rows
+        perm_sets.append({"z": z, "blind": rand()})
 
     if cs.permutation:
         B.permutation_commit([values_of[kk][c] for kk, c in cs.permutation], pk.sigma_values, beta, gamma, chunk_len, bf, rand, after_chunk)
+    for cm in B.commit_lagrange_many([S["z"] for S in perm_sets], [S["blind"] for S in perm_sets]):
+        transcript.write_point(cm)
     for S in perm_sets:
         S["poly"] = B.lagrange_to_coeff(S["z"])
         S["coset"] = B.coeff_to_extended(S["poly"])
     for L in lookups:
         L["z"] = B.lookup_product(L["ci"], L["ct"], L["pi"], L["pt"], beta, gamma, bf, rand)
         L["z_blind"] = rand()
-        transcript.write_point(B.commit_lagrange(L["z"], L["z_blind"]))
+    for cm in B.commit_lagrange_many([L["z"] for L in lookups], [L["z_blind"] for L in lookups]):
+        transcript.write_point(cm)
+    for L in lookups:
         L["z_poly"] = B.lagrange_to_coeff(L["z"])
     tick("grand_products")
 
@@ -571,8 +576,8 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
             raise AssertionError("the quotient does not satisfy h(X) (X^n - 1) = sum_i y^i expr_i(X): unsatisfied circuit or a "
                                  "fault in the quotient phase")
     h_blinds = [rand() for _ in pieces]
-    for piece, b in zip(pieces, h_blinds):
-        transcript.write_point(B.commit(piece, b))
+    for cm in B.commit_many(pieces, h_blinds):
+        transcript.write_point(cm)
     tick("quotient")
 
     # ---- evaluations -----------------------------------------------------------------------------------------------------------------
@@ -695,7 +700,8 @@ class GpuBackend:
         self.delta = pow(5, 1 << 32, self.p)
         self.ipa_params = _ipa.IpaParams(ctx, k, self.params.g_points, self.params.w, self.params.u)
         self.ev = P.new_evaluator(ctx)
-        self.launch_log = {}
+        self._static, self._static_keep = {}, []
+        self.static_budget_bytes = 48 << 30
 
     # -- conversions between canonical ints and Montgomery limb arrays (host side: scalars, points, short lists)
     def _limbs(self, vals, mod=None, R=None):
@@ -815,6 +821,25 @@ class GpuBackend:
     def commit_lagrange(self, v, blind): return self._commit(self.params.g_lagrange, v, blind)
     def commit(self, v, blind): return self._commit(self.params.g, v, blind)
 
+    def _commit_many(self, bases, vecs, blinds, batch=32):
+        """several commitments over the same bases as batched MSMs (trp_dev_msm_batch processes the columns concurrently)"""
+        t, n, out = self.torch, self.n, []
+        for b0 in range(0, len(vecs), batch):
+            vs, bs = vecs[b0:b0 + batch], blinds[b0:b0 + batch]
+            stage = t.empty((len(vs), n + 1, 4), dtype=t.int64, device="cuda")
+            for i, v in enumerate(vs):
+                stage[i, :n] = v
+            stage[:, n] = self._dev(self._limbs(bs))
+            res = t.zeros((len(vs), 12), dtype=t.int64, device="cuda")
+            self._sync()
+            self.ctx.check(self.lib.trp_dev_msm_batch(self.ctx.handle, bases.handle, stage.data_ptr(), n + 1, len(vs), res.data_ptr()))
+            self._sync()
+            out.extend(self._point(res[i]) for i in range(len(vs)))
+        return out
+
+    def commit_lagrange_many(self, vecs, blinds): return self._commit_many(self.params.g_lagrange, vecs, blinds)
+    def commit_many(self, vecs, blinds): return self._commit_many(self.params.g, vecs, blinds)
+
     def lagrange_to_coeff(self, v):
         c = v.clone()
         self._sync()
@@ -825,6 +850,22 @@ class GpuBackend:
     def coeff_to_extended(self, c):
         return c                          # lazy: the quotient evaluates cosets straight from coefficient form
 
+    def coeff_to_extended_static(self, c):
+        """key material (fixed / sigma / Lagrange-selector polynomials): its evaluations on the j - 1 cosets are computed once
+        and kept in HBM ((j - 1) * 32 B per row), so a proof only transforms its own columns"""
+        ncos = self.j - 1
+        held = sum(v.numel() for v in self._static.values()) * 8
+        if held + ncos * self.n * 32 > self.static_budget_bytes:
+            return c
+        vals = self.torch.empty((ncos, self.n, 4), dtype=self.torch.int64, device="cuda")
+        self._sync()
+        for cs in range(ncos):
+            self.ctx.check(self.lib.trp_dev_coeff_to_coset(self.dom.handle, c.data_ptr(), vals[cs].data_ptr(), 1, cs))
+        self._sync()
+        self._static[id(c)] = vals
+        self._static_keep.append(c)       # id() stays unique while the tensor is alive
+        return c
+
     def _run_program(self, ast, columns, out, coset):
         from ._lib import Q_CONTIGUOUS
         prog = P.compile_ast(ast, self.p)
@@ -834,13 +875,15 @@ class GpuBackend:
         from ._lib import Q_CONTIGUOUS
         t, n, ncos = self.torch, self.n, self.j - 1
         prog = P.compile_ast(ast, self.p)
-        coeff = t.stack(ext_polys)                                     # (cols, n, 4), contiguous for the batched coset NTT
+        dyn = [i for i, c in enumerate(ext_polys) if id(c) not in self._static]
+        coeff = t.stack([ext_polys[i] for i in dyn])                  # (cols, n, 4), contiguous for the batched coset NTT
         buf = t.empty_like(coeff)
         vals = t.empty((ncos, n, 4), dtype=t.int64, device="cuda")
-        ptrs = [buf[i].data_ptr() for i in range(len(ext_polys))]
+        slot = {i: s_ for s_, i in enumerate(dyn)}
         self._sync()
         for cs in range(ncos):
-            self.ctx.check(self.lib.trp_dev_coeff_to_coset(self.dom.handle, coeff.data_ptr(), buf.data_ptr(), len(ext_polys), cs))
+            self.ctx.check(self.lib.trp_dev_coeff_to_coset(self.dom.handle, coeff.data_ptr(), buf.data_ptr(), len(dyn), cs))
+            ptrs = [buf[slot[i]].data_ptr() if i in slot else self._static[id(c)][cs].data_ptr() for i, c in enumerate(ext_polys)]
             self.ev.evaluate_device(prog, self.dom, ptrs, vals[cs].data_ptr(), coset=cs | Q_CONTIGUOUS)
         h = t.empty((ncos, n, 4), dtype=t.int64, device="cuda")
         self.ctx.check(self.lib.trp_dev_cosets_to_coeff(self.dom.handle, vals.data_ptr(), ncos, h.data_ptr(), 1))
