@@ -378,6 +378,50 @@ def measure_extras(pkg, ctx, stream, peaks, peak_src, int_peak_tmacs):
         model.close()
     except Exception as e:   # e.g. not enough free HBM next to other tenants; the headline line must still print
         out["create_proof_model"] = {"error": str(e)}
+    # ---- a REAL create_proof at k = 20: satisfiable TinyRAM-shaped circuit, device-resident prover, Blake2b transcript ------------
+    try:
+        import gc
+        import random as _random
+        model = None
+        gc.collect(); torch.cuda.empty_cache()
+        from tiny_ram_halo2_b200 import plonk as PL, tinyram_circuit
+        t0 = time.perf_counter()
+        be = PL.GpuBackend(ctx, K_LOG, 6)
+        torch.cuda.synchronize(); t_params = time.perf_counter() - t0
+        cs, fixed, copies, adv, inst = tinyram_circuit.build(PL, be, seed=40)
+        t0 = time.perf_counter()
+        pk = PL.keygen(be, cs, fixed, copies)
+        torch.cuda.synchronize(); t_keygen = time.perf_counter() - t0
+
+        class _Rng:
+            def __init__(self, seed):
+                self.r, self.g = _random.Random(seed), np.random.Generator(np.random.PCG64(seed))
+            def __call__(self):
+                return self.r.randrange(be.p)
+            def vector(self, n):
+                a = self.g.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+                a[:, 3] &= np.uint64((1 << 62) - 1)
+                return a
+
+        runs = []
+        for rep in range(3):
+            advice = [a.clone() for a in adv]                      # create_proof overwrites the blinding rows in place
+            phases = {}
+            l0 = ctx.launches
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            proof = PL.create_proof(be, pk, inst, advice, _Rng(rep), PL.Blake2bWrite(be.q, be.p), timings=phases)
+            torch.cuda.synchronize()
+            runs.append((time.perf_counter() - t0, phases, ctx.launches - l0, len(proof)))
+        best = min(runs, key=lambda r: r[0])
+        out["create_proof_real"] = {"k": K_LOG, "seconds": best[0], "first_run_seconds": runs[0][0], "phases_s": {k: round(v, 3) for k, v in best[1].items()},
+                                    "kernel_launches": best[2], "proof_bytes": best[3], "params_new_s": round(t_params, 3), "keygen_s": round(t_keygen, 3),
+                                    "circuit": {"advice": cs.num_advice, "instance": cs.num_instance, "fixed": cs.num_fixed, "gates": len(cs.gates),
+                                                "lookups": len(cs.lookups), "equality_columns": len(cs.permutation), "degree": cs.degree()},
+                                    "scope": "plonk.create_proof over plonk.GpuBackend: a satisfiable circuit of the TinyRamCircuit's shape (tinyram_circuit.py), "
+                                             "device-generated witness, Blake2b transcript, serialized proof; the same run is accepted by the oracle's independent "
+                                             "verifier in tests/gpu_tinyram_proof.py (profiles/tinyram_proof_r01.md); wall clock, host logic included"}
+    except Exception as e:
+        out["create_proof_real"] = {"error": str(e)}
     return out
 
 
