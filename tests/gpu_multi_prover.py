@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--streamed", action="store_true", help="blockwise exchange: no rank holds all coefficient columns (default from k = 21)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -32,7 +33,7 @@ def main():
     ctx = pkg.Context(local, pkg.VESTA)
     st = torch.cuda.Stream()
     ctx.set_stream(st.cuda_stream)
-    model = ShardedProverModel(ctx, a.k, st, d, scale=a.scale)
+    model = ShardedProverModel(ctx, a.k, st, d, scale=a.scale, streamed=True if a.streamed else None)
     model.prove_once()
     best = None
     for _ in range(a.reps):
@@ -46,7 +47,7 @@ def main():
         t["total_ms_max_over_ranks"] = float(tt.item())
         if best is None or t["total_ms_max_over_ranks"] < best["total_ms_max_over_ranks"]:
             best = t
-    res = {"k": a.k, "scale": a.scale, "n_gpus": world, "per_proof_columns": model.n_proof, "cosets": model.cosets,
+    res = {"k": a.k, "scale": a.scale, "n_gpus": world, "streamed": model.streamed and world > 1, "torch_peak_gib": round(torch.cuda.max_memory_allocated() / 2**30, 1), "per_proof_columns": model.n_proof, "cosets": model.cosets,
            "phases_ms_rank0": {k: round(v, 2) for k, v in best.items()}}
     if a.check:
         ok = None

@@ -124,6 +124,12 @@ def _coset_worker(rank, world, port, n_cols, q):
         want = dom.extended_to_coeff(pm.evaluate_ast(dom, ast, [dom.coeff_to_extended(c) for c in coeff]))
         # the gather must also restore global column order
         order_ok = to_i(PL.all_gather_columns(to_t([coeff[c] for c in mine]), n_cols, dist)) == coeff
+        # the streamed (blockwise) exchange delivers the same columns in the same global order
+        seen = []
+        for g0, blk in PL.all_gather_column_blocks(to_t([coeff[c] for c in mine]), n_cols, 2, dist):
+            order_ok = order_ok and g0 == len(seen)
+            seen += to_i(blk)
+        order_ok = order_ok and seen == coeff
         q.put((rank, got == want, order_ok))
     finally:
         dist.destroy_process_group()

@@ -119,3 +119,25 @@ def quotient_cosets_sharded(coeff_local, n_cols: int, n_cosets: int, eval_coset:
     else:
         local = torch.zeros((0,) + tuple(coeff_local.shape[1:]), dtype=coeff_local.dtype, device=coeff_local.device)
     return combine(all_gather_columns(local, n_cosets, dist))
+
+
+def all_gather_column_blocks(local, n_cols: int, block_slots: int, dist):
+    """Streamed form of all_gather_columns: yields (first global column, block) where block holds the global columns
+    [g0, g0 + len(block)) in order, block_slots slots of every rank at a time (one all_gather per block; every rank must
+    consume the generator in lockstep).  A rank never holds more than one block of foreign columns."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per_rank = (n_cols + world - 1) // world
+    mine = len(shard_columns(n_cols, world, rank))
+    if local.shape[0] < mine:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} columns, expected {mine}")
+    for s0 in range(0, per_rank, block_slots):
+        s1 = min(s0 + block_slots, per_rank)
+        blk = torch.zeros((s1 - s0,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        hi = min(s1, mine)
+        if hi > s0:
+            blk[:hi - s0].copy_(local[s0:hi])
+        gathered = torch.empty((world,) + tuple(blk.shape), dtype=local.dtype, device=local.device)
+        dist.all_gather(list(gathered.unbind(0)), blk)
+        g0, g1 = s0 * world, min(s1 * world, n_cols)
+        yield g0, gathered.transpose(0, 1).reshape(((s1 - s0) * world,) + tuple(local.shape[1:]))[:g1 - g0].contiguous()

@@ -26,13 +26,19 @@ from ._lib import Q_CONTIGUOUS
 
 
 class ShardedProverModel:
-    def __init__(self, ctx, k: int, stream, dist=None, seed: int = 40, scale: float = 1.0, msm_batch: int = 32):
+    def __init__(self, ctx, k: int, stream, dist=None, seed: int = 40, scale: float = 1.0, msm_batch: int = 32, streamed: bool = None,
+                 block_slots: int = 8):
         import torch
         from .domain import EvaluationDomain
         self.torch, self.ctx, self.k, self.n, self.stream, self.dist = torch, ctx, k, 1 << k, stream, dist
         self.world = dist.get_world_size() if dist is not None else 1
         self.rank = dist.get_rank() if dist is not None else 0
         self.msm_batch = msm_batch
+        # streamed: the coefficient columns are all_gathered in blocks and transformed straight into the owner's coset buffer,
+        # so no rank ever holds all n_cols coefficient columns (what lets k = 22 fit: 62 GiB of coefficients there); costs one
+        # pass over the exchange per coset a rank owns.  Default: on from k = 21.
+        self.streamed = (k >= 21) if streamed is None else streamed
+        self.block_slots = block_slots
         self.dom = EvaluationDomain(ctx, 6, k)
         self.cosets = self.dom.j - 1
         self.shape = tinyram_shape.build(seed, scale=scale)
@@ -91,6 +97,28 @@ class ShardedProverModel:
         self.ev.evaluate_device(self.prog, self.dom, self.col_ptrs, out.data_ptr(), coset=cs | Q_CONTIGUOUS)
         return out
 
+    def _quotient_streamed(self):
+        """per round r every rank evaluates coset r * world + rank (if it exists): the columns arrive as blocks of
+        `block_slots` slots from every rank (one all_gather per block, all ranks take part in every collective) and each block
+        is transformed into the coset buffer at once, so a rank holds its own coefficients, one block and the coset buffer"""
+        torch, ctx, lib, dist = self.torch, self.ctx, self.ctx.lib, self.dist
+        world, rank, n = self.world, self.rank, self.n
+        m = len(self.mine)
+        out = []
+        for rnd in range((self.cosets + world - 1) // world):
+            cs = rnd * world + rank
+            active = cs < self.cosets
+            for g0, cols in PL.all_gather_column_blocks(self.coeff_local[:m], self.n_proof, self.block_slots, dist):
+                if active:
+                    ctx.check(lib.trp_dev_coeff_to_coset(self.dom.handle, cols.data_ptr(), self.coset_buf[g0].data_ptr(), cols.shape[0], cs))
+                    ctx.sync()
+            if active:
+                res = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+                self.ev.evaluate_device(self.prog, self.dom, self.col_ptrs, res.data_ptr(), coset=cs | Q_CONTIGUOUS)
+                ctx.sync()
+                out.append(res)
+        return out
+
     def _combine(self, vals):
         ctx, lib, torch = self.ctx, self.ctx.lib, self.torch
         vals = vals.contiguous().clone()                     # consumed by the call
@@ -123,10 +151,15 @@ class ShardedProverModel:
                 ctx.check(lib.trp_dev_lagrange_to_coeff(self.dom.handle, self.coeff_local.data_ptr(), m))
             mark("lagrange_to_coeff")
             commitments = PL.all_gather_columns(self.commit_local[:m], self.n_proof, dist)
-            all_coeff = PL.all_gather_columns(self.coeff_local[:m], self.n_proof, dist).contiguous()
-            mark("all_gather_columns")
-            local = [self._eval_coset(all_coeff, cs) for cs in self.my_cosets]
-            mark("quotient_cosets")
+            if self.streamed and self.world > 1:
+                local = self._quotient_streamed()
+                mark("quotient_cosets_streamed")
+            else:
+                all_coeff = PL.all_gather_columns(self.coeff_local[:m], self.n_proof, dist).contiguous()
+                mark("all_gather_columns")
+                local = [self._eval_coset(all_coeff, cs) for cs in self.my_cosets]
+                del all_coeff
+                mark("quotient_cosets")
             stacked = torch.stack(local) if local else torch.zeros((0, n, 4), dtype=torch.int64, device="cuda")
             h = self._combine(PL.all_gather_columns(stacked, self.cosets, dist))
             mark("gather_and_cosets_to_coeff")
