@@ -102,3 +102,24 @@ def test_keygen_permutation_cycles(PL):
     col_of = {kc: i for i, kc in enumerate(cs.permutation)}
     touched = {(col_of[(k_, c)], r) for pair in copies for (k_, c, r) in pair}
     assert moved == touched
+
+
+def test_permutation_mapping_is_sparse_and_cyclic(PL):
+    """chains and repeated copies merge into one cycle; untouched cells never enter the mapping (keygen is O(copies))"""
+    cs = PL.ConstraintSystem()
+    a, b = cs.advice_column(), cs.advice_column()
+    cs.enable_equality(PL.ADVICE, a); cs.enable_equality(PL.ADVICE, b)
+    A = PL.ADVICE
+    copies = [((A, a, 0), (A, b, 5)), ((A, b, 5), (A, a, 9)), ((A, a, 9), (A, a, 0)), ((A, b, 1), (A, b, 2)), ((A, a, 3), (A, a, 3))]
+    m = PL.permutation_mapping(cs, 1 << 20, copies)
+    assert set(m) == {(0, 0), (1, 5), (0, 9), (1, 1), (1, 2)}
+    # following the mapping from any cell of the 3-cycle visits all three cells and returns
+    cell, seen = (0, 0), []
+    for _ in range(3):
+        seen.append(cell); cell = m[cell]
+    assert cell == (0, 0) and set(seen) == {(0, 0), (1, 5), (0, 9)}
+    assert m[(1, 1)] == (1, 2) and m[(1, 2)] == (1, 1)
+    with pytest.raises(ValueError):
+        PL.permutation_mapping(cs, 16, [((A, a, 0), (PL.FIXED, 0, 0))])
+    with pytest.raises(ValueError):
+        PL.permutation_mapping(cs, 16, [((A, a, 0), (A, b, 16))])

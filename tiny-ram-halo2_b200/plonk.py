@@ -703,6 +703,14 @@ class GpuBackend:
         self._static, self._static_keep = {}, []
         self.static_budget_bytes = 48 << 30
 
+    def close(self):
+        """release the library-side handles (MSM tables of the opening, the domain); torch tensors follow Python's lifetime"""
+        if getattr(self, "ipa_params", None) is not None:
+            self.ipa_params.free(); self.ipa_params = None
+        if getattr(self, "dom", None) is not None:
+            self.dom.free(); self.dom = None
+        self._static.clear(); self._static_keep.clear()
+
     # -- conversions between canonical ints and Montgomery limb arrays (host side: scalars, points, short lists)
     def _limbs(self, vals, mod=None, R=None):
         np = self.np
