@@ -567,6 +567,8 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
         h_ast = h_ast * y + e
     pieces = B.quotient(h_ast, ext_polys)                       # the j - 1 pieces (n coefficients each) of h(X)
     if debug:        # h(X) (X^n - 1) must equal the folded constraint polynomial: checked at a point outside the domain
+        if not getattr(B, "leaves_are_coefficients", False):
+            raise ValueError("debug=True needs a backend whose quotient leaves stay in coefficient form (GpuBackend)")
         xd = 0x1234567890abcdef1234567890abcdef % p
         lhs = eval_ast_at_point(B, h_ast, ext_polys, xd)
         hx, xdn = 0, pow(xd, n, p)
@@ -702,6 +704,7 @@ class GpuBackend:
         self.ev = P.new_evaluator(ctx)
         self._static, self._static_keep = {}, []
         self.static_budget_bytes = 48 << 30
+        self.leaves_are_coefficients = True       # coeff_to_extended keeps coefficient form (cosets are expanded in quotient())
 
     def close(self):
         """release the library-side handles (MSM tables of the opening, the domain); torch tensors follow Python's lifetime"""
