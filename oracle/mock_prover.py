@@ -63,7 +63,7 @@ def check(PL, cs, n, p, fixed, advice, instances, copies=(), gate_names=None, ma
             failures.append(f"lookup {li}: input rows {bad[:8]} not in the table, e.g. {inp[bad[0]][:4]}")
             if len(failures) >= max_failures:
                 return failures
-    for (lk, lc, lr), (rk, rc, rr) in copies:
+    for (lk, lc, lr), (rk, rc, rr) in PL.expand_copies(copies):
         if cols[lk][lc][lr] != cols[rk][rc][rr]:
             failures.append(f"copy ({lk} {lc} row {lr}) != ({rk} {rc} row {rr})")
             if len(failures) >= max_failures:

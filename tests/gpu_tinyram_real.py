@@ -43,11 +43,9 @@ class Rng:
         return a
 
 
-# the longest counting loop whose trace fits `steps`: 2 set-up steps, (len(body) + 3) per pass, 1 Answer
-body = TP.mixed_body(T, W)
-iters = max(1, (steps - 3) // (len(body) + 3))
+from tiny_ram_halo2_b200 import programs
 t0 = time.perf_counter()
-tr = TP.counting_loop(T, W, iters, body)
+tr = programs.longest_loop(W, steps)                       # 2 set-up steps, (len(body) + 3) per pass, 1 Answer
 t_trace = time.perf_counter() - t0
 t0 = time.perf_counter()
 circ, fixed, copies, adv, inst = TR.build(PL, tr, k, dense=False, keygen_from_empty_circuit="--empty-keygen" in sys.argv)
@@ -80,7 +78,7 @@ for rep in range(2):
                  "kernel_launches": ctx.launches - launches0, "torch_peak_gib": round(torch.cuda.max_memory_allocated() / 2**30, 1)})
 res = {"circuit": "TinyRamCircuit (tinyram.py)", "word_bits": W, "k": k, "trace_steps": len(tr.exe), "program_lines": len(tr.prog),
        "table_len": circ.table_len, "advice": cs.num_advice, "instance": cs.num_instance, "fixed": cs.num_fixed, "gates": len(cs.gates),
-       "lookups": len(cs.lookups), "equality_columns": len(cs.permutation), "copies": len(copies), "cs_degree": cs.degree(),
+       "lookups": len(cs.lookups), "equality_columns": len(cs.permutation), "copies": sum(getattr(c, "rows", 1) for c in copies), "cs_degree": cs.degree(),
        "proof_bytes": len(proof), "interpreter_s": round(t_trace, 3), "synthesize_s": round(t_synth, 3), "params_new_s": round(t_params, 3),
        "upload_s": round(t_upload, 3), "keygen_s": round(t_keygen, 3), "first_proof": runs[0], "second_proof": runs[1]}
 if verify:

@@ -123,3 +123,32 @@ def test_permutation_mapping_is_sparse_and_cyclic(PL):
         PL.permutation_mapping(cs, 16, [((A, a, 0), (PL.FIXED, 0, 0))])
     with pytest.raises(ValueError):
         PL.permutation_mapping(cs, 16, [((A, a, 0), (A, b, 16))])
+
+
+def test_copy_blocks_are_swaps_only_when_nothing_else_touches_them(PL):
+    """keygen's block path (row-range swaps on the device) must equal the general cycle merge of the expanded constraints"""
+    cs = PL.ConstraintSystem()
+    cols = [cs.advice_column() for _ in range(4)]
+    inst = cs.instance_column()
+    A, I = PL.ADVICE, PL.INSTANCE
+    for c in cols: cs.enable_equality(A, c)
+    cs.enable_equality(I, inst)
+    n = 64
+    copies = [PL.CopyBlock((I, inst, 0), (A, cols[0], 0), 16),          # clean 2-cycles
+              PL.CopyBlock((A, cols[1], 4), (A, cols[2], 8), 10),       # overlaps the next block in column 2 -> general path
+              PL.CopyBlock((A, cols[2], 12), (A, cols[3], 0), 6),
+              PL.CopyBlock((A, cols[3], 20), (A, cols[3], 24), 8),      # overlaps itself (shifted copy within a column) -> general path
+              PL.CopyBlock((A, cols[1], 40), (A, cols[3], 40), 5),      # touched by a single pair below -> general path
+              ((A, cols[1], 42), (A, cols[0], 50)),
+              PL.CopyBlock((A, cols[0], 30), (A, cols[0], 30), 3)]      # a cell copied onto itself: no-op
+    want = PL.permutation_mapping(cs, n, copies)
+    pairs, blocks = PL._split_disjoint_blocks(cs, n, list(copies))
+    got = PL.permutation_mapping(cs, n, pairs)
+    assert len(blocks) == 1
+    for (i, r, i2, r2, rows) in blocks:
+        for t in range(rows):
+            assert (i, r + t) not in got and (i2, r2 + t) not in got
+            got[(i, r + t)], got[(i2, r2 + t)] = (i2, r2 + t), (i, r + t)
+    assert got == want
+    with pytest.raises(ValueError):
+        PL._split_disjoint_blocks(cs, n, [PL.CopyBlock((A, cols[0], 60), (A, cols[1], 0), 8)])

@@ -196,7 +196,7 @@ def test_keygen_from_the_empty_circuit(mods):
     fixed = [f.dense(64) for f in fixed]
     assert not any(fixed[c.s_table]) and not any(fixed[c.first_line]) and not any(fixed[c.time])
     assert sum(fixed[c.s_prog]) == 16 and fixed[c.prog_pc][:17] == list(range(16)) + [0]
-    assert len(copies) == 94 * 16
+    assert len(copies) == 94 and len(list(PL.expand_copies(copies))) == 94 * 16
     assert fixed[c.t_even][:16] == [TR.even_bits_at(i) for i in range(16)]
     assert fixed[c.t_pow_powers][:10] == [1, 2, 4, 8, 16, 32, 64, 128, 0, 1]          # row 8 = (W, 0), then the default row (0, 1)
     assert fixed[c.t_out_opcode][25:28] == [32, 0, 1]                                 # Answer + 1, the all-zero default row, fill = row 0

@@ -36,15 +36,11 @@ def answer_only(T, W):
 
 
 def counting_loop(T, W, iterations, body=()):
-    """not from the reference: the long-trace workload of BASELINE.json configs[3] -- r0 counts to `iterations`, the body runs
-    every pass; only instructions the reference's witness generation covers (immediate operands, CnJmp for the back edge)"""
-    prog = [T.Mov(0, T.Imm(0)), T.Mov(1, T.Imm(1))] + list(body) + [T.Add(0, 0, T.Imm(1)), T.Cmpe(0, T.Imm(iterations)), T.CnJmp(T.Imm(2)),
-                                                                    T.Answer(T.Imm(1))]
-    return T.eval_program(prog, T.Mem(W, [1]))
+    """the long-trace workload of BASELINE.json configs[3] (tiny-ram-halo2_b200/programs.py; not from the reference)"""
+    from tiny_ram_halo2_b200 import programs
+    return programs.counting_loop(W, iterations, body)
 
 
 def mixed_body(T, W):
-    m = (1 << W) - 1
-    return [T.Add(1, 1, T.Imm(3 & m)), T.Xor(2, 1, T.Imm(0x5A & m)), T.And(3, 2, T.Imm(0x3C & m)), T.Or(4, 3, T.Imm(0x81 & m)),
-            T.Mull(5, 1, T.Imm(7)), T.UMulh(6, 1, T.Imm(m)), T.Sub(7, 1, T.Imm(9)), T.Shr(2, 1, T.Imm(3)), T.Shl(3, 1, T.Imm(2)),
-            T.UDiv(4, 1, T.Imm(5)), T.UMod(5, 1, T.Imm(6)), T.Cmpa(1, T.Imm(100 & m)), T.Cmpge(1, T.Imm(17)), T.SMulh(6, 1, T.Imm(m - 2))]
+    from tiny_ram_halo2_b200 import programs
+    return programs.mixed_body(W)

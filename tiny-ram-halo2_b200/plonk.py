@@ -239,6 +239,70 @@ class ProvingKey:
     l_last: object
 
 
+@dataclass(frozen=True)
+class CopyBlock:
+    """`rows` consecutive copy constraints (kind, column, row0 + t) == (kind', column', row0' + t), t < rows: what a loop of
+    assign_advice_from_instance / copy_advice over a region produces (e.g. /root/reference/src/circuits/tables/prog.rs:206-216).
+    Equivalent to its expansion into pairs; keygen handles blocks that touch no other constraint without expanding them."""
+    left: Tuple[str, int, int]
+    right: Tuple[str, int, int]
+    rows: int
+
+
+def expand_copies(copies):
+    """the copy constraints as plain ((kind, column, row), (kind, column, row)) pairs"""
+    for c in copies:
+        if isinstance(c, CopyBlock):
+            (lk, lc, lr), (rk, rc, rr) = c.left, c.right
+            for t in range(c.rows):
+                yield ((lk, lc, lr + t), (rk, rc, rr + t))
+        else:
+            yield c
+
+
+def _split_disjoint_blocks(cs: ConstraintSystem, n: int, copies):
+    """(pairs, blocks): blocks = the CopyBlocks whose cells occur in no other copy constraint (their cycles are the 2-cycles
+    left <-> right, so sigma is a swap of two row ranges), as (column, row0, column', row0', rows) over cs.permutation indices;
+    every other constraint is returned expanded in `pairs`."""
+    col_of = {kc: i for i, kc in enumerate(cs.permutation)}
+    blocks = [c for c in copies if isinstance(c, CopyBlock)]
+    pairs = [c for c in copies if not isinstance(c, CopyBlock)]
+    spans = []                                  # (column, lo, hi, block index)
+    for bi, b in enumerate(blocks):
+        for kind, col, r0 in (b.left, b.right):
+            if (kind, col) not in col_of:
+                raise ValueError("copy constraint on a column without enable_equality")
+            if not (0 <= r0 and r0 + b.rows <= n):
+                raise ValueError("copy constraint outside the domain")
+            spans.append((col_of[(kind, col)], r0, r0 + b.rows, bi))
+    spans.sort()
+    shared = set()
+    for (c0, lo0, hi0, b0), (c1, lo1, hi1, b1) in zip(spans, spans[1:]):
+        if c0 == c1 and lo1 < hi0:
+            shared.update((b0, b1))
+    if pairs and blocks:
+        import bisect
+        starts = [(c, lo) for c, lo, _, _ in spans]
+        for pair in pairs:
+            for kind, col, r in pair:
+                i = bisect.bisect_right(starts, (col_of.get((kind, col), -1), r)) - 1
+                if i >= 0 and spans[i][0] == col_of.get((kind, col), -1) and spans[i][1] <= r < spans[i][2]:
+                    shared.add(spans[i][3])
+    out, ordered, bi = [], [], 0                # halo2 merges cycles in the order of the copy calls: keep that order
+    for c in copies:
+        if not isinstance(c, CopyBlock):
+            ordered.append(c)
+            continue
+        b = c
+        if bi in shared or b.left[:2] == b.right[:2] and abs(b.left[2] - b.right[2]) < b.rows:
+            ordered.extend(expand_copies([b]))
+        elif b.rows:
+            out.append((col_of[b.left[:2]], b.left[2], col_of[b.right[:2]], b.right[2], b.rows))
+        bi += 1
+    pairs = ordered
+    return pairs, out
+
+
 def permutation_mapping(cs: ConstraintSystem, n: int, copies):
     """permutation::keygen::Assembly: cycles of the copy constraints (copy -> merge the two cycles, smaller into larger).
     Returns {(column, row): (column', row')} for the cells whose image differs from themselves; column = index into
@@ -246,7 +310,7 @@ def permutation_mapping(cs: ConstraintSystem, n: int, copies):
     so keygen stays O(copies) however large n is."""
     col_of = {kc: i for i, kc in enumerate(cs.permutation)}
     mapping, aux, sizes = {}, {}, {}
-    for (lk, lc, lr), (rk, rc, rr) in copies:
+    for (lk, lc, lr), (rk, rc, rr) in expand_copies(copies):
         if (lk, lc) not in col_of or (rk, rc) not in col_of:
             raise ValueError("copy constraint on a column without enable_equality")
         left, right = (col_of[(lk, lc)], lr), (col_of[(rk, rc)], rr)
@@ -297,7 +361,11 @@ def keygen(backend, cs: ConstraintSystem, fixed_values, copies=()) -> ProvingKey
         raise ValueError("one column per fixed column")
     fixed_values = [backend.vec(v) for v in fixed_values]
     fixed_commitments = backend.commit_lagrange_many(fixed_values, [1] * len(fixed_values))          # Blind::default() = 1
-    sigma_values = backend.sigma_vecs(len(cs.permutation), permutation_mapping(cs, n, copies))
+    if hasattr(backend, "sigma_swap_blocks"):     # row-range swaps for the blocks no other constraint touches
+        pairs, blocks = _split_disjoint_blocks(cs, n, list(copies))
+        sigma_values = backend.sigma_swap_blocks(backend.sigma_vecs(len(cs.permutation), permutation_mapping(cs, n, pairs)), blocks)
+    else:
+        sigma_values = backend.sigma_vecs(len(cs.permutation), permutation_mapping(cs, n, copies))
     permutation_commitments = backend.commit_lagrange_many(sigma_values, [1] * len(sigma_values))
     pt = lambda c: "Identity" if c is None else f"({c[0]:#066x}, {c[1]:#066x})"
     text = (f"PinnedVerificationKey {{ base_modulus: {backend.q:#066x}, scalar_modulus: {p:#066x}, domain: PinnedEvaluationDomain {{ k: {backend.k}, "
@@ -819,6 +887,25 @@ class GpuBackend:
                 out[i][idx] = self._dev(self._limbs(vals))
             self._sync()
         return out
+
+    def sigma_swap_blocks(self, sigmas, blocks):
+        """blocks: (column, row0, column', row0', rows) 2-cycles left <-> right that no other constraint touches: the two row
+        ranges exchange their identity labels delta^column * omega^row (device copies, nothing per cell on the host)"""
+        if not blocks:
+            return sigmas
+        base = self._new()
+        self._sync()
+        self.ctx.check(self.lib.trp_dev_powers(self.ctx.handle, 0, self._m(self.omega), self.n, base.data_ptr()))
+        scal = {}
+        for (i, r, i2, r2, rows) in blocks:
+            for (dst, d0, src, s0) in ((i, r, i2, r2), (i2, r2, i, r)):
+                if src not in scal:
+                    scal[src] = self._dev(self._limbs([pow(self.delta, src, self.p)]))
+                self._sync()
+                self.ctx.check(self.lib.trp_dev_field_op(self.ctx.handle, 0, 2 | 16, base[s0:s0 + rows].data_ptr(), scal[src].data_ptr(),
+                                                         sigmas[dst][d0:d0 + rows].data_ptr(), rows))
+        self._sync()
+        return sigmas
 
     # -- commitments and transforms
     def _commit(self, bases, v, blind):

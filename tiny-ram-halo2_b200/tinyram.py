@@ -486,7 +486,7 @@ class TinyRamCircuit:
     def synthesize(self, trace: Optional[T.Trace], n: int, a_flag_rand: Optional[Callable[[], int]] = None,
                    reg_operand_value: bool = True):
         """Returns (fixed, copies, advice): fixed = one FixedColumn (assigned prefix + fill value) per fixed column, advice = one
-        sparse {row: value} dict per advice column, copies = the copy constraints of assign_advice_from_instance.  Values are
+        sparse {row: value} dict per advice column, copies = the copy constraints of assign_advice_from_instance (one plonk.CopyBlock per column pair).  Values are
         canonical ints of the circuit field.
 
         reg_operand_value: push_temp_var_vals takes a REGISTER operand's temp-var value to be the register's INDEX
@@ -519,8 +519,7 @@ class TinyRamCircuit:
 
         # ProgConfig::assign_prog (prog.rs:195-233): the program table is a copy of the instance columns
         for ic, tc in zip(self.prog_input.to_vec(), self.prog_table.to_vec()):
-            for off in range(TL):
-                copies.append(((I, ic, off), (A, tc, off)))
+            copies.append(PL.CopyBlock((I, ic, 0), (A, tc, 0), TL))
         for off in range(TL):
             fixed[self.s_prog][off] = 1
             fixed[self.dyn_tag][off] = 1
@@ -779,11 +778,11 @@ def device_columns(be, columns) -> list:
         if len(prefix) > be.n:
             raise ValueError("column longer than the domain")
         if (not prefix or max(prefix) < 1 << 64) and fill < 1 << 64:
-            host = np.full((be.n, 4), 0, dtype=np.uint64)
-            host[:, 0] = fill
+            v = torch.zeros((be.n, 4), dtype=torch.int64, device="cuda")       # only the assigned prefix crosses PCIe
+            if fill:
+                v[:, 0] = int(np.uint64(fill).view(np.int64)) if fill >= 1 << 63 else fill
             if prefix:
-                host[:len(prefix), 0] = np.array(prefix, dtype=np.uint64)
-            v = torch.from_numpy(host.view(np.int64)).cuda()
+                v[:len(prefix), 0] = torch.from_numpy(np.array(prefix, dtype=np.uint64).view(np.int64)).cuda()
             be._sync()
             be.ctx.check(be.lib.trp_dev_field_op(be.ctx.handle, 0, 2 | 16, v.data_ptr(), r2.data_ptr(), v.data_ptr(), be.n))
             be._sync()
