@@ -198,6 +198,15 @@ int trp_permute_expression_pair(trp_ctx* ctx, const uint64_t* input, const uint6
 /* out[j] = sum_i polys[j * stride + i] * x^i, i < n, for j < m: m evaluations at ONE point (the evaluations at x * omega^rot) */
 int trp_dev_eval_polynomials(trp_ctx* ctx, int which_field, const uint64_t* d_polys, size_t stride, size_t n, size_t m,
                              const uint64_t x[4], uint64_t* d_out /* m x 4 */);
+/* the same for m polynomials that live in separate device buffers: d_poly_ptrs is a HOST array of m device pointers (the ~700
+ * openings of create_proof are evaluations of separately allocated polynomials at four points: x, x*omega, x*omega^-1, x*omega^-(bf+1)) */
+int trp_dev_eval_polynomials_at(trp_ctx* ctx, int which_field, const uint64_t* const* d_poly_ptrs, size_t n, size_t m, const uint64_t x[4],
+                                uint64_t* d_out /* m x 4 */);
+/* d_out[i] = sum_j scalars[j] * d_poly_ptrs[j][i], i < n: the random linear combinations of poly/multiopen/prover.rs (q_polys folded
+ * with powers of x_1, the final polynomial with powers of x_4).  d_poly_ptrs: HOST array of m device pointers; scalars: HOST array
+ * of m Montgomery field elements; d_out must not alias an input. */
+int trp_dev_linear_combination(trp_ctx* ctx, int which_field, const uint64_t* const* d_poly_ptrs, const uint64_t* scalars, size_t n, size_t m,
+                               uint64_t* d_out);
 int trp_eval_polynomial(trp_ctx* ctx, int which_field, const uint64_t* coeffs, size_t n, const uint64_t x[4], uint64_t out[4]);
 /* out[j] = <a_j, b_j>, vectors j at d_a + j * a_stride / d_b + j * b_stride elements (stride 0 = shared vector) */
 int trp_dev_inner_products(trp_ctx* ctx, int which_field, const uint64_t* d_a, size_t a_stride, const uint64_t* d_b, size_t b_stride,

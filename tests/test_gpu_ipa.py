@@ -49,7 +49,7 @@ def pt_of(curve, limbs):
 
 
 @pytest.mark.parametrize("curve", [O.VESTA, O.PALLAS])
-@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 8191, 8192, 8193, 100001])
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 255, 256, 257, 8191, 8192, 8193, 16385, 100001])
 def test_eval_polynomial(pkg, ctxs, curve, n):
     ctx = ctxs[curve]
     field, F = FIELD_OF[curve]
@@ -73,6 +73,28 @@ def test_eval_polynomials_batched_device(pkg, ctxs):
     ctx.check(ctx.lib.trp_dev_eval_polynomials(ctx.handle, 0, d.data_ptr(), stride, n, m, mont(O.FP, [x])[0].ctypes.data, out.data_ptr()))
     ctx.sync()
     assert ints(O.FP, out.cpu().numpy().view(np.uint64)) == [pm.eval_polynomial(pm.Fp, c[:n], x) for c in cols]
+
+
+@pytest.mark.parametrize("n", [1, 300, 8192, 8200, 40000])
+def test_eval_polynomials_at_pointer_table(pkg, ctxs, n):
+    """trp_dev_eval_polynomials_at: separately allocated polynomials (the openings of create_proof), one point"""
+    import ctypes
+    import torch
+    ctx = ctxs[O.VESTA]
+    rng = random.Random(n)
+    m = 9
+    cols = [[rng.randrange(pm.Fp.p) for _ in range(n)] for _ in range(m)]
+    cols[3] = [0] * n
+    bufs = [torch.from_numpy(mont(O.FP, c).view(np.int64)).cuda() for c in cols]
+    pad = torch.zeros(77, dtype=torch.int64, device="cuda")          # keeps the allocations from being one strided block
+    out = torch.zeros((m, 4), dtype=torch.int64, device="cuda")
+    tab = (ctypes.c_void_p * m)(*[b.data_ptr() for b in bufs])
+    for x in (rng.randrange(pm.Fp.p), 0, 1):
+        torch.cuda.synchronize()
+        ctx.check(ctx.lib.trp_dev_eval_polynomials_at(ctx.handle, 0, tab, n, m, mont(O.FP, [x])[0].ctypes.data, out.data_ptr()))
+        ctx.sync()
+        assert ints(O.FP, out.cpu().numpy().view(np.uint64)) == [pm.eval_polynomial(pm.Fp, c, x) for c in cols]
+    assert ctx.lib.trp_dev_eval_polynomials_at(ctx.handle, 0, None, n, m, mont(O.FP, [1])[0].ctypes.data, out.data_ptr()) != 0
 
 
 @pytest.mark.parametrize("curve", [O.VESTA, O.PALLAS])

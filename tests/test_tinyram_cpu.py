@@ -219,3 +219,14 @@ def test_real_proof_on_the_cpu_backend_verifies(mods):
     assert not VM.verify_proof(C, be.params, pk.vk, other, proof)
     with pytest.raises(ValueError):
         PL.create_proof(be, pk, inst, adv, lambda: 1, PL.Blake2bWrite(C.base.p, C.scalar.p), debug=True)
+
+
+def test_word_size_32_short_trace(mods):
+    """BASELINE.json configs[3] uses word size 32 (untested in the reference): 2^16-row tables, k >= 17"""
+    PL, TR, T = mods
+    tr = TP.counting_loop(T, 32, 2, TP.mixed_body(T, 32))
+    circ, fixed, copies, adv, inst = TR.build(PL, tr, 17, dense=False)
+    assert circ.table_len == 1 << 16 and len(inst[0]) == 1 << 16
+    n = 1 << 17
+    dense = [f.dense(n) for f in fixed]
+    assert MP.check(PL, circ.cs, n, TR.PL_FIELD_MODULUS, dense, adv, inst, copies, circ.gate_names) == []

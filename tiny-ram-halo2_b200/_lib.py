@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "trp_dev_batch_invert", "trp_batch_invert", "trp_dev_grand_product", "trp_grand_product",
     "trp_dev_permutation_product", "trp_permutation_product", "trp_dev_lookup_product", "trp_lookup_product",
     "trp_dev_permute_expression_pair", "trp_permute_expression_pair",
-    "trp_dev_eval_polynomials", "trp_eval_polynomial", "trp_dev_inner_products", "trp_compute_inner_product", "trp_dev_powers",
+    "trp_dev_eval_polynomials", "trp_dev_eval_polynomials_at", "trp_dev_linear_combination", "trp_eval_polynomial", "trp_dev_inner_products", "trp_compute_inner_product", "trp_dev_powers",
     "trp_dev_kate_division", "trp_kate_division", "trp_dev_fold", "trp_dev_generator_collapse", "trp_dev_msm_var",
     "trp_dev_hash_to_curve", "trp_hash_to_curve", "trp_dev_group_fft", "trp_group_fft", "trp_params_new", "trp_dev_params_new",
 ]
@@ -122,6 +122,8 @@ def load_library():
     L.trp_dev_permute_expression_pair.argtypes = [vp, vp, vp, sz, vp, vp, ctypes.POINTER(i)]
     L.trp_permute_expression_pair.argtypes = [vp, vp, vp, sz, vp, vp, ctypes.POINTER(i)]
     L.trp_dev_eval_polynomials.argtypes = [vp, i, vp, sz, sz, sz, vp, vp]
+    L.trp_dev_eval_polynomials_at.argtypes = [vp, i, vp, sz, sz, vp, vp]
+    L.trp_dev_linear_combination.argtypes = [vp, i, vp, vp, sz, sz, vp]
     L.trp_eval_polynomial.argtypes = [vp, i, vp, sz, vp, vp]
     L.trp_dev_inner_products.argtypes = [vp, i, vp, sz, vp, sz, sz, sz, vp]
     L.trp_compute_inner_product.argtypes = [vp, i, vp, vp, sz, vp]

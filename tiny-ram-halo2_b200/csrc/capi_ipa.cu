@@ -44,7 +44,46 @@ int trp_dev_eval_polynomials(trp_ctx* ctx, int which_field, const uint64_t* d_po
   if ((n && !d_polys) || !x || !d_out) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
   if (m > 1 && stride < n) TRP_FAIL(ctx, TRP_E_INVALID, "stride %zu is smaller than the polynomial length %zu", stride, n);
   TRP_TRY(trp_ws_reserve(ctx, trp_reduce_ws_bytes(ctx, n, m)));
-  return trp_eval_polys_impl(ctx, field_id(ctx, which_field), d_polys, stride, n, m, x, d_out, ctx->ws);
+  return trp_eval_polys_impl(ctx, field_id(ctx, which_field), d_polys, stride, nullptr, n, m, x, d_out, ctx->ws);
+}
+
+int trp_dev_eval_polynomials_at(trp_ctx* ctx, int which_field, const uint64_t* const* d_poly_ptrs, size_t n, size_t m, const uint64_t x[4],
+                                uint64_t* d_out) {
+  if (!ctx) return TRP_E_INVALID;
+  Locked l(ctx);
+  if (m == 0) return TRP_OK;
+  if (!d_poly_ptrs || !x || !d_out) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
+  for (size_t j = 0; n && j < m; ++j)
+    if (!d_poly_ptrs[j]) TRP_FAIL(ctx, TRP_E_INVALID, "polynomial %zu is NULL", j);
+  const size_t rb = trp_reduce_ws_bytes(ctx, n, m), tb = ws_align(m * sizeof(void*));
+  TRP_TRY(trp_ws_reserve(ctx, rb + tb));
+  void* d_tab = (char*)ctx->ws + rb;            // the pointer table rides in the workspace behind the reduction scratch
+  TRP_CUDA(ctx, cudaMemcpyAsync(d_tab, d_poly_ptrs, m * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = trp_eval_polys_impl(ctx, field_id(ctx, which_field), nullptr, 0, (const void* const*)d_tab, n, m, x, d_out, ctx->ws);
+  TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // d_poly_ptrs is a pageable host array: the copy must have left it
+  return rc;
+}
+
+int trp_dev_linear_combination(trp_ctx* ctx, int which_field, const uint64_t* const* d_poly_ptrs, const uint64_t* scalars, size_t n, size_t m,
+                               uint64_t* d_out) {
+  if (!ctx) return TRP_E_INVALID;
+  Locked l(ctx);
+  if (!d_out && n) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
+  if (m == 0) { if (n) TRP_CUDA(ctx, cudaMemsetAsync(d_out, 0, n * 32, ctx->stream)); return TRP_OK; }
+  if (!d_poly_ptrs || !scalars) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
+  if (m > 0xffffffffu) TRP_FAIL(ctx, TRP_E_INVALID, "too many terms");
+  for (size_t j = 0; n && j < m; ++j) {
+    if (!d_poly_ptrs[j]) TRP_FAIL(ctx, TRP_E_INVALID, "polynomial %zu is NULL", j);
+    if (d_poly_ptrs[j] == d_out) TRP_FAIL(ctx, TRP_E_INVALID, "the output may not alias input %zu", j);
+  }
+  const size_t tb = ws_align(m * sizeof(void*)), sb = ws_align(m * 32);
+  TRP_TRY(trp_ws_reserve(ctx, tb + sb));
+  char* d_tab = (char*)ctx->ws; char* d_scal = d_tab + tb;
+  TRP_CUDA(ctx, cudaMemcpyAsync(d_tab, d_poly_ptrs, m * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+  TRP_CUDA(ctx, cudaMemcpyAsync(d_scal, scalars, m * 32, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = trp_lincomb_impl(ctx, field_id(ctx, which_field), (const void* const*)d_tab, d_scal, m, n, d_out);
+  TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the host arrays are pageable: the copies must have left them
+  return rc;
 }
 
 int trp_eval_polynomial(trp_ctx* ctx, int which_field, const uint64_t* coeffs, size_t n, const uint64_t x[4], uint64_t out[4]) {
@@ -55,7 +94,7 @@ int trp_eval_polynomial(trp_ctx* ctx, int which_field, const uint64_t* coeffs, s
   TRP_TRY(trp_ws_reserve(ctx, rb + cb + 256));
   char* dc = (char*)ctx->ws + rb; char* dout = dc + cb;
   if (n) TRP_CUDA(ctx, cudaMemcpyAsync(dc, coeffs, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  TRP_TRY(trp_eval_polys_impl(ctx, field_id(ctx, which_field), dc, n, n, 1, x, dout, ctx->ws));
+  TRP_TRY(trp_eval_polys_impl(ctx, field_id(ctx, which_field), dc, n, nullptr, n, 1, x, dout, ctx->ws));
   TRP_CUDA(ctx, cudaMemcpyAsync(out, dout, 32, cudaMemcpyDeviceToHost, ctx->stream));
   TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return TRP_OK;

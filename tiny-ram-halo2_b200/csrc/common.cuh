@@ -181,7 +181,9 @@ int trp_lookup_product_impl(trp_domain* d, const void* d_a, const void* d_s, con
 int trp_suffix_sum_impl(trp_ctx* ctx, int field, void* d_a, size_t n, void* d_tiles);
 // ipa.cu (row f2): evaluations, inner products, Kate division, IPA round folding; msm.cu: MSM over caller-owned bases
 size_t trp_reduce_ws_bytes(trp_ctx* ctx, size_t n, size_t m);
-int trp_eval_polys_impl(trp_ctx* ctx, int field, const void* d_polys, size_t stride, size_t n, size_t m, const uint64_t x[4], void* d_out, void* ws);
+int trp_lincomb_impl(trp_ctx* ctx, int field, const void* const* d_ptrs, const void* d_scal, size_t m, size_t n, void* d_out);
+int trp_eval_polys_impl(trp_ctx* ctx, int field, const void* d_polys, size_t stride, const void* const* d_ptrs, size_t n, size_t m,
+                        const uint64_t x[4], void* d_out, void* ws);
 int trp_inner_products_impl(trp_ctx* ctx, int field, const void* d_a, size_t a_stride, const void* d_b, size_t b_stride, size_t n, size_t m,
                             void* d_out, void* ws);
 int trp_fold_impl(trp_ctx* ctx, int field, void* d_a, size_t half, const uint64_t u[4]);

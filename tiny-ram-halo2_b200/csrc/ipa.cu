@@ -47,20 +47,38 @@ template <class PR> __device__ __forceinline__ Fe<PR> fe_pow_u64(const Fe<PR>& a
   return fe_pow(a, l, 2);
 }
 
-// partial[poly][block] = sum over the block's chunks of x^start * Horner(chunk);  poly = blockIdx.y
+// Evaluation of m polynomials at one point.  A CTA covers RED_THREADS * CHUNK consecutive coefficients; thread t takes the
+// coefficients base + t + k * RED_THREADS (coalesced 32-byte loads across the warp), runs Horner in y = x^RED_THREADS over
+// them and scales by x^t; thread 0 scales the CTA's sum by x^base.  The powers come from a table made once per call
+// (eval_setup_kernel): pw[t] = x^t for t <= RED_THREADS, then x^(b * RED_THREADS * CHUNK) for every CTA b.
+// partial[poly][block];  poly = blockIdx.y, addressed as polys + poly * stride or through the pointer table `ptrs`.
 template <class PR>
-__global__ void __launch_bounds__(RED_THREADS) eval_poly_kernel(const uint4* polys, size_t stride, size_t n, Fe<PR> x, uint4* partial) {
-  const uint4* c = polys + 2 * (size_t)blockIdx.y * stride;
-  const size_t start = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * CHUNK;
+__global__ void eval_setup_kernel(uint4* pw, unsigned blocks, Fe<PR> x) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > RED_THREADS + blocks) return;
+  const uint64_t e = i <= RED_THREADS ? (uint64_t)i : (uint64_t)(i - RED_THREADS - 1) * RED_THREADS * CHUNK;
+  fe_store(pw + 2 * (size_t)i, e ? fe_pow_u64(x, e) : fe_one<PR>());
+}
+
+template <class PR>
+__global__ void __launch_bounds__(RED_THREADS) eval_poly_kernel(const uint4* polys, size_t stride, const uint4* const* ptrs, size_t n,
+                                                                const uint4* pw, uint4* partial) {
+  const uint4* c = ptrs ? ptrs[blockIdx.y] : polys + 2 * (size_t)blockIdx.y * stride;
+  const size_t i0 = (size_t)blockIdx.x * (RED_THREADS * CHUNK) + threadIdx.x;
   Fe<PR> acc = fe_zero<PR>();
-  if (start < n) {
-    const size_t end = start + CHUNK < n ? start + CHUNK : n;
-    acc = fe_load<PR>(c + 2 * (end - 1));
-    for (size_t k = end - 1; k-- > start;) acc = fe_add(fe_mul(acc, x), fe_load<PR>(c + 2 * k));
-    if (start) acc = fe_mul(acc, fe_pow_u64(x, start));
+  if (i0 < n) {
+    size_t kmax = (n - 1 - i0) / RED_THREADS;
+    if (kmax > CHUNK - 1) kmax = CHUNK - 1;
+    const Fe<PR> y = fe_load<PR>(pw + 2 * RED_THREADS);
+    acc = fe_load<PR>(c + 2 * (i0 + kmax * RED_THREADS));
+    for (size_t k = kmax; k-- > 0;) acc = fe_add(fe_mul(acc, y), fe_load<PR>(c + 2 * (i0 + k * RED_THREADS)));
+    if (threadIdx.x) acc = fe_mul(acc, fe_load<PR>(pw + 2 * threadIdx.x));
   }
   acc = block_sum(acc);
-  if (threadIdx.x == 0) fe_store(partial + 2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x), acc);
+  if (threadIdx.x == 0) {
+    if (blockIdx.x) acc = fe_mul(acc, fe_load<PR>(pw + 2 * (size_t)(RED_THREADS + 1 + blockIdx.x)));
+    fe_store(partial + 2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x), acc);
+  }
 }
 
 // partial[pair][block] = sum_i a[i] * b[i] over the block's grid-stride slice;  pair = blockIdx.y
@@ -83,6 +101,17 @@ __global__ void __launch_bounds__(RED_THREADS) sum_partials_kernel(const uint4* 
   for (unsigned i = threadIdx.x; i < count; i += blockDim.x) acc = fe_add(acc, fe_load<PR>(partial + 2 * ((size_t)blockIdx.x * count + i)));
   acc = block_sum(acc);
   if (threadIdx.x == 0) fe_store(out + 2 * (size_t)blockIdx.x, acc);
+}
+
+// out[i] = sum_j scal[j] * polys[j][i]: the random linear combinations of multiopen (q_polys = sum_j x_1^e_j * p_j over the ~700
+// opened polynomials, poly/multiopen/prover.rs) in one pass over separately allocated inputs
+template <class PR>
+__global__ void __launch_bounds__(RED_THREADS) lincomb_kernel(const uint4* const* polys, const uint4* scal, unsigned m, size_t n, uint4* out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<PR> acc = fe_zero<PR>();
+  for (unsigned j = 0; j < m; ++j) acc = fe_add(acc, fe_mul(fe_load<PR>(polys[j] + 2 * i), fe_load<PR>(scal + 2 * (size_t)j)));
+  fe_store(out + 2 * i, acc);
 }
 
 // a[i] += a[i + half] * u, i < half   (p' with u^-1 and b with u in the IPA round)
@@ -165,12 +194,19 @@ inline unsigned reduce_blocks(trp_ctx* ctx, size_t n, size_t per_block) {
 }
 
 template <class PR>
-int eval_polys_run(trp_ctx* ctx, const void* d_polys, size_t stride, size_t n, size_t m, const uint64_t x[4], void* d_out, void* ws) {
+int eval_polys_run(trp_ctx* ctx, const void* d_polys, size_t stride, const void* const* d_ptrs, size_t n, size_t m, const uint64_t x[4],
+                   void* d_out, void* ws) {
   const unsigned blocks = (unsigned)((n + (size_t)RED_THREADS * CHUNK - 1) / ((size_t)RED_THREADS * CHUNK));
   Fe<PR> fx = fe_from_limbs<PR>(x);
+  const size_t mm_max = m < 65535 ? m : 65535;
+  uint4* pw = (uint4*)((char*)ws + ws_align((size_t)blocks * mm_max * 32));
+  const unsigned entries = RED_THREADS + 1 + blocks;
+  eval_setup_kernel<PR><<<(entries + 63) / 64, 64, 0, ctx->stream>>>(pw, blocks, fx);
+  TRP_LAUNCHED(ctx);
   for (size_t m0 = 0; m0 < m; m0 += 65535) {
     unsigned mm = (unsigned)(m - m0 < 65535 ? m - m0 : 65535);
-    eval_poly_kernel<PR><<<dim3(blocks, mm), RED_THREADS, 0, ctx->stream>>>((const uint4*)d_polys + 2 * m0 * stride, stride, n, fx, (uint4*)ws);
+    eval_poly_kernel<PR><<<dim3(blocks, mm), RED_THREADS, 0, ctx->stream>>>(d_ptrs ? nullptr : (const uint4*)d_polys + 2 * m0 * stride, stride,
+                                                                           d_ptrs ? (const uint4* const*)d_ptrs + m0 : nullptr, n, pw, (uint4*)ws);
     TRP_LAUNCHED(ctx);
     sum_partials_kernel<PR><<<mm, RED_THREADS, 0, ctx->stream>>>((const uint4*)ws, blocks, (uint4*)d_out + 2 * m0);
     TRP_LAUNCHED(ctx);
@@ -194,18 +230,29 @@ int inner_products_run(trp_ctx* ctx, const void* d_a, size_t a_stride, const voi
 
 }  // namespace
 
+int trp_lincomb_impl(trp_ctx* ctx, int field, const void* const* d_ptrs, const void* d_scal, size_t m, size_t n, void* d_out) {
+  if (n == 0) return TRP_OK;
+  const unsigned blocks = (unsigned)((n + RED_THREADS - 1) / RED_THREADS);
+  if (field == 0) lincomb_kernel<FpParams><<<blocks, RED_THREADS, 0, ctx->stream>>>((const uint4* const*)d_ptrs, (const uint4*)d_scal, (unsigned)m, n, (uint4*)d_out);
+  else lincomb_kernel<FqParams><<<blocks, RED_THREADS, 0, ctx->stream>>>((const uint4* const*)d_ptrs, (const uint4*)d_scal, (unsigned)m, n, (uint4*)d_out);
+  TRP_LAUNCHED(ctx);
+  return TRP_OK;
+}
+
 // scratch for m simultaneous reductions over n elements
 size_t trp_reduce_ws_bytes(trp_ctx* ctx, size_t n, size_t m) {
   size_t b1 = (n + (size_t)RED_THREADS * CHUNK - 1) / ((size_t)RED_THREADS * CHUNK);
   size_t b2 = reduce_blocks(ctx, n, (size_t)RED_THREADS * 8);
   size_t mm = m < 65535 ? m : 65535;
-  return ws_align((b1 > b2 ? b1 : b2) * (mm ? mm : 1) * 32) + 256;
+  return ws_align((b1 > b2 ? b1 : b2) * (mm ? mm : 1) * 32) + ws_align((RED_THREADS + 2 + b1) * 32) + 256;   // partials + the power table
 }
 
-int trp_eval_polys_impl(trp_ctx* ctx, int field, const void* d_polys, size_t stride, size_t n, size_t m, const uint64_t x[4], void* d_out, void* ws) {
+int trp_eval_polys_impl(trp_ctx* ctx, int field, const void* d_polys, size_t stride, const void* const* d_ptrs, size_t n, size_t m,
+                        const uint64_t x[4], void* d_out, void* ws) {
   if (m == 0) return TRP_OK;
   if (n == 0) { TRP_CUDA(ctx, cudaMemsetAsync(d_out, 0, m * 32, ctx->stream)); return TRP_OK; }
-  return field == 0 ? eval_polys_run<FpParams>(ctx, d_polys, stride, n, m, x, d_out, ws) : eval_polys_run<FqParams>(ctx, d_polys, stride, n, m, x, d_out, ws);
+  return field == 0 ? eval_polys_run<FpParams>(ctx, d_polys, stride, d_ptrs, n, m, x, d_out, ws)
+                    : eval_polys_run<FqParams>(ctx, d_polys, stride, d_ptrs, n, m, x, d_out, ws);
 }
 
 int trp_inner_products_impl(trp_ctx* ctx, int field, const void* d_a, size_t a_stride, const void* d_b, size_t b_stride, size_t n, size_t m,

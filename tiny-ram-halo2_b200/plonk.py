@@ -353,6 +353,8 @@ def keygen(backend, cs: ConstraintSystem, fixed_values, copies=()) -> ProvingKey
     """keygen_vk + keygen_pk.  fixed_values: one column per fixed column -- a list of at most n ints (zero-padded) or a
     backend vector."""
     n, p = backend.n, backend.p
+    if hasattr(backend, "end_proof"):
+        backend.end_proof()                    # key material never lives in a proof's polynomial arena
     if n < cs.minimum_rows():
         raise ValueError("NotEnoughRowsAvailable")
     if backend.j != cs.degree():
@@ -497,6 +499,9 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     if len(instances) != cs.num_instance or len(advice) != cs.num_advice:
         raise ValueError("InvalidInstances / wrong number of advice columns")
     transcript.common_scalar(vk.transcript_repr)
+    if hasattr(B, "begin_proof"):              # instance + advice + (A', S', Z) per lookup + one Z per permutation chunk
+        chunks = -(-len(cs.permutation) // (vk.cs_degree - 2)) if cs.permutation else 0
+        B.begin_proof(cs.num_instance + cs.num_advice + 3 * len(cs.lookups) + chunks)
     import time as _time
     _t = [_time.perf_counter()]
 
@@ -662,17 +667,33 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
             cache[key] = B.eval_polynomial(poly, point)
         return cache[key]
 
-    for kind in (INSTANCE, ADVICE, FIXED):
-        for c, r in cs.queries[kind]:
-            transcript.write_scalar(ev(polys_of[kind][c], rot(x, r)))
     h_poly, h_blind = None, 0
     for piece, b in zip(reversed(pieces), reversed(h_blinds)):
         h_poly = B.mul_add(h_poly, xn, piece)
         h_blind = (h_blind * xn + b) % p
+    x_next, x_inv, x_last = rot(x, 1), rot(x, -1), rot(x, -(bf + 1))
+    many = getattr(B, "eval_polynomials_at", None)
+    if many is not None:       # nothing below feeds the transcript back into x: all openings are computed up front, point by point
+        want = [(polys_of[kind][c], rot(x, r)) for kind in (INSTANCE, ADVICE, FIXED) for c, r in cs.queries[kind]]
+        want += [(random_poly, x), (h_poly, x)] + [(sp, x) for sp in pk.sigma_polys]
+        for i, S in enumerate(perm_sets):
+            want += [(S["poly"], x), (S["poly"], x_next)] + ([(S["poly"], x_last)] if i + 1 < len(perm_sets) else [])
+        for L in lookups:
+            want += [(L["z_poly"], x), (L["z_poly"], x_next), (L["pi_poly"], x), (L["pi_poly"], x_inv), (L["pt_poly"], x)]
+        by_point = {}
+        for poly, pt_ in want:
+            if (id(poly), pt_) not in cache:
+                cache[(id(poly), pt_)] = None
+                by_point.setdefault(pt_, []).append(poly)
+        for pt_, polys_ in by_point.items():
+            for poly, val in zip(polys_, many(polys_, pt_)):
+                cache[(id(poly), pt_)] = val
+    for kind in (INSTANCE, ADVICE, FIXED):
+        for c, r in cs.queries[kind]:
+            transcript.write_scalar(ev(polys_of[kind][c], rot(x, r)))
     transcript.write_scalar(ev(random_poly, x))
     for sp in pk.sigma_polys:
         transcript.write_scalar(ev(sp, x))
-    x_next, x_inv, x_last = rot(x, 1), rot(x, -1), rot(x, -(bf + 1))
     for i, S in enumerate(perm_sets):
         transcript.write_scalar(ev(S["poly"], x))
         transcript.write_scalar(ev(S["poly"], x_next))
@@ -715,11 +736,19 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     ns = len(point_sets)
     q_polys, q_blinds = [None] * ns, [0] * ns
     q_eval_sets = [[0] * len(ps) for ps in point_sets]
+    lincomb = getattr(B, "linear_combination", None)
+    members = [[] for _ in range(ns)]
     for cd in cmap:
         s, o = cd["set_index"], cd["commitment"]
-        q_polys[s] = B.mul_add(q_polys[s], x_1, o.poly)
+        if lincomb is None:
+            q_polys[s] = B.mul_add(q_polys[s], x_1, o.poly)
+        members[s].append(o.poly)
         q_blinds[s] = (q_blinds[s] * x_1 + o.blind) % p
         q_eval_sets[s] = [(a * x_1 + e) % p for a, e in zip(q_eval_sets[s], cd["evals"])]
+    if lincomb is not None:       # q_polys[s] = sum_j x_1^(r - 1 - j) * member_j: the same Horner fold, one pass over the inputs
+        for s, polys_ in enumerate(members):
+            r = len(polys_)
+            q_polys[s] = lincomb(polys_, [pow(x_1, r - 1 - j, p) for j in range(r)])
     q_prime = None
     for points, evals, poly in zip(point_sets, q_eval_sets, q_polys):
         cur = B.sub_low(poly, lagrange_interpolate(points, evals, p))
@@ -739,6 +768,8 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     tick("multiopen")
     B.ipa_create_proof(rand, transcript, p_poly, p_blind, x_3)
     tick("ipa")
+    if hasattr(B, "end_proof"):
+        B.end_proof()
     return transcript.finalize()
 
 
@@ -772,6 +803,7 @@ class GpuBackend:
         self.ev = P.new_evaluator(ctx)
         self._static, self._static_keep = {}, []
         self.static_budget_bytes = 48 << 30
+        self._arena, self._arena_used, self._arena_slot, self._arena_on, self._coset_buf = None, 0, {}, False, None
         self.leaves_are_coefficients = True       # coeff_to_extended keeps coefficient form (cosets are expanded in quotient())
 
     def close(self):
@@ -781,6 +813,7 @@ class GpuBackend:
         if getattr(self, "dom", None) is not None:
             self.dom.free(); self.dom = None
         self._static.clear(); self._static_keep.clear()
+        self._arena, self._arena_slot, self._arena_on, self._coset_buf = None, {}, False, None
 
     # -- conversions between canonical ints and Montgomery limb arrays (host side: scalars, points, short lists)
     def _limbs(self, vals, mod=None, R=None):
@@ -938,8 +971,27 @@ class GpuBackend:
     def commit_lagrange_many(self, vecs, blinds): return self._commit_many(self.params.g_lagrange, vecs, blinds)
     def commit_many(self, vecs, blinds): return self._commit_many(self.params.g, vecs, blinds)
 
+    # -- per-proof polynomial arena: create_proof announces how many polynomials it will bring to coefficient form; they are then
+    #    laid out in ONE (count, n, 4) block, which the quotient's batched coset NTT reads in place (no 15.5 GiB staging copy at
+    #    k = 20).  Polynomials made outside a proof (keygen) never come from the arena.
+    def begin_proof(self, n_polys):
+        t = self.torch
+        if self._arena is None or self._arena.shape[0] < n_polys:
+            self._arena = None
+            self._arena = t.empty((n_polys, self.n, 4), dtype=t.int64, device="cuda")
+        self._arena_used, self._arena_slot, self._arena_on = 0, {}, True
+
+    def end_proof(self):
+        self._arena_on = False            # the views handed out stay valid until the next begin_proof
+
     def lagrange_to_coeff(self, v):
-        c = v.clone()
+        if self._arena_on and self._arena_used < self._arena.shape[0]:
+            c = self._arena[self._arena_used]
+            self._arena_slot[id(c)] = (self._arena_used, c)      # the view is kept alive: id() must stay unique
+            self._arena_used += 1
+            c.copy_(v)
+        else:
+            c = v.clone()
         self._sync()
         self.ctx.check(self.lib.trp_dev_lagrange_to_coeff(self.dom.handle, c.data_ptr(), 1))
         self._sync()
@@ -974,13 +1026,22 @@ class GpuBackend:
         t, n, ncos = self.torch, self.n, self.j - 1
         prog = P.compile_ast(ast, self.p)
         dyn = [i for i, c in enumerate(ext_polys) if id(c) not in self._static]
-        coeff = t.stack([ext_polys[i] for i in dyn])                  # (cols, n, 4), contiguous for the batched coset NTT
-        buf = t.empty_like(coeff)
+        in_arena = [self._arena_slot.get(id(ext_polys[i])) for i in dyn]
+        if dyn and all(a is not None and a[1] is ext_polys[i] for a, i in zip(in_arena, dyn)):
+            coeff = self._arena[:self._arena_used]                    # the proof's polynomials, already one contiguous block
+            slot = {i: a[0] for a, i in zip(in_arena, dyn)}
+        else:                                                          # (cols, n, 4) staging copy for the batched coset NTT
+            coeff = t.stack([ext_polys[i] for i in dyn])
+            slot = {i: s_ for s_, i in enumerate(dyn)}
+        ncols = coeff.shape[0]
+        if self._coset_buf is None or self._coset_buf.shape[0] < ncols:      # kept across proofs: a fresh 15.5 GiB block per proof
+            self._coset_buf = None                                           # costs the caching allocator 0.1 s every other proof
+            self._coset_buf = t.empty((ncols, n, 4), dtype=t.int64, device="cuda")
+        buf = self._coset_buf[:ncols]
         vals = t.empty((ncos, n, 4), dtype=t.int64, device="cuda")
-        slot = {i: s_ for s_, i in enumerate(dyn)}
         self._sync()
         for cs in range(ncos):
-            self.ctx.check(self.lib.trp_dev_coeff_to_coset(self.dom.handle, coeff.data_ptr(), buf.data_ptr(), len(dyn), cs))
+            self.ctx.check(self.lib.trp_dev_coeff_to_coset(self.dom.handle, coeff.data_ptr(), buf.data_ptr(), ncols, cs))
             ptrs = [buf[slot[i]].data_ptr() if i in slot else self._static[id(c)][cs].data_ptr() for i, c in enumerate(ext_polys)]
             self.ev.evaluate_device(prog, self.dom, ptrs, vals[cs].data_ptr(), coset=cs | Q_CONTIGUOUS)
         h = t.empty((ncos, n, 4), dtype=t.int64, device="cuda")
@@ -994,6 +1055,28 @@ class GpuBackend:
         self.ctx.check(self.lib.trp_dev_eval_polynomials(self.ctx.handle, 0, v.data_ptr(), self.n, self.n, 1, self._m(x), out.data_ptr()))
         self._sync()
         return self._ints(out.cpu().numpy().view(self.np.uint64))[0]
+
+    def eval_polynomials_at(self, vs, x):
+        """the values of many separately allocated polynomials at ONE point: one library call (trp_dev_eval_polynomials_at)"""
+        if not vs:
+            return []
+        out = self._new(len(vs))
+        tab = (self.ct.c_void_p * len(vs))(*[v.data_ptr() for v in vs])
+        self._sync()
+        self.ctx.check(self.lib.trp_dev_eval_polynomials_at(self.ctx.handle, 0, tab, self.n, len(vs), self._m(x), out.data_ptr()))
+        self._sync()
+        return self._ints(out.cpu().numpy().view(self.np.uint64))
+
+    def linear_combination(self, vs, scalars):
+        """sum_j scalars[j] * vs[j] in one pass (trp_dev_linear_combination)"""
+        out = self._new()
+        tab = (self.ct.c_void_p * len(vs))(*[v.data_ptr() for v in vs])
+        sc = self._limbs(scalars)
+        self._sync()
+        from ._lib import ptr
+        self.ctx.check(self.lib.trp_dev_linear_combination(self.ctx.handle, 0, tab, ptr(sc), self.n, len(vs), out.data_ptr()))
+        self._sync()
+        return out
 
     def kate_division(self, v, b):
         q = self._new(zero=True)
