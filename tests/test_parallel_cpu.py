@@ -149,3 +149,53 @@ def test_coset_split_world2_gloo(n_cols):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(r[1] and r[2] for r in res), res
+
+
+def _proof_worker(rank, world, port, q):
+    """plonk.create_proof with the commitments sharded over two gloo ranks (sharded_backend.ShardedCommits over the oracle's
+    PythonBackend): every rank must produce the bytes of the unsharded proof"""
+    import random
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.load_package()
+    from tiny_ram_halo2_b200 import plonk as PL, sharded_backend as SB
+    from util import pm
+    import plonk_model as VM
+    import plonk_circuits
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        C = pm.Vesta
+
+        class ShardedPython(SB.ShardedCommits, VM.PythonBackend):
+            pass
+
+        proofs = []
+        for sharded in (True, False):
+            cs, fixed, copies, adv, inst = plonk_circuits.standard(PL, with_lookup=True, wide_lookup=True)
+            be = ShardedPython(C, 4, cs.degree())
+            be.dist = dist if sharded else None
+            pk = PL.keygen(be, cs, fixed, copies)
+            rnd = random.Random(3)
+            proofs.append((PL.create_proof(be, pk, inst, adv, lambda: rnd.randrange(C.scalar.p), PL.Blake2bWrite(C.base.p, C.scalar.p)),
+                           pk.vk.fixed_commitments, pk.vk.permutation_commitments))
+        ok = proofs[0] == proofs[1] and VM.verify_proof(C, be.params, pk.vk, inst, proofs[0][0])
+        q.put((rank, bool(ok), proofs[0][0]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_commitments_give_the_same_proof_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_proof_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=400) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), [r[:2] for r in res]
+    assert res[0][2] == res[1][2]

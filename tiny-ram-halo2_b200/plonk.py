@@ -520,7 +520,8 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     inst_values = [column(c, "InstanceTooLarge: instance") for c in instances]
     for cm in B.commit_lagrange_many(inst_values, [1] * len(inst_values)):
         transcript.common_point(cm)
-    inst_polys = [B.lagrange_to_coeff(v) for v in inst_values]
+    to_coeff_many = getattr(B, "lagrange_to_coeff_many", lambda vs: [B.lagrange_to_coeff(v) for v in vs])
+    inst_polys = to_coeff_many(inst_values)
     inst_cosets = [B.coeff_to_extended(c) for c in inst_polys]
     tick("instance")
 
@@ -531,7 +532,7 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     adv_blinds = [rand() for _ in adv_values]
     for cm in B.commit_lagrange_many(adv_values, adv_blinds):
         transcript.write_point(cm)
-    adv_polys = [B.lagrange_to_coeff(v) for v in adv_values]
+    adv_polys = to_coeff_many(adv_values)
     adv_cosets = [B.coeff_to_extended(c) for c in adv_polys]
     values_of = {ADVICE: adv_values, FIXED: pk.fixed_values, INSTANCE: inst_values}
     tick("advice")
@@ -546,9 +547,10 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
         B.set_rows(pt, usable, [rand() for _ in range(bf + 1)])
         L = {"ci": ci, "ct": ct, "pi": pi, "pt": pt}
         for name in ("pi", "pt"):
-            L[name + "_poly"] = B.lagrange_to_coeff(L[name])
             L[name + "_blind"] = rand()
         lookups.append(L)
+    for L, pi_poly, pt_poly in zip(lookups, *[to_coeff_many([L[nm] for L in lookups]) for nm in ("pi", "pt")]):
+        L["pi_poly"], L["pt_poly"] = pi_poly, pt_poly
     # the commitments do not feed the RNG, so they are computed as one batch and written in halo2's order
     for cm in B.commit_lagrange_many([L[nm] for L in lookups for nm in ("pi", "pt")], [L[nm + "_blind"] for L in lookups for nm in ("pi", "pt")]):
         transcript.write_point(cm)
@@ -567,16 +569,16 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
         B.permutation_commit([values_of[kk][c] for kk, c in cs.permutation], pk.sigma_values, beta, gamma, chunk_len, bf, rand, after_chunk)
     for cm in B.commit_lagrange_many([S["z"] for S in perm_sets], [S["blind"] for S in perm_sets]):
         transcript.write_point(cm)
-    for S in perm_sets:
-        S["poly"] = B.lagrange_to_coeff(S["z"])
-        S["coset"] = B.coeff_to_extended(S["poly"])
+    for S, poly in zip(perm_sets, to_coeff_many([S["z"] for S in perm_sets])):
+        S["poly"] = poly
+        S["coset"] = B.coeff_to_extended(poly)
     for L in lookups:
         L["z"] = B.lookup_product(L["ci"], L["ct"], L["pi"], L["pt"], beta, gamma, bf, rand)
         L["z_blind"] = rand()
     for cm in B.commit_lagrange_many([L["z"] for L in lookups], [L["z_blind"] for L in lookups]):
         transcript.write_point(cm)
-    for L in lookups:
-        L["z_poly"] = B.lagrange_to_coeff(L["z"])
+    for L, poly in zip(lookups, to_coeff_many([L["z"] for L in lookups])):
+        L["z_poly"] = poly
     tick("grand_products")
 
     # ---- vanishing argument: random polynomial ------------------------------------------------------------------------------------------
@@ -997,6 +999,24 @@ class GpuBackend:
         self._sync()
         return c
 
+    def lagrange_to_coeff_many(self, vs):
+        """the same for a batch: inside a proof the results are consecutive arena slots, transformed by ONE batched iNTT"""
+        k = len(vs)
+        if not (self._arena_on and k and self._arena_used + k <= self._arena.shape[0]):
+            return [self.lagrange_to_coeff(v) for v in vs]
+        first = self._arena_used
+        out = []
+        for v in vs:
+            c = self._arena[self._arena_used]
+            self._arena_slot[id(c)] = (self._arena_used, c)
+            self._arena_used += 1
+            c.copy_(v)
+            out.append(c)
+        self._sync()
+        self.ctx.check(self.lib.trp_dev_lagrange_to_coeff(self.dom.handle, self._arena[first].data_ptr(), k))
+        self._sync()
+        return out
+
     def coeff_to_extended(self, c):
         return c                          # lazy: the quotient evaluates cosets straight from coefficient form
 
@@ -1040,14 +1060,23 @@ class GpuBackend:
         buf = self._coset_buf[:ncols]
         vals = t.empty((ncos, n, 4), dtype=t.int64, device="cuda")
         self._sync()
-        for cs in range(ncos):
+        mine = self._my_cosets(ncos)
+        for cs in mine:
             self.ctx.check(self.lib.trp_dev_coeff_to_coset(self.dom.handle, coeff.data_ptr(), buf.data_ptr(), ncols, cs))
             ptrs = [buf[slot[i]].data_ptr() if i in slot else self._static[id(c)][cs].data_ptr() for i, c in enumerate(ext_polys)]
             self.ev.evaluate_device(prog, self.dom, ptrs, vals[cs].data_ptr(), coset=cs | Q_CONTIGUOUS)
+        vals = self._exchange_cosets(vals, mine)
         h = t.empty((ncos, n, 4), dtype=t.int64, device="cuda")
         self.ctx.check(self.lib.trp_dev_cosets_to_coeff(self.dom.handle, vals.data_ptr(), ncos, h.data_ptr(), 1))
         self._sync()
         return [h[i] for i in range(ncos)]
+
+    # hooks of the multi-GPU backend (sharded_backend.py): which cosets this process evaluates, and the exchange of the results
+    def _my_cosets(self, ncos):
+        return list(range(ncos))
+
+    def _exchange_cosets(self, vals, mine):
+        return vals
 
     def eval_polynomial(self, v, x):
         out = self._new(1)
