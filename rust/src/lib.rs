@@ -42,6 +42,9 @@ extern "C" {
     pub fn trp_permute_expression_pair(ctx: *mut trp_ctx, input: *const u64, table: *const u64, rows: usize, perm_input: *mut u64,
                                        perm_table: *mut u64, all_found: *mut c_int) -> c_int;
     pub fn trp_eval_polynomial(ctx: *mut trp_ctx, which_field: c_int, coeffs: *const u64, n: usize, x: *const u64, out: *mut u64) -> c_int;
+    // device-resident openings (include/tr_prover.h): m separately allocated polynomials at one point / one linear combination of them
+    pub fn trp_dev_eval_polynomials_at(ctx: *mut trp_ctx, which_field: c_int, d_poly_ptrs: *const *const u64, n: usize, m: usize, x: *const u64, d_out: *mut u64) -> c_int;
+    pub fn trp_dev_linear_combination(ctx: *mut trp_ctx, which_field: c_int, d_poly_ptrs: *const *const u64, scalars: *const u64, n: usize, m: usize, d_out: *mut u64) -> c_int;
     pub fn trp_compute_inner_product(ctx: *mut trp_ctx, which_field: c_int, a: *const u64, b: *const u64, n: usize, out: *mut u64) -> c_int;
     pub fn trp_kate_division(ctx: *mut trp_ctx, which_field: c_int, coeffs: *const u64, n: usize, b: *const u64, q: *mut u64) -> c_int;
     /// Params::new(k): g, g_lagrange (2^k affine points each, 8 x u64), w, u
