@@ -199,3 +199,47 @@ def test_sharded_commitments_give_the_same_proof_world2_gloo():
         assert p.exitcode == 0
     assert all(r[1] for r in res), [r[:2] for r in res]
     assert res[0][2] == res[1][2]
+
+
+def _coset_exchange_worker(rank, world, port, ncos, q):
+    """sharded_backend.ShardedGpuBackend's coset partition (which cosets a rank evaluates, how the results are exchanged), run
+    over gloo on CPU tensors with the device-specific parts stubbed out"""
+    import types
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.load_package()
+    from tiny_ram_halo2_b200 import sharded_backend as SB
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fake = types.SimpleNamespace(dist=dist, torch=torch, _sync=lambda: None)
+        mine = SB.ShardedGpuBackend._my_cosets(fake, ncos)
+        n = 16
+        want = torch.arange(ncos * n * 4, dtype=torch.int64).reshape(ncos, n, 4)
+        vals = torch.zeros_like(want)
+        for cs in mine:
+            vals[cs] = want[cs]                                 # this rank "evaluated" only its own cosets
+        got = SB.ShardedGpuBackend._exchange_cosets(fake, vals, mine)
+        every = [None] * world
+        dist.all_gather_object(every, mine)
+        covered = sorted(c for m in every for c in m)
+        q.put((rank, bool(torch.equal(got, want)) and got.is_contiguous(), covered == list(range(ncos))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,ncos", [(2, 5), (3, 5), (2, 1)])
+def test_coset_partition_and_exchange_gloo(world, ncos):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_coset_exchange_worker, args=(r, world, port, ncos, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] and r[2] for r in res), res
