@@ -230,3 +230,27 @@ def test_word_size_32_short_trace(mods):
     n = 1 << 17
     dense = [f.dense(n) for f in fixed]
     assert MP.check(PL, circ.cs, n, TR.PL_FIELD_MODULUS, dense, adv, inst, copies, circ.gate_names) == []
+
+
+def test_random_programs_mock_prover(mods):
+    """beyond the reference's three-instruction programs: random straight-line programs over the instruction set its witness
+    generation covers (immediate and register operands, all eight registers), W = 8, up to 14 steps"""
+    PL, TR, T = mods
+    rnd = random.Random(2024)
+    three = ("And", "Xor", "Or", "Add", "Sub", "Mull", "UMulh", "SMulh", "UDiv", "UMod")
+    two = ("Cmpe", "Cmpa", "Cmpae", "Cmpg", "Cmpge", "Mov", "CMov")
+    for trial in range(60):
+        prog = [T.Mov(rnd.randrange(8), T.Imm(rnd.randrange(256))) for _ in range(2)]
+        for _ in range(rnd.randrange(1, 11)):
+            operand = T.Imm(rnd.randrange(256)) if rnd.random() < 0.6 else T.Reg(rnd.randrange(8))
+            kind = rnd.random()
+            if kind < 0.55:
+                prog.append(getattr(T, rnd.choice(three))(rnd.randrange(8), rnd.randrange(8), operand))
+            elif kind < 0.9:
+                prog.append(getattr(T, rnd.choice(two))(rnd.randrange(8), operand))
+            else:
+                prog.append(getattr(T, rnd.choice(("Shl", "Shr")))(rnd.randrange(8), rnd.randrange(8), T.Imm(rnd.randrange(8))))
+        prog.append(T.Answer(T.Imm(1)))
+        tr = T.eval_program(prog, T.Mem(8, [1]))
+        fails = _check(mods, tr)
+        assert fails == [], (trial, [(i.name, i.ri, i.rj, i.a) for i in prog], fails[:3])
