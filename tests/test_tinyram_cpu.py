@@ -254,3 +254,19 @@ def test_random_programs_mock_prover(mods):
         tr = T.eval_program(prog, T.Mem(8, [1]))
         fails = _check(mods, tr)
         assert fails == [], (trial, [(i.name, i.ri, i.rj, i.a) for i in prog], fails[:3])
+
+
+def test_exe_circuit_mock_prover(mods):
+    """the reference's second circuit, ExeCircuit (tables/exe.rs:1082-1116): the execution table without the program table; its
+    tests run the same programs with no instance (exe.rs:1434-1570)"""
+    PL, TR, T = mods
+    c = TR.TinyRamCircuit(PL, 8, with_prog=False)
+    assert (c.cs.num_advice, c.cs.num_instance, c.cs.num_fixed) == (263 - 94, 0, 24 - 3)
+    assert len(c.cs.gates) == 138 and len(c.cs.lookups) == 30 and len(c.cs.permutation) == 0
+    rnd = random.Random(5)
+    traces = [TP.answer_only(T, 8), TP.load_and_answer(T, 8, 1, 2)]
+    traces += [TP.mov_named(T, 8, name, *_operands(name, rnd)) for name in TP.THREE_OPERAND + TP.TWO_OPERAND]
+    for tr in traces:
+        circ, fixed, copies, adv, inst = TR.build(PL, tr, 6, with_prog=False)
+        assert inst == [] and copies == []
+        assert MP.check(PL, circ.cs, 64, TR.PL_FIELD_MODULUS, fixed, adv, inst, copies, circ.gate_names) == []

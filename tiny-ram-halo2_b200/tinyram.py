@@ -196,10 +196,12 @@ def program_instance(prog: List[T.Instruction], word_bits: int, reg_count: int =
 class TinyRamCircuit:
     """configure() at construction; synthesize(trace) -> (fixed, copies, advice); the ConstraintSystem is .cs"""
 
-    def __init__(self, PL, word_bits: int, reg_count: int = 8):
+    def __init__(self, PL, word_bits: int, reg_count: int = 8, with_prog: bool = True):
+        """with_prog=False is the reference's ExeCircuit (tables/exe.rs:1082-1116): the execution table alone, no program table,
+        no instance columns, no dynamic lookup"""
         if word_bits % 8 or not 8 <= word_bits <= 32:
             raise ValueError("WORD_BITS must be 8, 16, 24 or 32")
-        self.PL, self.W, self.R = PL, word_bits, reg_count
+        self.PL, self.W, self.R, self.with_prog = PL, word_bits, reg_count, with_prog
         self.table_len = 1 << (word_bits // 2)                   # ExeConfig::TABLE_LEN = ProgConfig::TABLE_LEN (exe.rs:106, prog.rs:137)
         self.cs = PL.ConstraintSystem()
         self.gate_names: List[str] = []
@@ -277,13 +279,14 @@ class TinyRamCircuit:
         adv, fix = self._adv, self._fix
 
         # ProgConfig::configure (prog.rs:139-161)
-        self.s_prog = cs.fixed_column()                                        # meta.selector(): never queried by a gate
-        self.prog_input = ProgramLine(cs.instance_column, R)
-        self.prog_table = ProgramLine(cs.advice_column, R)
-        self.prog_pc = cs.fixed_column()
-        self.dyn_tag = cs.fixed_column()                                       # create_dynamic_table (fork): the table's tag column
-        for c in self.prog_input.to_vec(): cs.enable_equality(I, c)
-        for c in self.prog_table.to_vec(): cs.enable_equality(A, c)
+        if self.with_prog:
+            self.s_prog = cs.fixed_column()                                    # meta.selector(): never queried by a gate
+            self.prog_input = ProgramLine(cs.instance_column, R)
+            self.prog_table = ProgramLine(cs.advice_column, R)
+            self.prog_pc = cs.fixed_column()
+            self.dyn_tag = cs.fixed_column()                                   # create_dynamic_table (fork): the table's tag column
+            for c in self.prog_input.to_vec(): cs.enable_equality(I, c)
+            for c in self.prog_table.to_vec(): cs.enable_equality(A, c)
 
         # ExeChip::configure_instructions (exe.rs:535-767)
         self.time = cs.fixed_column()
@@ -474,6 +477,8 @@ class TinyRamCircuit:
         immediate_gate(sd["a"], d_w, "d"); simple_gate("zero", sd["zero"], d_w, "d", lambda _, t: t)
         simple_gate("one", sd["one"], d_w, "d", lambda _, t: C(1) - t)
 
+        if not self.with_prog:
+            return
         # prog_config.lookup (circuits/mod.rs:52-57 -> prog.rs:163-193): the fork's lookup_dynamic
         s_tr = adv(self.s_trace)
         pc_ = adv(self.pc)
@@ -500,7 +505,7 @@ class TinyRamCircuit:
             raise ValueError("NotEnoughRowsAvailable")
         fixed = [[] for _ in range(cs.num_fixed)]                # the assigned prefix of each column; (prefix, fill) pairs are returned
         fill = [0] * cs.num_fixed
-        for col in (self.s_prog, self.dyn_tag, self.prog_pc) + ((self.first_line, self.s_table, self.time) if trace is not None else ()):
+        for col in ((self.s_prog, self.dyn_tag, self.prog_pc) if self.with_prog else ()) + ((self.first_line, self.s_table, self.time) if trace is not None else ()):
             fixed[col] = [0] * TL
         advice: List[Dict[int, int]] = [dict() for _ in range(cs.num_advice)]
         copies = []
@@ -518,12 +523,13 @@ class TinyRamCircuit:
                **{self.t_out[nm]: [int(nm in r[1]) for r in rows] for nm in OUT_NAMES}})
 
         # ProgConfig::assign_prog (prog.rs:195-233): the program table is a copy of the instance columns
-        for ic, tc in zip(self.prog_input.to_vec(), self.prog_table.to_vec()):
-            copies.append(PL.CopyBlock((I, ic, 0), (A, tc, 0), TL))
-        for off in range(TL):
-            fixed[self.s_prog][off] = 1
-            fixed[self.dyn_tag][off] = 1
-            fixed[self.prog_pc][off] = off
+        if self.with_prog:
+            for ic, tc in zip(self.prog_input.to_vec(), self.prog_table.to_vec()):
+                copies.append(PL.CopyBlock((I, ic, 0), (A, tc, 0), TL))
+            for off in range(TL):
+                fixed[self.s_prog][off] = 1
+                fixed[self.dyn_tag][off] = 1
+                fixed[self.prog_pc][off] = off
 
         if trace is not None:
             if trace.word_bits != W or trace.reg_count != R:
@@ -747,19 +753,22 @@ def columns_to_lists(advice: List[Dict[int, int]]) -> List[List[int]]:
     return out
 
 
-def build(PL, trace: T.Trace, k: int, keygen_from_empty_circuit: bool = False, dense: bool = True, **kw):
+def build(PL, trace: T.Trace, k: int, keygen_from_empty_circuit: bool = False, dense: bool = True, with_prog: bool = True, **kw):
     """The whole of `TinyRamCircuit { trace }` + program_instance: returns (circuit, fixed, copies, advice, instances) ready for
     plonk.keygen / plonk.create_proof at n = 2^k (reference: mock_prover_test, circuits/mod.rs:364-375, uses k = 2 + W / 2).
+    with_prog=False builds the reference's ExeCircuit (no program table, `instances` is empty).
     keygen_from_empty_circuit: the fixed columns are those of `TinyRamCircuit::default()` (trace: None), which is what
     gen_proofs_and_verify hands keygen_vk / keygen_pk (test_utils.rs:22-25): the execution table's selectors are then all off.
     dense=False leaves the fixed columns as FixedColumn (prefix, fill) pairs (large n)."""
-    circ = TinyRamCircuit(PL, trace.word_bits, trace.reg_count)
+    circ = TinyRamCircuit(PL, trace.word_bits, trace.reg_count, with_prog=with_prog)
     n = 1 << k
     fixed, copies, advice = circ.synthesize(trace, n, **kw)
     if keygen_from_empty_circuit:
         fixed, _, _ = circ.synthesize(None, n)
-    instances = program_instance(trace.prog, trace.word_bits, trace.reg_count)
-    circ.assign_instance(advice, instances)
+    instances = []
+    if with_prog:
+        instances = program_instance(trace.prog, trace.word_bits, trace.reg_count)
+        circ.assign_instance(advice, instances)
     if dense:
         fixed = [f.dense(n) for f in fixed]
     return circ, fixed, copies, columns_to_lists(advice), instances
