@@ -361,6 +361,20 @@ def measure_extras(pkg, ctx, stream, peaks, peak_src, int_peak_tmacs):
                   "hbm_peak_source": peak_src, "algorithmic_tmacs": tmacs, "int_peak_tmacs": int_peak_tmacs,
                   "int_frac": tmacs / int_peak_tmacs, "bound": "int32-pipe (SURVEY.md 0.5: 255-bit NTT is ~14x above the HBM balance point)",
                   "model": "bytes = 2*N*32 per column; MACs = (N/2)*log2(N)*128 per column"}
+    try:     # the CPU path of the same transform beside it: the oracle's best_fft (C++ restatement) on all host threads, one column
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O
+        cores = O.hw_threads()
+        host = O.random_field_mont(O.FP, N, 30)
+        omega = np.ascontiguousarray(dom.omega, dtype=np.uint64)
+        O.fft(O.FP, host[: 1 << 12], 12, omega, threads=cores)             # warm the thread pool (result unused)
+        t0 = time.perf_counter()
+        O.fft(O.FP, host, logn, omega, threads=cores)
+        dt = time.perf_counter() - t0
+        out["ntt"]["cpu_baseline"] = {"ms_per_column": dt * 1e3, "algorithmic_gbs": N * 64 / dt / 1e9, "cores": cores, "kind": "port",
+                                      "sample": f"one 2^{logn} best_fft over Fp on {cores} threads, oracle/liboracle.so (C++ restatement of halo2_proofs 0.2.0)"}
+    except Exception as e:
+        out["ntt"]["cpu_baseline"] = {"error": repr(e)}
     del a
     dom.free()
     # ---- create_proof hot-path model at k = 20 (TinyRAM circuit shape, one proof, one GPU) -------------------------------
