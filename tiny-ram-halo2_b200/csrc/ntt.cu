@@ -203,7 +203,9 @@ __global__ void __launch_bounds__(NTT_THREADS, R >= 3 ? 2 : 3) ntt_pass_reg_kern
             const int el = b & ((1 << a) - 1);                 // bits of e below a
             const int e0 = ((b >> a) << (a + 1)) | el, e1 = e0 | (1 << a);
             Fe<PR> y = x[e1];
-            if (tt > 0) {
+            // first group of the first pass: lo = q0 = 0 and low = j_low = 0, so the exponent is el << (L - tt - 1) and the
+            // butterflies with el == 0 (known at compile time) multiply by omega^0 = 1: skipped, bit-identical
+            if (tt > 0 && !(el == 0 && gfirst && p.first)) {
               const unsigned jl = j_low | ((unsigned)el << q0);
               const unsigned expo = ((jl << lo) | low) << (L - tt - 1);
               y = fe_mul(y, fe_load_ro<PR>(p.tw + 2 * (size_t)expo));
