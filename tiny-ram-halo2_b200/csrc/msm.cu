@@ -171,6 +171,55 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accum_l1_kernel(const uint32_
   store_xyzz(partials + 8 * (size_t)t, acc);
 }
 
+// UNMEASURED EXPERIMENT (TRP_MSM_CALL=1): the same level-1 task with the field multiplication OUT OF LINE.
+// The inlined loop body of msm_accum_l1_kernel is 72 KB of SASS (10 + 7 multiplications of ~3.8 KB each), beyond the 32 KB
+// L1.5 instruction cache, and ncu shows stall_no_instruction at 1.26 cycles per issue; with calls the loop is ~18 KB.  The
+// price is ~36 register moves per call (the ABI passes both operands in registers, no stack).  Same arithmetic, same result.
+template <class PR> __device__ __noinline__ Fe<PR> fe_mul_call(Fe<PR> a, Fe<PR> b) { return fe_mul(a, b); }
+template <class PR> __device__ __noinline__ XYZZ<PR> xyzz_dbl_affine_call(Affine<PR> q) { return xyzz_dbl_affine(q); }
+
+template <class PR> __device__ __forceinline__ void xyzz_add_mixed_call(XYZZ<PR>& p, const Affine<PR>& q) {   // ec.cuh xyzz_add_mixed
+  if (affine_is_identity(q)) return;
+  if (xyzz_is_identity(p)) { p.x = q.x; p.y = q.y; p.zz = fe_one<PR>(); p.zzz = fe_one<PR>(); return; }
+  Fe<PR> u2 = fe_mul_call(q.x, p.zz);
+  Fe<PR> s2 = fe_mul_call(q.y, p.zzz);
+  Fe<PR> pp_ = fe_sub(u2, p.x);
+  Fe<PR> r = fe_sub(s2, p.y);
+  if (fe_is_zero(pp_)) {
+    if (fe_is_zero(r)) p = xyzz_dbl_affine_call(q);
+    else p = xyzz_identity<PR>();
+    return;
+  }
+  Fe<PR> pp = fe_mul_call(pp_, pp_);
+  Fe<PR> ppp = fe_mul_call(pp_, pp);
+  Fe<PR> qv = fe_mul_call(p.x, pp);
+  Fe<PR> x3 = fe_sub(fe_sub(fe_mul_call(r, r), ppp), fe_dbl(qv));
+  Fe<PR> y3 = fe_sub(fe_mul_call(r, fe_sub(qv, x3)), fe_mul_call(p.y, ppp));
+  p.x = x3; p.y = y3;
+  p.zz = fe_mul_call(p.zz, pp);
+  p.zzz = fe_mul_call(p.zzz, ppp);
+}
+
+template <class BPR>
+__global__ void __launch_bounds__(ACC_THREADS) msm_accum_l1_call_kernel(const uint32_t* entries, const uint32_t* in_off,
+                                                                      const uint32_t* task_off, unsigned nb,
+                                                                      const uint4* bases, uint4* partials) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= __ldg(task_off + nb)) return;
+  unsigned b = find_segment(task_off, nb, t);
+  uint32_t j = t - __ldg(task_off + b);
+  uint32_t start = __ldg(in_off + b) + j * L1;
+  uint32_t end = min(start + L1, __ldg(in_off + b + 1));
+  XYZZ<BPR> acc = xyzz_identity<BPR>();
+  for (uint32_t e = start; e < end; ++e) {
+    uint32_t ent = __ldg(entries + e);
+    Affine<BPR> p = load_affine<BPR>(bases, ent & 0x7fffffffu);
+    if (ent >> 31) p.y = fe_neg(p.y);
+    xyzz_add_mixed_call(acc, p);
+  }
+  store_xyzz(partials + 8 * (size_t)t, acc);
+}
+
 // levels >= 2: partial sums of the previous level, full adds
 template <class BPR>
 __global__ void __launch_bounds__(ACC_THREADS) msm_accum_ln_kernel(const uint4* in, const uint32_t* in_off,
@@ -435,8 +484,13 @@ int msm_chunk(trp_ctx* ctx, const trp_bases_impl* bs, const uint4* d_scalars, si
   {
     ProfScope ps(ctx, PROF_MSM_ACCUM_L1);
     unsigned gridl1 = (unsigned)((level_tasks[0] + ACC_THREADS - 1) / ACC_THREADS);
-    msm_accum_l1_kernel<BPR><<<gridl1, ACC_THREADS, 0, ctx->stream>>>(w.entries, w.offsets, w.task_off[0], (unsigned)NB,
-                                                                     (const uint4*)bs->pub.d_xy, w.part[0]);
+    static const bool out_of_line = [] { const char* e = getenv("TRP_MSM_CALL"); return e && atoi(e) == 1; }();
+    if (out_of_line)
+      msm_accum_l1_call_kernel<BPR><<<gridl1, ACC_THREADS, 0, ctx->stream>>>(w.entries, w.offsets, w.task_off[0], (unsigned)NB,
+                                                                            (const uint4*)bs->pub.d_xy, w.part[0]);
+    else
+      msm_accum_l1_kernel<BPR><<<gridl1, ACC_THREADS, 0, ctx->stream>>>(w.entries, w.offsets, w.task_off[0], (unsigned)NB,
+                                                                       (const uint4*)bs->pub.d_xy, w.part[0]);
     TRP_LAUNCHED(ctx);
   }
   int curp = 0;
