@@ -6,7 +6,9 @@ scalars, device resident (bench.py's step), 5 timed steps with CUDA events; the 
   python tests/gpu_msm_variants.py            # K = 20
   K=16 python tests/gpu_msm_variants.py
 
-Variants: TRP_MSM_CALL=1 (field multiplication out of line in the level-1 accumulation)."""
+Variants: TRP_MSM_CALL=1 (field multiplication out of line in the level-1 accumulation) and TRP_MSM_C=17..20 (wider windows:
+fewer bucket additions per scalar, more buckets to reduce) -- DESIGN.md section 9.  K=22 / K=24 are where wider windows
+should pay most (set B=4 / B=1 columns to stay inside the scratch budget)."""
 import hashlib
 import json
 import os
@@ -14,7 +16,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-VARIANTS = [("default", {}), ("fe_mul out of line", {"TRP_MSM_CALL": "1"})]
+VARIANTS = [("default", {}), ("fe_mul out of line", {"TRP_MSM_CALL": "1"})] + [(f"c = {c}", {"TRP_MSM_C": str(c)}) for c in (17, 18, 19, 20)]
 
 
 def child():
@@ -26,7 +28,7 @@ def child():
     pkg = ge.load_package()
     from tiny_ram_halo2_b200 import synthetic
     k = int(os.environ.get("K", "20"))
-    n, m = (1 << k) + 1, 8
+    n, m = (1 << k) + 1, int(os.environ.get("B", "8"))
     ctx = pkg.Context(0, pkg.VESTA)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)

@@ -414,7 +414,9 @@ unsigned choose_c(size_t n) {
   int c = (int)lg - 4;
   if (c < 4) c = 4;
   if (c > 16) c = 16;
-  if (const char* e = getenv("TRP_MSM_C")) { int v = atoi(e); if (v >= 2 && v <= 16) c = v; }
+  // the default stops at 16 (best of the widths measured at 8 x 2^20, round 1); 17..22 are accepted from the environment for
+  // the sweep of DESIGN.md section 9 (fewer windows per scalar against 2^(c-1) buckets per column to reduce)
+  if (const char* e = getenv("TRP_MSM_C")) { int v = atoi(e); if (v >= 2 && v <= 22) c = v; }
   return (unsigned)c;
 }
 
@@ -529,7 +531,7 @@ size_t msm_cols_per_chunk(const MsmGeom& g, size_t n, size_t m) {
     if (cap < 1) cap = 1;
     if (mc > cap) mc = cap;
   }
-  while (mc > 1 && carve(g, n, mc, nullptr).bytes > budget) mc = (mc + 1) / 2;
+  while (mc > 1 && (carve(g, n, mc, nullptr).bytes > budget || (size_t)g.nb * mc > (size_t)SCAN_BLOCK * SCAN_BLOCK)) mc = (mc + 1) / 2;
   return mc;
 }
 
