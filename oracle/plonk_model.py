@@ -110,6 +110,17 @@ class PythonBackend:
     def ipa_create_proof(self, rand, transcript, p_poly, p_blind, x_3):
         pm.ipa_create_proof(self.C, self.k, self.params["g"], self.params["w"], self.params["u"], rand, transcript, list(p_poly), p_blind, x_3)
 
+    # -- what the product's own verifier (tiny-ram-halo2_b200/verifier.py) asks of a backend beyond the prover's interface
+    def fixed_points(self): return self.params["g"][0], self.params["w"], self.params["u"]
+
+    def ipa_s_vector(self, us, init=1):
+        s = [init % self.p]
+        for u_j in reversed(us):
+            s = s + [v * u_j % self.p for v in s]
+        return s
+
+    def msm_points(self, scalars, points): return self.C.best_multiexp(list(scalars), list(points))
+
 
 # ---- verifier -------------------------------------------------------------------------------------------------------------------------
 class VerifyError(Exception):

@@ -15,7 +15,7 @@ from .arithmetic import best_multiexp, best_fft, best_fft_group, hash_to_curve, 
 from .domain import EvaluationDomain  # noqa: F401
 from .commitment import Params  # noqa: F401
 from .poly import Evaluator, new_evaluator  # noqa: F401
-from . import permutation, lookup, ipa, plonk  # noqa: F401
+from . import permutation, lookup, ipa, plonk, verifier  # noqa: F401
 
 __all__ = ["TrpError", "Context", "Bases", "best_multiexp", "best_fft", "best_fft_group", "hash_to_curve", "EvaluationDomain", "Params", "Evaluator", "new_evaluator",
            "PALLAS", "VESTA", "lib_path", "load_library", "build_library"]

@@ -973,6 +973,40 @@ class GpuBackend:
     def commit_lagrange_many(self, vecs, blinds): return self._commit_many(self.params.g_lagrange, vecs, blinds)
     def commit_many(self, vecs, blinds): return self._commit_many(self.params.g, vecs, blinds)
 
+    # -- the verifier's three extras (verifier.py): the fixed points, the challenges' s vector, a variable-base MSM
+    def fixed_points(self):
+        pt = lambda arr: tuple(self._ints(self.np.asarray(arr, dtype=self.np.uint64).reshape(-1, 8)[0].reshape(2, 4), self.q, self.Rqinv))
+        return pt(self.params.g_points), pt(self.params.w), pt(self.params.u)
+
+    def ipa_s_vector(self, us, init=1):
+        """commitment::compute_s on the device: s[0] = init, then one broadcast multiplication per round doubles the filled
+        prefix (s[len .. 2 len) = s[0 .. len) * u_j, last round first)"""
+        s = self._new(zero=True)
+        s[:1] = self._dev(self._limbs([init]))
+        filled = 1
+        for u_j in reversed(us):
+            d_u = self._dev(self._limbs([u_j]))
+            self._sync()
+            self.ctx.check(self.lib.trp_dev_field_op(self.ctx.handle, 0, 2 | 16, s[:filled].data_ptr(), d_u.data_ptr(),
+                                                     s[filled:2 * filled].data_ptr(), filled))
+            filled *= 2
+        self._sync()
+        if filled != self.n:
+            raise ValueError("one challenge per round: len(us) must equal k")
+        return s
+
+    def msm_points(self, scalars, points):
+        """sum_i scalars[i] * points[i] over caller-supplied affine points (trp_dev_msm_var: no table, one bucket set per window)"""
+        t = self.torch
+        if not scalars:
+            return None
+        d_pts = self._dev(self._limbs([c for pt in points for c in pt], self.q, self.Rq).reshape(len(points), 8))
+        d_sc = self._dev(self._limbs(scalars))
+        out = t.zeros(12, dtype=t.int64, device="cuda")
+        self._sync()
+        self.ctx.check(self.lib.trp_dev_msm_var(self.ctx.handle, d_pts.data_ptr(), d_sc.data_ptr(), len(scalars), 1, out.data_ptr()))
+        return self._point(out)
+
     # -- per-proof polynomial arena: create_proof announces how many polynomials it will bring to coefficient form; they are then
     #    laid out in ONE (count, n, 4) block, which the quotient's batched coset NTT reads in place (no 15.5 GiB staging copy at
     #    k = 20).  Polynomials made outside a proof (keygen) never come from the arena.
