@@ -69,3 +69,16 @@ def test_gen_proofs_and_verify_on_the_device():
         assert not bv.finalize(be, pk.vk)
     finally:
         be.close()
+    # and the same flow through the package's mirror of src/test_utils.rs (its own backend, keys and OsRng-style blinding)
+    from tiny_ram_halo2_b200 import test_utils as TU
+    made = []
+    def backend_of(k_, degree):
+        made.append(PL.GpuBackend(ctx, k_, degree))
+        return made[-1]
+    try:
+        out = TU.gen_proofs_and_verify(backend_of, W, traces)
+        assert len(out) == 2 and made[0].k == 2 + W // 2
+        TU.gen_proofs_and_verify_should_fail(backend_of, W, traces[0], TR.program_instance([T.Answer(T.Imm(0))], W), k=6)
+    finally:
+        for b in made:
+            b.close()

@@ -217,6 +217,14 @@ def test_real_proof_on_the_cpu_backend_verifies(mods):
     assert VM.verify_proof(C, be.params, pk.vk, inst, proof), VM.verify_proof.last_error
     other = TR.program_instance([T.Answer(T.Imm(0))], 8)
     assert not VM.verify_proof(C, be.params, pk.vk, other, proof)
+    # the package's own verifier (verifier.py) on the same proof: BatchVerifier, then SingleVerifier (test_utils.rs:56-70)
+    from tiny_ram_halo2_b200 import verifier as V
+    bv = V.BatchVerifier()
+    bv.add_proof(inst, proof)
+    assert bv.finalize(be, pk.vk)
+    assert V.verify_proof(be, pk.vk, V.SingleVerifier(be), inst, V.Blake2bRead(proof, be.q, be.p)) is None
+    with pytest.raises(V.VerifyError):
+        V.verify_proof(be, pk.vk, V.SingleVerifier(be), other, V.Blake2bRead(proof, be.q, be.p))
     with pytest.raises(ValueError):
         PL.create_proof(be, pk, inst, adv, lambda: 1, PL.Blake2bWrite(C.base.p, C.scalar.p), debug=True)
 

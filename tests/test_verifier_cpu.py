@@ -176,19 +176,23 @@ def test_blake2b_read(mods):
         assert V._sqrt(0, F.p) == 0
 
 
-def test_tinyram_gen_proofs_and_verify(mods):
-    """gen_proofs_and_verify::<8, TinyRamCircuit> on `Answer 1` (k = 6) and gen_proofs_and_verify_should_fail's shape: the proof
-    checked against another program's public input is rejected"""
+def test_reference_test_utils_flow(mods):
+    """test_utils.py = src/test_utils.rs: `two_programs` of the execution table (exe.rs:1443-1467: ExeCircuit, no public input)
+    through gen_proofs_and_verify, and gen_proofs_and_verify_should_fail (the TinyRamCircuit variant of the same flow, with a
+    program instance, is tests/test_tinyram_cpu.py::test_real_proof_on_the_cpu_backend_verifies and, on the device, tests/test_gpu_zz_verifier.py)"""
     PL, V, TR, T = mods
+    from tiny_ram_halo2_b200 import test_utils as TU
     C = pm.Vesta
-    circ, fixed, copies, adv, inst = TR.build(PL, TP.answer_only(T, 8), 6)
-    be = VM.PythonBackend(C, 6, circ.cs.degree())
-    pk = PL.keygen(be, circ.cs, fixed, copies)
-    rnd = random.Random(1)
-    proof = PL.create_proof(be, pk, inst, adv, lambda: rnd.randrange(C.scalar.p), PL.Blake2bWrite(C.base.p, C.scalar.p))
-    bv = V.BatchVerifier()
-    bv.add_proof(inst, proof)
-    assert bv.finalize(be, pk.vk)
-    assert _accepts(V, be, pk.vk, inst, proof) and VM.verify_proof(C, be.params, pk.vk, inst, proof)
-    other = TR.program_instance([T.Answer(T.Imm(0))], 8)
-    assert not _accepts(V, be, pk.vk, other, proof) and not VM.verify_proof(C, be.params, pk.vk, other, proof)
+    made = []
+    def backend_of(k, degree):
+        made.append(VM.PythonBackend(C, k, degree))
+        return made[-1]
+    rnd = random.Random(11)
+    rand = lambda: rnd.randrange(C.scalar.p)
+    proofs = TU.gen_proofs_and_verify(backend_of, 8, [TP.answer_only(T, 8), TP.load_and_answer(T, 8, 1, 2)], with_prog=False, rand=rand)
+    assert len(proofs) == 2 and made[0].k == 6 and len(proofs[0]) == len(proofs[1])
+    # a proof checked against a public input the circuit does not have is rejected; the same proof against its own is not
+    tr = TP.answer_only(T, 8)
+    TU.gen_proofs_and_verify_should_fail(backend_of, 8, tr, [[1]], with_prog=False, rand=rand, k=6)
+    with pytest.raises(AssertionError, match="Erroneously verified proof"):
+        TU.gen_proofs_and_verify_should_fail(backend_of, 8, tr, [], with_prog=False, rand=rand, k=6)
