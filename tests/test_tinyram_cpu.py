@@ -278,3 +278,32 @@ def test_exe_circuit_mock_prover(mods):
         circ, fixed, copies, adv, inst = TR.build(PL, tr, 6, with_prog=False)
         assert inst == [] and copies == []
         assert MP.check(PL, circ.cs, 64, TR.PL_FIELD_MODULUS, fixed, adv, inst, copies, circ.gate_names) == []
+
+
+def test_witness_digests(mods):
+    """The witness (fixed columns, copy constraints, advice, instance) of 33 circuit / trace / option combinations, including
+    bench.py's 65 521-step trace at word size 32, against the SHA-256 digests frozen from the row-by-row implementation that
+    followed ExeChip::assign_trace line by line (tests/golden/make_witness_digests.py): the column-wise synthesis must not
+    move a bit."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_witness_digests", os.path.join(here, "golden", "make_witness_digests.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(here, "golden", "witness_digests.json")) as f:
+        want = json.load(f)
+    got = mod.all_digests()
+    assert sorted(got) == sorted(want)
+    assert {k: v for k, v in got.items() if v != want[k]} == {}
+
+
+def test_batch_inverse(mods):
+    TR = mods[1]
+    p = TR.PL_FIELD_MODULUS
+    rnd = random.Random(4)
+    vals = [rnd.randrange(p) for _ in range(50)] + [0, 1, p - 1, 0, 0, 7]
+    rnd.shuffle(vals)
+    assert TR._batch_inverse(vals, p) == [pow(v, -1, p) if v else 0 for v in vals]
+    assert TR._batch_inverse([], p) == [] and TR._batch_inverse([0, 0], p) == [0, 0]

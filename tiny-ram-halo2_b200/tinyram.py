@@ -106,12 +106,13 @@ class ProgramLine:
     def to_vec(self) -> List[int]:
         """ProgramLine::to_vec = the order of ProgramLine::map (prog.rs:106-128); ChangedSelectors::map visits pc, flag, regs
         (changed.rs:73-81), everything else in allocation order"""
-        out = [self.opcode, self.immediate]
-        for part in (self.a, self.b, self.c, self.d):
-            for v in part.values():
-                out.extend(v if isinstance(v, list) else [v])
-        out += [self.ch["pc"], self.ch["flag"]] + self.ch["regs"]
-        return out
+        if getattr(self, "_vec", None) is None:
+            out = [self.opcode, self.immediate]
+            for part in (self.a, self.b, self.c, self.d):
+                for v in part.values():
+                    out.extend(v if isinstance(v, list) else [v])
+            self._vec = out + [self.ch["pc"], self.ch["flag"]] + self.ch["regs"]
+        return list(self._vec)
 
     def row_values(self, ins: T.Instruction) -> Dict[int, int]:
         """ProgramLine::assign_cells for one line (prog.rs:81-104): {column: value}"""
@@ -176,6 +177,26 @@ def decompose(word: int) -> Tuple[int, int]:
     return word & _EVEN_MASK, ((word & _ODD_MASK) & ((1 << 128) - 1)) >> 1
 
 
+_NO_GADGET = frozenset(("Add", "Sub", "Mull", "UMulh", "Cmpa", "Cmpae", "CMov", "Jmp", "CJmp", "CnJmp", "LoadW", "StoreW", "Answer", "Not"))
+
+
+def _batch_inverse(values: List[int], p: int) -> List[int]:
+    """the inverses modulo p of `values` with ONE modular inversion (prefix products); zeros stay zero"""
+    prefix, run = [], 1
+    for v in values:
+        prefix.append(run)
+        if v:
+            run = run * v % p
+    inv = pow(run, -1, p)
+    out = [0] * len(values)
+    for i in range(len(values) - 1, -1, -1):
+        v = values[i]
+        if v:
+            out[i] = inv * prefix[i] % p
+            inv = inv * v % p
+    return out
+
+
 def program_instance(prog: List[T.Instruction], word_bits: int, reg_count: int = 8) -> List[List[int]]:
     """tables/prog.rs:38-60: the 94 instance columns; the program is padded to TABLE_LEN lines with its terminal Answer"""
     table_len = 1 << (word_bits // 2)
@@ -187,9 +208,18 @@ def program_instance(prog: List[T.Instruction], word_bits: int, reg_count: int =
     counter = iter(range(1 << 30))
     line = ProgramLine(lambda: next(counter), reg_count)
     cols = [[0] * table_len for _ in range(len(line.to_vec()))]
-    for off, ins in enumerate(padded):
-        for c, v in line.row_values(ins).items():
-            cols[c][off] = v
+    rows_of = {}
+    for off, ins in enumerate(prog):
+        if id(ins) not in rows_of:
+            rows_of[id(ins)] = line.row_values(ins)
+        for c, v in rows_of[id(ins)].items():
+            if v:
+                cols[c][off] = v
+    pad = len(padded) - len(prog)                       # the terminal Answer, repeated
+    if pad:
+        for c, v in line.row_values(prog[-1]).items():
+            if v:
+                cols[c][len(prog):] = [v] * pad
     return cols
 
 
@@ -507,7 +537,8 @@ class TinyRamCircuit:
         fill = [0] * cs.num_fixed
         for col in ((self.s_prog, self.dyn_tag, self.prog_pc) if self.with_prog else ()) + ((self.first_line, self.s_table, self.time) if trace is not None else ()):
             fixed[col] = [0] * TL
-        advice: List[Dict[int, int]] = [dict() for _ in range(cs.num_advice)]
+        rows_cap = max(TL, len(trace.exe) + 1 if trace is not None else 0)
+        advice: List[list] = [[None] * rows_cap for _ in range(cs.num_advice)]     # None = unassigned (columns_to_lists trims / zero-fills)
         copies = []
 
         # ExeChip::construct: the three lookup tables (exe.rs:519-533); unused rows repeat row 0 (SimpleTableLayouter)
@@ -526,10 +557,7 @@ class TinyRamCircuit:
         if self.with_prog:
             for ic, tc in zip(self.prog_input.to_vec(), self.prog_table.to_vec()):
                 copies.append(PL.CopyBlock((I, ic, 0), (A, tc, 0), TL))
-            for off in range(TL):
-                fixed[self.s_prog][off] = 1
-                fixed[self.dyn_tag][off] = 1
-                fixed[self.prog_pc][off] = off
+            fixed[self.s_prog], fixed[self.dyn_tag], fixed[self.prog_pc] = [1] * TL, [1] * TL, list(range(TL))
 
         if trace is not None:
             if trace.word_bits != W or trace.reg_count != R:
@@ -537,38 +565,66 @@ class TinyRamCircuit:
             exe = trace.exe
             if len(exe) > TL - 1:
                 raise ValueError("trace longer than TABLE_LEN - 1")
-            # ExeChip::assign_trace (exe.rs:792-1080)
+            # ExeChip::assign_trace (exe.rs:792-1080).  The reference assigns row by row; the same cells are written here
+            # column by column where a column's value depends on the instruction alone (one table row per distinct instruction,
+            # gathered with numpy), then the machine state and the temporary variables, then -- row by row, in the reference's
+            # order, last write wins -- what the instruction's gadget assigns, and `value` last.
+            import numpy as np
             fixed[self.first_line][0] = 1
-            for off in range(TL):
-                fixed[self.s_table][off] = 1
-                fixed[self.time][off] = off
-            for off in range(len(exe)):
-                advice[self.s_trace][off] = 1
-            mask = (1 << W) - 1
+            fixed[self.s_table], fixed[self.time] = [1] * TL, list(range(TL))
+            ne = len(exe)
+            advice[self.s_trace][:ne] = [1] * ne
+            # -- static part: intermediate fill, opcode, immediate, the selector vector of the line, the Out row
+            kinds, kind_of, templates = {}, [0] * ne, []
             for off, step in enumerate(exe):
                 ins = step.instruction
-                put = lambda col, v, _off=off: advice[col].__setitem__(_off, v % p)
-                for c in self.intermediate:
-                    put(c, U64_MAX)
-                put(self.pc, step.pc)
-                put(self.line.opcode, ins.opcode)
-                put(self.line.immediate, ins.immediate())
-                for rc, v in zip(self.reg, step.regs):
-                    put(rc, v)
-                put(self.flag, int(step.flag))
-                for c, v in self.line.row_values(ins).items():
-                    if c not in (self.line.opcode, self.line.immediate):
-                        put(c, v)
-                for nm in OUT_NAMES:
-                    put(self.out[nm], int(nm in OUT[ins.name]))
-                ta, tb, tc, td = self._temp_var_vals(exe, off, reg_operand_value, p)
-                for cfg, v in ((self.tv_a, ta), (self.tv_b, tb), (self.tv_c, tc), (self.tv_d, td)):      # temp_vars.rs:125-169
-                    put(cfg.word, v)
-                    self._assign_decompose(put, cfg, v)
-                flag_next = int(exe[off + 1].flag) if off + 1 < len(exe) else 0
-                s = (tc + flag_next) % p                                                                # flag2.rs:62-74
-                put(self.a_flag, pow(s, -1, p) if s else (a_flag_rand() if a_flag_rand else 0))
+                ki = kinds.get(id(ins))
+                if ki is None:
+                    ki = kinds[id(ins)] = len(templates)
+                    tm = {c: U64_MAX for c in self.intermediate}
+                    tm[self.line.opcode], tm[self.line.immediate] = ins.opcode, ins.immediate()
+                    for c, v in self.line.row_values(ins).items():
+                        if c not in (self.line.opcode, self.line.immediate):
+                            tm[c] = v
+                    for nm in OUT_NAMES:
+                        tm[self.out[nm]] = int(nm in OUT[ins.name])
+                    templates.append(tm)
+                kind_of[off] = ki
+            if ne:
+                static_cols = list(templates[0])
+                if any(list(tm) != static_cols for tm in templates):
+                    raise AssertionError("internal: the static columns do not depend on the instruction")
+                table_ = np.array([[tm[c] % p for c in static_cols] for tm in templates], dtype=np.uint64)     # all below 2^64
+                gathered = table_[np.array(kind_of, dtype=np.int64)]
+                for j_, c in enumerate(static_cols):
+                    advice[c][:ne] = gathered[:, j_].tolist()
+            # -- machine state
+            advice[self.pc][:ne] = [st.pc for st in exe]
+            for r_, rc in enumerate(self.reg):
+                advice[rc][:ne] = [st.regs[r_] % p for st in exe]
+            advice[self.flag][:ne] = [int(st.flag) for st in exe]
+            # -- temporary variables and their even / odd halves (temp_vars.rs:125-169), a_flag (flag2.rs:62-74)
+            sel_cache = {}
+            tvs = [self._temp_var_vals(exe, off, reg_operand_value, p, sel_cache) for off in range(ne)]
+            m128 = (1 << 128) - 1
+            for idx, cfg in enumerate((self.tv_a, self.tv_b, self.tv_c, self.tv_d)):
+                words = [t[idx] for t in tvs]
+                advice[cfg.word][:ne] = words
+                advice[cfg.even][:ne] = [w & _EVEN_MASK for w in words]
+                advice[cfg.odd][:ne] = [((w & _ODD_MASK) & m128) >> 1 for w in words]
+            sums = [(tvs[off][2] + (int(exe[off + 1].flag) if off + 1 < ne else 0)) % p for off in range(ne)]
+            advice[self.a_flag][:ne] = [x if x else (a_flag_rand() % p if a_flag_rand else 0) for x in _batch_inverse(sums, p)]
+            # -- the gadget of the row's instruction
+            cur = [0]
+            def put(col, v):
+                advice[col][cur[0]] = v % p
+            for off, step in enumerate(exe):
+                ins = step.instruction
                 nm = ins.name
+                if nm in _NO_GADGET:
+                    continue
+                cur[0] = off
+                ta, tb, tc, td = tvs[off]
                 if nm == "And":
                     self._assign_logic(put, ta, tb, lambda x, y: x & y)
                 elif nm in ("Xor", "Cmpe", "Mov"):
@@ -598,15 +654,16 @@ class TinyRamCircuit:
                     put(self.lsb_b, b64 & 1)                                                            # flag4.rs:67-91
                     put(self.b_flag, int(nm == "Shl"))
                     self._assign_signed(put, self.signed_b, b64)
-                put(self.value, step.v_addr or 0)
-            advice[self.s_trace][len(exe)] = 0
+            advice[self.value][:ne] = [(st.v_addr or 0) % p for st in exe]
+            advice[self.s_trace][ne] = 0
         return [FixedColumn(pre, f) for pre, f in zip(fixed, fill)], copies, advice
 
     def assign_instance(self, advice, instances):
         """assign_advice_from_instance: the program-table advice cells take the instance values (prog.rs:206-216)"""
+        TL = self.table_len
         for ic, tc in zip(self.prog_input.to_vec(), self.prog_table.to_vec()):
-            for off in range(self.table_len):
-                advice[tc][off] = instances[ic][off] if off < len(instances[ic]) else 0
+            col = list(instances[ic][:TL])
+            advice[tc][:TL] = col + [0] * (TL - len(col))
         return advice
 
     # ---- witness helpers -------------------------------------------------------------------------------------------------------------
@@ -647,17 +704,18 @@ class TinyRamCircuit:
         put(self.r_dec.word, r)
         self._assign_decompose(put, self.r_dec, r)
 
-    def _temp_var_vals(self, steps, i, reg_operand_value, p):
+    def _temp_var_vals(self, steps, i, reg_operand_value, p, sel_cache=None):
         """TempVarSelectorsRow::push_temp_var_vals (aux.rs:409-560): the values of the temporary variables a, b, c, d"""
         W = self.W
         step = steps[i]
         ins = step.instruction
         mask32 = 0xFFFFFFFF
-        sa, sb, sc, sd, *_ = selections(ins)
-        pc = lambda: step.pc
-        pc_n = lambda: steps[i + 1].pc
-        reg = lambda r: step.regs[r]
-        reg_n = lambda r: steps[i + 1].regs[r]
+        sel = sel_cache.get(id(ins)) if sel_cache is not None else None       # one `selections` per distinct instruction of a trace
+        if sel is None:
+            sel = selections(ins)[:4]
+            if sel_cache is not None:
+                sel_cache[id(ins)] = sel
+        sa, sb, sc, sd = sel
         get = lambda op: op.value if isinstance(op, T.Imm) else step.regs[op.index]     # ImmediateOrRegName::get
 
         def a_of(op):
@@ -666,15 +724,15 @@ class TinyRamCircuit:
 
         def common(s):
             k = s[0]
-            if k == "Pc": return pc()
-            if k == "PcN": return pc_n()
-            if k == "PcPlusOne": return pc() + 1
-            if k == "Reg": return reg(s[1])
-            if k == "RegN": return reg_n(s[1])
+            if k == "Zero" or k == "Unset": return 0
+            if k == "Reg": return step.regs[s[1]]
+            if k == "RegN": return steps[i + 1].regs[s[1]]
             if k == "A": return a_of(s[1])
+            if k == "Pc": return step.pc
+            if k == "PcN": return steps[i + 1].pc
+            if k == "PcPlusOne": return step.pc + 1
             if k == "VAddr": return step.v_addr
             if k == "MaxWord": return (1 << W) - 1
-            if k in ("Zero", "Unset"): return 0
             if k == "One": return 1
             return None
 
@@ -741,14 +799,20 @@ class FixedColumn:
 PL_FIELD_MODULUS = 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001   # pasta Fp: the circuit field (test_utils.rs:2)
 
 
-def columns_to_lists(advice: List[Dict[int, int]]) -> List[List[int]]:
-    """sparse {row: value} columns -> dense lists just long enough to hold the assigned rows (create_proof zero-pads)"""
+def columns_to_lists(advice: List[list]) -> List[List[int]]:
+    """columns with None for unassigned cells -> dense lists just long enough to hold the assigned rows (create_proof zero-pads)"""
     out = []
     for col in advice:
-        m = max(col) + 1 if col else 0
-        dense = [0] * m
-        for r, v in col.items():
-            dense[r] = v
+        m = len(col)
+        if m and col[-1] is None:
+            if col.count(None) == m:
+                m = 0
+            else:
+                while col[m - 1] is None:
+                    m -= 1
+        dense = col[:m]
+        if None in dense:
+            dense = [0 if v is None else v for v in dense]
         out.append(dense)
     return out
 
