@@ -318,7 +318,7 @@ class BatchVerifier:
 # ---- plonk::verify_proof -------------------------------------------------------------------------------------------------------------------
 def verify_proof(backend, vk, strategy, instances, transcript: Blake2bRead):
     """plonk::verify_proof for ONE circuit instance (what the reference passes, test_utils.rs:67, 111).  instances: one list of
-    ints per instance column.  Returns strategy.process(...)'s value (None for SingleVerifier) or raises VerifyError."""
+    ints (or one backend vector) per instance column.  Returns strategy.process(...)'s value (None for SingleVerifier) or raises VerifyError."""
     B, cs = backend, vk.cs
     n, p, k = B.n, B.p, B.k
     if vk.k != k or B.j != vk.cs_degree:
@@ -329,12 +329,17 @@ def verify_proof(backend, vk, strategy, instances, transcript: Blake2bRead):
     rot = B.rotate_omega
     if len(instances) != cs.num_instance:
         raise VerifyError("InvalidInstances")
-    for col in instances:
-        if len(col) > usable:
-            raise VerifyError("InstanceTooLarge")
+    def column(col):            # lists of at most usable_rows ints, or backend vectors of n values (as plonk.create_proof takes them)
+        if isinstance(col, (list, tuple)):
+            if len(col) > usable:
+                raise VerifyError("InstanceTooLarge")
+            return B.vec(list(col))
+        return B.vec(col)
+
+    inst_values = [column(col) for col in instances]
     t = transcript
     t.common_scalar(vk.transcript_repr)
-    inst_commitments = B.commit_lagrange_many([B.vec(list(col)) for col in instances], [1] * len(instances))    # Blind::default() = 1
+    inst_commitments = B.commit_lagrange_many(inst_values, [1] * len(inst_values))    # Blind::default() = 1
     for cm in inst_commitments:
         t.common_point(cm)
     adv_commitments = [t.read_point() for _ in range(cs.num_advice)]
