@@ -88,5 +88,19 @@ if verify:
     res["verify_s"] = round(time.perf_counter() - t0, 2)
     bad = bytearray(proof); bad[len(proof) // 3] ^= 2
     res["tampered_rejected"] = not VU.verify(be, pk.vk, inst, bytes(bad))[0]
+try:        # the package's own verifier on the device (verifier.py), instance columns as device vectors: reported, not gating
+    from tiny_ram_halo2_b200 import verifier as V
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    V.verify_proof(be, pk.vk, V.SingleVerifier(be), d_inst, V.Blake2bRead(proof, be.q, be.p))
+    torch.cuda.synchronize()
+    res["product_verifier"] = {"accepted": True, "seconds": round(time.perf_counter() - t0, 3)}
+    bad = bytearray(proof); bad[len(proof) // 3] ^= 2
+    try:
+        V.verify_proof(be, pk.vk, V.SingleVerifier(be), d_inst, V.Blake2bRead(bytes(bad), be.q, be.p))
+        res["product_verifier"]["tampered_rejected"] = False
+    except V.VerifyError:
+        res["product_verifier"]["tampered_rejected"] = True
+except Exception as e:
+    res["product_verifier"] = {"error": repr(e)}
 print(json.dumps(res))
 sys.exit(0 if (not verify or (res["verified"] and res["tampered_rejected"])) else 1)
