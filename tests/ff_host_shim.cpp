@@ -3,6 +3,7 @@
 #include "../tiny-ram-halo2_b200/csrc/ff.cuh"
 #include "../tiny-ram-halo2_b200/csrc/ec.cuh"
 #include "../tiny-ram-halo2_b200/csrc/affine_add.cuh"
+#include "../tiny-ram-halo2_b200/csrc/bucket_reduce.cuh"
 #include <vector>
 #include <cstring>
 using namespace ff;
@@ -61,7 +62,35 @@ template <class PR> static void affine_level(const uint32_t* in, size_t n_out, u
   }
 }
 
+// the two-level weighted bucket sum of bucket_reduce.cuh the way msm_reduce_chunks2 / msm_reduce_sets2 run it: chunks of
+// 2^log_chunk buckets, `threads` leaves of 2^log_m chunks each, a binary tree over the leaves
+template <class PR> static void bucket_reduce2(const uint32_t* buckets_aff, unsigned threads, unsigned log_m, unsigned log_chunk, uint32_t* out_aff) {
+  const unsigned S = 1u << log_chunk, m = 1u << log_m, chunks = threads * m;
+  auto bucket = [&](size_t b) {
+    ec::Affine<PR> p; memcpy(p.x.v, buckets_aff + 16 * b, 32); memcpy(p.y.v, buckets_aff + 16 * b + 8, 32);
+    return ec::xyzz_from_affine(p);
+  };
+  std::vector<ec::XYZZ<PR>> acc(chunks), tot(chunks);
+  for (unsigned ch = 0; ch < chunks; ++ch) {
+    ec::XYZZ<PR> run = ec::xyzz_identity<PR>(), a = ec::xyzz_identity<PR>();
+    for (int k = (int)S - 1; k >= 0; --k) { ec::xyzz_add(run, bucket((size_t)ch * S + k)); ec::xyzz_add(a, run); }
+    acc[ch] = a; tot[ch] = run;
+  }
+  std::vector<ec::WNode<PR>> node(threads);
+  for (unsigned t = 0; t < threads; ++t)
+    node[t] = ec::wnode_leaf<PR>(m, [&](unsigned ch) { return acc[t * m + ch]; }, [&](unsigned ch) { return tot[t * m + ch]; });
+  unsigned lv = 0;
+  for (unsigned stride = 1; stride < threads; stride <<= 1, ++lv)
+    for (unsigned t = 0; t < threads; t += 2 * stride) ec::wnode_combine(node[t], node[t + stride], log_m + lv);
+  ec::Affine<PR> r = ec::xyzz_to_affine(ec::wnode_root(node[0], log_chunk));
+  memcpy(out_aff, r.x.v, 32); memcpy(out_aff + 8, r.y.v, 32);
+}
+
 extern "C" {
+void ffh_bucket_reduce2(int base_field, const uint32_t* buckets_aff, unsigned threads, unsigned log_m, unsigned log_chunk, uint32_t* out_aff) {
+  if (base_field == 0) bucket_reduce2<FpParams>(buckets_aff, threads, log_m, log_chunk, out_aff);
+  else bucket_reduce2<FqParams>(buckets_aff, threads, log_m, log_chunk, out_aff);
+}
 void ffh_affine_level(int base_field, const uint32_t* in, size_t n_out, uint32_t* out) {
   if (base_field == 0) affine_level<FpParams>(in, n_out, out); else affine_level<FqParams>(in, n_out, out);
 }

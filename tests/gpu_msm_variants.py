@@ -6,8 +6,9 @@ scalars, device resident (bench.py's step), 5 timed steps with CUDA events; the 
   python tests/gpu_msm_variants.py            # K = 20
   K=16 python tests/gpu_msm_variants.py
 
-Variants: TRP_MSM_CALL=1 (field multiplication out of line in the level-1 accumulation) and TRP_MSM_C=17..20 (wider windows:
-fewer bucket additions per scalar, more buckets to reduce) -- DESIGN.md section 9.  K=22 / K=24 are where wider windows
+Variants: TRP_MSM_CALL=1 (field multiplication out of line in the level-1 accumulation), TRP_MSM_C=17..20 (wider windows: fewer
+bucket additions per scalar, more buckets to reduce) and TRP_MSM_REDUCE=2 (the two-level weighted bucket sum of
+csrc/bucket_reduce.cuh, which is what makes the wider windows affordable) -- DESIGN.md section 9.  K=22 / K=24 are where wider windows
 should pay most (set B=4 / B=1 columns to stay inside the scratch budget)."""
 import hashlib
 import json
@@ -16,7 +17,9 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-VARIANTS = [("default", {}), ("fe_mul out of line", {"TRP_MSM_CALL": "1"})] + [(f"c = {c}", {"TRP_MSM_C": str(c)}) for c in (17, 18, 19, 20)]
+VARIANTS = ([("default", {}), ("fe_mul out of line", {"TRP_MSM_CALL": "1"}), ("two-level reduction", {"TRP_MSM_REDUCE": "2"})]
+            + [(f"c = {c}", {"TRP_MSM_C": str(c)}) for c in (17, 18, 19, 20)]
+            + [(f"c = {c}, two-level reduction", {"TRP_MSM_C": str(c), "TRP_MSM_REDUCE": "2"}) for c in (18, 19, 20)])
 
 
 def child():
@@ -64,7 +67,9 @@ def main():
             continue
         r = json.loads(out.stdout.strip().splitlines()[-1])
         results.append((name, r))
-        print(f"{name:24s} {r['ms_per_step']:8.3f} ms/step {r['mpts']:7.1f} Mpts/s  accumulate {r['phase_ms_per_launch'].get('msm_accum_l1', float('nan')):.3f} ms  {r['sha256'][:16]}")
+        ph = r["phase_ms_per_launch"]
+        print(f"{name:32s} {r['ms_per_step']:8.3f} ms/step {r['mpts']:7.1f} Mpts/s  sort {ph.get('msm_sort', float('nan')):.3f}  accumulate "
+              f"{ph.get('msm_accum_l1', float('nan')):.3f}  levels {ph.get('msm_levels', float('nan')):.3f}  reduce {ph.get('msm_reduce', float('nan')):.3f} ms  {r['sha256'][:16]}")
     if len({r["sha256"] for _, r in results}) > 1:
         print("MISMATCH between variants")
         sys.exit(1)

@@ -136,3 +136,26 @@ def test_affine_tree_level_matches_bigint(shim, cid, C):
             acc = C.add(acc, Q)
         want.append(acc)
     assert got == want
+
+
+@pytest.mark.parametrize("cid,C", [(0, pm.Pallas), (1, pm.Vesta)])
+@pytest.mark.parametrize("threads,log_m,log_chunk", [(8, 2, 2), (4, 0, 3), (1, 3, 1), (16, 1, 0)])
+def test_two_level_bucket_sum_matches_bigint(shim, cid, C, threads, log_m, log_chunk):
+    """csrc/bucket_reduce.cuh: sum_b (b + 1) B_b through chunk sums, per-thread running sums over the chunk totals and the
+    (sum, weighted sum) tree across threads, with empty buckets, repeated points (the doubling case) and cancelling pairs"""
+    rnd = random.Random(31 + cid + 7 * threads)
+    F = C.base
+    bf = O.BASE_FIELD[cid]
+    nb = threads << (log_m + log_chunk)
+    P = [C.mul(rnd.randrange(C.scalar.p), C.G) for _ in range(12)]
+    buckets = [rnd.choice(P + [None, None, None, C.neg(P[0]), C.neg(P[1])]) for _ in range(nb)]
+    aff = lambda Q: [0, 0] if Q is None else [F.to_mont(Q[0]), F.to_mont(Q[1])]
+    arr = O.ints_to_limbs([c for Q in buckets for c in aff(Q)])
+    out = np.zeros((2, 4), dtype=np.uint64)
+    shim.ffh_bucket_reduce2(bf, arr.ctypes.data_as(ctypes.c_void_p), threads, log_m, log_chunk, out.ctypes.data_as(ctypes.c_void_p))
+    vals = [F.from_mont(v) for v in O.limbs_to_ints(out)]
+    got = None if vals == [0, 0] else (vals[0], vals[1])
+    want = None
+    for b, Q in enumerate(buckets):
+        want = C.add(want, C.mul(b + 1, Q) if Q is not None else None)
+    assert got == want

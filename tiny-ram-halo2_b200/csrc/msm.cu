@@ -20,6 +20,7 @@
 // uniform bucket runs.  When that table would not fit the budget the windows keep separate bucket sets.
 #include "common.cuh"
 #include "ec.cuh"
+#include "bucket_reduce.cuh"
 #include "scan.cuh"
 
 #include <algorithm>
@@ -300,6 +301,76 @@ __global__ void __launch_bounds__(256) msm_reduce_sets_kernel(const uint4* chunk
   }
 }
 
+// UNMEASURED EXPERIMENT (TRP_MSM_REDUCE=2; the arithmetic is bucket_reduce.cuh, host-tested): chunks emit
+// their own weighted sum AND their total; the per-set kernel turns the totals into sum_ch ch * tot_ch by running sums inside a
+// thread's run of chunks and a (sum, weighted sum) tree across threads, instead of one doubling chain per chunk.
+constexpr unsigned LOG_RED_S = 4;            // RED_S = 16
+constexpr int RED2_THREADS = 128;
+static_assert((1u << LOG_RED_S) == RED_S, "LOG_RED_S");
+template <class BPR>
+__global__ void __launch_bounds__(ACC_THREADS) msm_reduce_chunks2_kernel(const uint4* part, const uint32_t* off, MsmGeom g, unsigned total_sets,
+                                                                       uint4* chunk_acc, uint4* chunk_tot) {
+  const unsigned chunks_per_set = g.B / RED_S;
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total_sets * chunks_per_set) return;
+  unsigned set = t / chunks_per_set, lo = (t % chunks_per_set) * RED_S;
+  XYZZ<BPR> run = xyzz_identity<BPR>(), acc = xyzz_identity<BPR>();
+  for (int k = (int)RED_S - 1; k >= 0; --k) {
+    xyzz_add(run, bucket_value<BPR>(part, off, set * g.B + lo + k));
+    xyzz_add(acc, run);
+  }
+  store_xyzz(chunk_acc + 8 * (size_t)t, acc);
+  store_xyzz(chunk_tot + 8 * (size_t)t, run);
+}
+
+// block b sums the RED2_THREADS << log_m chunks that start at chunk b * (RED2_THREADS << log_m) into one node (G blocks per set)
+template <class BPR> __device__ __forceinline__ void put_node(uint4* p, const WNode<BPR>& n) {
+  store_xyzz(p, n.a); store_xyzz(p + 8, n.s); store_xyzz(p + 16, n.w);
+}
+template <class BPR> __device__ __forceinline__ WNode<BPR> get_node(const uint4* p) {
+  WNode<BPR> n;
+  n.a = load_xyzz<BPR>(p); n.s = load_xyzz<BPR>(p + 8); n.w = load_xyzz<BPR>(p + 16);
+  return n;
+}
+template <class BPR>
+__global__ void __launch_bounds__(RED2_THREADS) msm_reduce_sets2_kernel(const uint4* chunk_acc, const uint4* chunk_tot, unsigned log_m, uint4* nodes) {
+  __shared__ uint4 sm[RED2_THREADS * 24];    // a, s, w per thread
+  const unsigned m = 1u << log_m, tid = threadIdx.x;
+  const size_t first = ((size_t)blockIdx.x * RED2_THREADS + tid) << log_m;
+  const uint4* acc = chunk_acc + 8 * first;
+  const uint4* tot = chunk_tot + 8 * first;
+  put_node<BPR>(sm + 24 * tid, wnode_leaf<BPR>(m, [&](unsigned ch) { return load_xyzz<BPR>(acc + 8 * (size_t)ch); },
+                                               [&](unsigned ch) { return load_xyzz<BPR>(tot + 8 * (size_t)ch); }));
+  __syncthreads();
+  unsigned lv = 0;
+  for (unsigned stride = 1; stride < RED2_THREADS; stride <<= 1, ++lv) {
+    if ((tid & (2 * stride - 1)) == 0) {
+      WNode<BPR> l = get_node<BPR>(sm + 24 * tid);
+      wnode_combine(l, get_node<BPR>(sm + 24 * (tid + stride)), log_m + lv);
+      put_node<BPR>(sm + 24 * tid, l);
+    }
+    __syncthreads();
+  }
+  if (tid < 24) nodes[24 * (size_t)blockIdx.x + tid] = sm[tid];
+}
+
+// one block per set: the G = 2^log_g nodes of the set (each covering 2^log_len chunks) -> set_sums[set]
+template <class BPR>
+__global__ void __launch_bounds__(RED2_THREADS) msm_reduce_nodes_kernel(uint4* nodes, unsigned log_g, unsigned log_len, uint4* set_sums) {
+  const unsigned G = 1u << log_g, tid = threadIdx.x;
+  uint4* mine = nodes + 24 * ((size_t)blockIdx.x << log_g);
+  unsigned lv = 0;
+  for (unsigned stride = 1; stride < G; stride <<= 1, ++lv) {
+    if (tid < G && (tid & (2 * stride - 1)) == 0) {
+      WNode<BPR> l = get_node<BPR>(mine + 24 * tid);
+      wnode_combine(l, get_node<BPR>(mine + 24 * (tid + stride)), log_len + lv);
+      put_node<BPR>(mine + 24 * tid, l);
+    }
+    __syncthreads();     // one block per set: its threads are the only readers and writers of the set's nodes
+  }
+  if (tid == 0) store_xyzz(set_sums + 8 * (size_t)blockIdx.x, wnode_root(get_node<BPR>(mine), LOG_RED_S));
+}
+
 // Horner over sets (window w has weight 2^(c*w)) and conversion XYZZ -> Jacobian (X*ZZ^4... no inversion):
 // (X', Y', Z') = (X * ZZ^4, Y * ZZZ^4, ZZ * ZZZ) since Z'^2 = ZZ^5 and Z'^3 = ZZZ^5.
 template <class BPR>
@@ -438,7 +509,7 @@ std::vector<size_t> plan_levels(const MsmGeom& g, size_t n, size_t mc) {
 
 struct MsmWs {
   uint32_t *counts, *offsets, *cursor, *block_sums, *total, *entries, *task_off[2];
-  uint4 *part[2], *chunk_out, *set_sums;
+  uint4 *part[2], *chunk_out, *nodes, *set_sums;
   size_t bytes;
 };
 MsmWs carve(const MsmGeom& g, size_t n, size_t mc, char* base) {
@@ -457,7 +528,8 @@ MsmWs carve(const MsmGeom& g, size_t n, size_t mc, char* base) {
   w.task_off[1] = cur.take<uint32_t>(NB + 1);
   w.part[0] = cur.take<uint4>(8 * lt[0]);
   w.part[1] = cur.take<uint4>(8 * (lt.size() > 1 ? lt[1] : 1));
-  w.chunk_out = cur.take<uint4>(8 * (size_t)g.nsets * mc * chunks_per_set);
+  w.chunk_out = cur.take<uint4>(2 * 8 * (size_t)g.nsets * mc * chunks_per_set);   // second half: the chunk totals of TRP_MSM_REDUCE=2
+  w.nodes = cur.take<uint4>(24 * ((size_t)g.nsets * mc * chunks_per_set / RED2_THREADS + 1));   // and its per-block nodes
   w.set_sums = cur.take<uint4>(8 * (size_t)g.nsets * mc);
   w.bytes = cur.off + 4096;
   return w;
@@ -511,10 +583,27 @@ int msm_chunk(trp_ctx* ctx, const trp_bases_impl* bs, const uint4* d_scalars, si
     unsigned chunks_per_set = g.B / RED_S ? g.B / RED_S : 1;
     unsigned total_sets = (unsigned)(g.nsets * mc);
     unsigned nchunks = total_sets * chunks_per_set;
-    msm_reduce_chunks_kernel<BPR><<<(nchunks + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, ctx->stream>>>(w.part[curp], w.task_off[curp], g, total_sets, w.chunk_out);
-    TRP_LAUNCHED(ctx);
-    msm_reduce_sets_kernel<BPR><<<total_sets, 256, 0, ctx->stream>>>(w.chunk_out, chunks_per_set, w.set_sums);
-    TRP_LAUNCHED(ctx);
+    static const bool two_level = [] { const char* e = getenv("TRP_MSM_REDUCE"); return e && atoi(e) == 2; }();
+    if (two_level && g.B >= RED_S * (unsigned)RED2_THREADS) {
+      // chunks per set = RED2_THREADS * 2^log_m * 2^log_g: at most 4 chunks per thread, the rest as blocks (B is a power of two)
+      unsigned log_cps = 0;
+      while ((2u << log_cps) <= chunks_per_set) ++log_cps;
+      const unsigned log_t = 7;                                                       // RED2_THREADS = 128
+      unsigned log_m = log_cps - log_t < 2 ? log_cps - log_t : 2, log_g = log_cps - log_t - log_m;
+      if (log_g > log_t) { log_m += log_g - log_t; log_g = log_t; }                  // at most RED2_THREADS nodes per set
+      uint4* chunk_tot = w.chunk_out + 8 * (size_t)nchunks;
+      msm_reduce_chunks2_kernel<BPR><<<(nchunks + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, ctx->stream>>>(w.part[curp], w.task_off[curp], g, total_sets, w.chunk_out, chunk_tot);
+      TRP_LAUNCHED(ctx);
+      msm_reduce_sets2_kernel<BPR><<<total_sets << log_g, RED2_THREADS, 0, ctx->stream>>>(w.chunk_out, chunk_tot, log_m, w.nodes);
+      TRP_LAUNCHED(ctx);
+      msm_reduce_nodes_kernel<BPR><<<total_sets, RED2_THREADS, 0, ctx->stream>>>(w.nodes, log_g, log_t + log_m, w.set_sums);
+      TRP_LAUNCHED(ctx);
+    } else {
+      msm_reduce_chunks_kernel<BPR><<<(nchunks + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, ctx->stream>>>(w.part[curp], w.task_off[curp], g, total_sets, w.chunk_out);
+      TRP_LAUNCHED(ctx);
+      msm_reduce_sets_kernel<BPR><<<total_sets, 256, 0, ctx->stream>>>(w.chunk_out, chunks_per_set, w.set_sums);
+      TRP_LAUNCHED(ctx);
+    }
     msm_final_kernel<BPR><<<(unsigned)((mc + 31) / 32), 32, 0, ctx->stream>>>(w.set_sums, g, (unsigned)mc, d_out);
     TRP_LAUNCHED(ctx);
   }
