@@ -8,7 +8,8 @@ scalars, device resident (bench.py's step), 5 timed steps with CUDA events; the 
 
 Variants: TRP_MSM_CALL=1 (field multiplication out of line in the level-1 accumulation), TRP_MSM_C=17..20 (wider windows: fewer
 bucket additions per scalar, more buckets to reduce) and TRP_MSM_REDUCE=2 (the two-level weighted bucket sum of
-csrc/bucket_reduce.cuh, which is what makes the wider windows affordable) -- DESIGN.md section 9.  K=22 / K=24 are where wider windows
+csrc/bucket_reduce.cuh, which is what makes the wider windows affordable) and TRP_MSM_SEG=1 (level-1 tasks as aligned windows
+of the sorted entry list: no partial tasks, whatever the bucket sizes) -- DESIGN.md section 9.  K=22 / K=24 are where wider windows
 should pay most (set B=4 / B=1 columns to stay inside the scratch budget)."""
 import hashlib
 import json
@@ -19,7 +20,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = ([("default", {}), ("fe_mul out of line", {"TRP_MSM_CALL": "1"}), ("two-level reduction", {"TRP_MSM_REDUCE": "2"})]
             + [(f"c = {c}", {"TRP_MSM_C": str(c)}) for c in (17, 18, 19, 20)]
-            + [(f"c = {c}, two-level reduction", {"TRP_MSM_C": str(c), "TRP_MSM_REDUCE": "2"}) for c in (18, 19, 20)])
+            + [(f"c = {c}, two-level reduction", {"TRP_MSM_C": str(c), "TRP_MSM_REDUCE": "2"}) for c in (18, 19, 20)]
+            + [("segmented level 1", {"TRP_MSM_SEG": "1"})]
+            + [(f"c = {c}, segmented, two-level", {"TRP_MSM_C": str(c), "TRP_MSM_SEG": "1", "TRP_MSM_REDUCE": "2"}) for c in (18, 19, 20)])
 
 
 def child():

@@ -221,6 +221,36 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accum_l1_call_kernel(const ui
   store_xyzz(partials + 8 * (size_t)t, acc);
 }
 
+// UNMEASURED EXPERIMENT (TRP_MSM_SEG=1): level-1 tasks cut the SORTED ENTRY LIST into aligned windows of L1
+// entries instead of cutting every bucket into tasks of its own, so every thread of a warp performs exactly L1 additions
+// whatever the bucket sizes are (today the last task of a bucket is partial: ~6 % idle lanes at 512 entries per bucket, ~30 % at
+// the 26 entries per bucket of c = 20).  A thread emits one partial per bucket its window meets: bucket b's partials are the
+// slots pbase[b] + (t - off[b] / L1), pbase = the scan of scan_input mode 2, which is exactly the per-bucket layout the upper
+// levels read.
+template <class BPR>
+__global__ void __launch_bounds__(ACC_THREADS) msm_accum_l1_seg_kernel(const uint32_t* entries, const uint32_t* off, const uint32_t* pbase,
+                                                                     unsigned nb, const uint4* bases, uint4* partials) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t total = __ldg(off + nb);
+  if ((uint64_t)t * L1 >= total) return;
+  const uint32_t e0 = t * L1, e1 = min(e0 + L1, total);
+  unsigned b = find_segment(off, nb, e0);              // the (non-empty) bucket holding entry e0
+  uint32_t next = __ldg(off + b + 1);
+  XYZZ<BPR> acc = xyzz_identity<BPR>();
+  for (uint32_t e = e0; e < e1; ++e) {
+    if (e == next) {                                   // bucket boundary inside the window: emit, move to the next non-empty bucket
+      store_xyzz(partials + 8 * (size_t)(__ldg(pbase + b) + (t - __ldg(off + b) / L1)), acc);
+      acc = xyzz_identity<BPR>();
+      do { ++b; next = __ldg(off + b + 1); } while (next <= e);
+    }
+    uint32_t ent = __ldg(entries + e);
+    Affine<BPR> p = load_affine<BPR>(bases, ent & 0x7fffffffu);
+    if (ent >> 31) p.y = fe_neg(p.y);
+    xyzz_add_mixed(acc, p);
+  }
+  store_xyzz(partials + 8 * (size_t)(__ldg(pbase + b) + (t - __ldg(off + b) / L1)), acc);
+}
+
 // levels >= 2: partial sums of the previous level, full adds
 template <class BPR>
 __global__ void __launch_bounds__(ACC_THREADS) msm_accum_ln_kernel(const uint4* in, const uint32_t* in_off,
@@ -491,12 +521,18 @@ unsigned choose_c(size_t n) {
   return (unsigned)c;
 }
 
+bool seg_mode() {      // TRP_MSM_SEG=1: the segmented level-1 tasks (msm_accum_l1_seg_kernel)
+  static const bool on = [] { const char* e = getenv("TRP_MSM_SEG"); return e && atoi(e) == 1; }();
+  return on;
+}
+
 // Worst-case task counts per level for mc columns processed together (entries may all fall into one bucket, or
 // spread over all of them).
 std::vector<size_t> plan_levels(const MsmGeom& g, size_t n, size_t mc) {
   const size_t M = n * g.W * mc, NB = (size_t)g.nb * mc;
   std::vector<size_t> level_tasks;
   size_t single = (n * g.W + L1 - 1) / L1;      // tasks if ONE bucket of a column held all its entries
+  if (seg_mode()) ++single;                     // an unaligned run of entries meets one window more
   size_t bound = (M + L1 - 1) / L1 + NB;        // sum_b ceil(cnt_b / L1) <= M / L1 + NB
   level_tasks.push_back(bound);
   while (single > 1) {
@@ -544,6 +580,7 @@ int msm_chunk(trp_ctx* ctx, const trp_bases_impl* bs, const uint4* d_scalars, si
   std::vector<size_t> level_tasks = plan_levels(g, n, mc);
   MsmWs w = carve(g, n, mc, ws);
   if (w.bytes > ws_cap) TRP_FAIL(ctx, TRP_E_INVALID, "internal: MSM workspace underestimated (%zu > %zu)", w.bytes, ws_cap);
+  const bool segmented = seg_mode();
   {
     ProfScope ps(ctx, PROF_MSM_SORT);
     TRP_CUDA(ctx, cudaMemsetAsync(w.counts, 0, (NB + 1) * sizeof(uint32_t), ctx->stream));
@@ -553,13 +590,16 @@ int msm_chunk(trp_ctx* ctx, const trp_bases_impl* bs, const uint4* d_scalars, si
     TRP_TRY(run_scan(ctx, w.counts, w.offsets, w.cursor, w.block_sums, w.total, NB, 0, 1));
     msm_scatter_kernel<SPR><<<sgrid, 128, 0, ctx->stream>>>(d_scalars, n, g, w.cursor, w.entries);
     TRP_LAUNCHED(ctx);
-    TRP_TRY(run_scan(ctx, w.offsets, w.task_off[0], nullptr, w.block_sums, w.total, NB, 1, L1));
+    TRP_TRY(run_scan(ctx, w.offsets, w.task_off[0], nullptr, w.block_sums, w.total, NB, segmented ? 2 : 1, L1));
   }
   {
     ProfScope ps(ctx, PROF_MSM_ACCUM_L1);
     unsigned gridl1 = (unsigned)((level_tasks[0] + ACC_THREADS - 1) / ACC_THREADS);
     static const bool out_of_line = [] { const char* e = getenv("TRP_MSM_CALL"); return e && atoi(e) == 1; }();
-    if (out_of_line)
+    if (segmented)
+      msm_accum_l1_seg_kernel<BPR><<<(unsigned)(((M + L1 - 1) / L1 + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(
+          w.entries, w.offsets, w.task_off[0], (unsigned)NB, (const uint4*)bs->pub.d_xy, w.part[0]);
+    else if (out_of_line)
       msm_accum_l1_call_kernel<BPR><<<gridl1, ACC_THREADS, 0, ctx->stream>>>(w.entries, w.offsets, w.task_off[0], (unsigned)NB,
                                                                             (const uint4*)bs->pub.d_xy, w.part[0]);
     else

@@ -29,12 +29,14 @@ static __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint
   return prefix + x - v;
 }
 
-// mode 0: in = counts as is; mode 1: in = ceil((off[i+1]-off[i]) / L) (task counts derived from offsets)
+// mode 0: in = counts as is; mode 1: in = ceil((off[i+1]-off[i]) / L) (task counts derived from offsets); mode 2: the number
+// of aligned windows [L t, L t + L) that the range [off[i], off[i+1]) meets (the segmented level-1 tasks of msm.cu)
 static __device__ __forceinline__ uint32_t scan_input(const uint32_t* in, size_t i, size_t n, int mode, unsigned L) {
   if (i >= n) return 0;
   if (mode == 0) return in[i];
-  uint32_t cnt = in[i + 1] - in[i];
-  return (cnt + L - 1) / L;
+  uint32_t lo = in[i], hi = in[i + 1];
+  if (mode == 2) return hi > lo ? (hi - 1) / L - lo / L + 1 : 0;
+  return (hi - lo + L - 1) / L;
 }
 
 static __global__ void scan_local_kernel(const uint32_t* in, uint32_t* out, uint32_t* block_sums, size_t n, int mode, unsigned L) {
