@@ -307,3 +307,65 @@ def test_batch_inverse(mods):
     rnd.shuffle(vals)
     assert TR._batch_inverse(vals, p) == [pow(v, -1, p) if v else 0 for v in vals]
     assert TR._batch_inverse([], p) == [] and TR._batch_inverse([0, 0], p) == [0, 0]
+
+
+def test_array_columns_equal_list_columns(mods):
+    """build(arrays=True) -- the upload path of bench.py -- returns the same witness: every column that comes back as a uint64
+    numpy array holds exactly the ints of the list version (and goes through device_columns' fast path, _column_u64)"""
+    import numpy as np
+    PL, TR, T = mods
+    from tiny_ram_halo2_b200 import programs
+    for tr, k, kw in ((TP.load_and_answer(T, 8, 1, 2), 6, {}), (programs.counting_loop(16, 3, programs.mixed_body(16)), 11, {}),
+                      (programs.counting_loop(16, 3, programs.mixed_body(16)), 11, {"with_prog": False}),
+                      (programs.counting_loop(32, 12, programs.mixed_body(32)), 17, {})):
+        _, f0, c0, a0, i0 = TR.build(PL, tr, k, dense=False, **kw)
+        _, f1, c1, a1, i1 = TR.build(PL, tr, k, dense=False, arrays=True, **kw)
+        assert c0 == c1 and len(a0) == len(a1) and len(i0) == len(i1) and len(f0) == len(f1)
+        n_arrays = 0
+        for x, y in list(zip(a0, a1)) + list(zip(i0, i1)) + [(f.prefix, g.prefix) for f, g in zip(f0, f1)]:
+            if isinstance(y, np.ndarray):
+                n_arrays += 1
+                assert y.dtype == np.uint64 and TR._column_u64(y) is not None
+                assert [int(v) for v in y] == list(x)
+            else:
+                assert y == x
+        assert [f.fill for f in f0] == [g.fill for g in f1]
+        assert n_arrays >= (200 if kw.get("with_prog", True) else 100)
+    assert TR._column_u64([1, 1 << 64]) is None and TR._column_u64([]).shape == (0,)
+    assert TR._column_u64(np.arange(10, dtype=np.uint64).reshape(5, 2)[:, 1]).flags.c_contiguous
+    assert TR.even_bits_table(1 << 10) == [TR.even_bits_at(i) for i in range(1 << 10)]
+
+
+def test_device_columns_host_logic_on_a_fake_backend(mods, monkeypatch):
+    """tinyram.device_columns with the CUDA calls stubbed out (torch on the CPU, the Montgomery conversion kernel a no-op): list
+    columns and the uint64-array columns of build(arrays=True) must stage the same limb-0 values, fill included"""
+    import types
+    import numpy as np
+    import torch
+    PL, TR, T = mods
+    from tiny_ram_halo2_b200 import programs
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    fake_torch = types.SimpleNamespace(zeros=lambda shape, dtype=None, device=None: torch.zeros(shape, dtype=dtype), int64=torch.int64,
+                                       from_numpy=torch.from_numpy)
+    calls = []
+    be = types.SimpleNamespace(torch=fake_torch, n=1 << 11, R=5, _limbs=lambda vals: np.zeros((len(vals), 4), dtype=np.uint64),
+                               _dev=lambda limbs: torch.zeros((len(limbs), 4), dtype=torch.int64), _sync=lambda: None,
+                               ctx=types.SimpleNamespace(check=lambda rc: None, handle=None),
+                               lib=types.SimpleNamespace(trp_dev_field_op=lambda *a: calls.append(a[-1]) or 0))
+    tr = programs.counting_loop(16, 3, programs.mixed_body(16))
+    _, f0, _, a0, i0 = TR.build(PL, tr, 11, dense=False)
+    _, f1, _, a1, i1 = TR.build(PL, tr, 11, dense=False, arrays=True)
+    small = lambda col: all(v < 1 << 64 for v in (col.prefix if isinstance(col, TR.FixedColumn) else col))
+    for lists, arrs in ((f0, f1), (a0, a1), (i0, i1)):
+        keep = [j for j, c in enumerate(lists) if small(c)]             # the others go through be.vec, which the fake does not have
+        got0 = TR.device_columns(be, [lists[j] for j in keep])
+        got1 = TR.device_columns(be, [arrs[j] for j in keep])
+        assert len(got0) == len(got1) == len(keep) > 0
+        for j, x, y in zip(keep, got0, got1):
+            assert torch.equal(x, y), j
+            col = lists[j]
+            prefix, fill = (col.prefix, col.fill) if isinstance(col, TR.FixedColumn) else (col, 0)
+            want = np.full(be.n, fill, dtype=np.uint64)
+            want[:len(prefix)] = np.array(list(prefix), dtype=np.uint64)
+            assert np.array_equal(x[:, 0].numpy().view(np.uint64), want) and not x[:, 1:].any()
+    assert calls and set(calls) == {be.n}

@@ -168,6 +168,18 @@ def even_bits_at(i: int) -> int:
     return r
 
 
+def even_bits_table(count: int) -> List[int]:
+    """[even_bits_at(i) for i in range(count)], count <= 2^32, by the usual mask-and-shift bit spreading on a uint64 array"""
+    import numpy as np
+    if count > 1 << 32:
+        raise ValueError("even-bits table beyond 2^32 rows")
+    x = np.arange(count, dtype=np.uint64)
+    for shift, mask in ((16, 0x0000FFFF0000FFFF), (8, 0x00FF00FF00FF00FF), (4, 0x0F0F0F0F0F0F0F0F), (2, 0x3333333333333333),
+                        (1, 0x5555555555555555)):
+        x = (x | (x << np.uint64(shift))) & np.uint64(mask)
+    return x.tolist()
+
+
 _EVEN_MASK = int.from_bytes(bytes([0x55] * 32), "little")
 _ODD_MASK = int.from_bytes(bytes([0xAA] * 32), "little")
 
@@ -197,8 +209,9 @@ def _batch_inverse(values: List[int], p: int) -> List[int]:
     return out
 
 
-def program_instance(prog: List[T.Instruction], word_bits: int, reg_count: int = 8) -> List[List[int]]:
-    """tables/prog.rs:38-60: the 94 instance columns; the program is padded to TABLE_LEN lines with its terminal Answer"""
+def program_instance(prog: List[T.Instruction], word_bits: int, reg_count: int = 8, arrays: bool = False) -> List[List[int]]:
+    """tables/prog.rs:38-60: the 94 instance columns; the program is padded to TABLE_LEN lines with its terminal Answer.
+    arrays: the columns as uint64 numpy arrays (same values)"""
     table_len = 1 << (word_bits // 2)
     if not prog or prog[-1].name != "Answer":
         raise ValueError("Empty programs are invalid / the last instruction must be Answer")
@@ -220,6 +233,9 @@ def program_instance(prog: List[T.Instruction], word_bits: int, reg_count: int =
         for c, v in line.row_values(prog[-1]).items():
             if v:
                 cols[c][len(prog):] = [v] * pad
+    if arrays:
+        import numpy as np
+        return [np.array(c, dtype=np.uint64) for c in cols]
     return cols
 
 
@@ -519,7 +535,7 @@ class TinyRamCircuit:
 
     # ---- synthesize (circuits/mod.rs:62-75) ---------------------------------------------------------------------------------------------
     def synthesize(self, trace: Optional[T.Trace], n: int, a_flag_rand: Optional[Callable[[], int]] = None,
-                   reg_operand_value: bool = True):
+                   reg_operand_value: bool = True, arrays: bool = False):
         """Returns (fixed, copies, advice): fixed = one FixedColumn (assigned prefix + fill value) per fixed column, advice = one
         sparse {row: value} dict per advice column, copies = the copy constraints of assign_advice_from_instance (one plonk.CopyBlock per column pair).  Values are
         canonical ints of the circuit field.
@@ -527,7 +543,10 @@ class TinyRamCircuit:
         reg_operand_value: push_temp_var_vals takes a REGISTER operand's temp-var value to be the register's INDEX
         (`ImmediateOrRegName::RegName(r) => r.0.into()`, aux.rs:419-427) although the selector it sets is reg[r], whose gate
         (exe.rs:267-289) demands the register's VALUE; True (default) assigns the value, False reproduces the reference.
-        a_flag_rand: flag2.rs:70 fills a_flag with F::random(OsRng) when c + flag_next = 0; here a_flag_rand() or 0."""
+        a_flag_rand: flag2.rs:70 fills a_flag with F::random(OsRng) when c + flag_next = 0; here a_flag_rand() or 0.
+        arrays: columns whose cells depend on the instruction alone (the program line's selector vector, the Out row) and the
+        fixed range columns come back as uint64 numpy arrays instead of lists (same values; device_columns uploads them without
+        a list round trip)."""
         PL, cs, W, R, TL = self.PL, self.cs, self.W, self.R, self.table_len
         p = PL_FIELD_MODULUS
         A, I = PL.ADVICE, PL.INSTANCE
@@ -546,7 +565,10 @@ class TinyRamCircuit:
             for col, rows in cols_rows.items():
                 fixed[col], fill[col] = list(rows), rows[0]
 
-        table({self.t_even: [even_bits_at(i) for i in range(TL)]})                                          # even_bits.rs:56-74
+        import numpy as np
+        ones = (lambda: np.ones(TL, dtype=np.uint64)) if arrays else (lambda: [1] * TL)
+        ramp = (lambda: np.arange(TL, dtype=np.uint64)) if arrays else (lambda: list(range(TL)))
+        table({self.t_even: even_bits_table(TL)})                                                           # even_bits.rs:56-74
         table({self.t_pow_values: list(range(W)) + [W],
                self.t_pow_powers: [(1 << i) % (1 << W) for i in range(W)] + [0]})                          # pow.rs:21-66
         rows = [(T.OPCODES[nm] + 1, OUT[nm], nm != "Answer") for nm in OUT_TABLE_ORDER] + [(0, (), False)]  # out_table.rs:133-215
@@ -557,7 +579,7 @@ class TinyRamCircuit:
         if self.with_prog:
             for ic, tc in zip(self.prog_input.to_vec(), self.prog_table.to_vec()):
                 copies.append(PL.CopyBlock((I, ic, 0), (A, tc, 0), TL))
-            fixed[self.s_prog], fixed[self.dyn_tag], fixed[self.prog_pc] = [1] * TL, [1] * TL, list(range(TL))
+            fixed[self.s_prog], fixed[self.dyn_tag], fixed[self.prog_pc] = ones(), ones(), ramp()
 
         if trace is not None:
             if trace.word_bits != W or trace.reg_count != R:
@@ -571,7 +593,7 @@ class TinyRamCircuit:
             # order, last write wins -- what the instruction's gadget assigns, and `value` last.
             import numpy as np
             fixed[self.first_line][0] = 1
-            fixed[self.s_table], fixed[self.time] = [1] * TL, list(range(TL))
+            fixed[self.s_table], fixed[self.time] = ones(), ramp()
             ne = len(exe)
             advice[self.s_trace][:ne] = [1] * ne
             # -- static part: intermediate fill, opcode, immediate, the selector vector of the line, the Out row
@@ -596,8 +618,12 @@ class TinyRamCircuit:
                     raise AssertionError("internal: the static columns do not depend on the instruction")
                 table_ = np.array([[tm[c] % p for c in static_cols] for tm in templates], dtype=np.uint64)     # all below 2^64
                 gathered = table_[np.array(kind_of, dtype=np.int64)]
+                untouched = (set(self.line.to_vec()) | set(self.out.values())) if arrays else ()     # nothing below writes these
                 for j_, c in enumerate(static_cols):
-                    advice[c][:ne] = gathered[:, j_].tolist()
+                    if c in untouched:
+                        advice[c] = np.ascontiguousarray(gathered[:, j_])
+                    else:
+                        advice[c][:ne] = gathered[:, j_].tolist()
             # -- machine state
             advice[self.pc][:ne] = [st.pc for st in exe]
             for r_, rc in enumerate(self.reg):
@@ -662,6 +688,9 @@ class TinyRamCircuit:
         """assign_advice_from_instance: the program-table advice cells take the instance values (prog.rs:206-216)"""
         TL = self.table_len
         for ic, tc in zip(self.prog_input.to_vec(), self.prog_table.to_vec()):
+            if not isinstance(instances[ic], list):          # program_instance(arrays=True): TABLE_LEN values each
+                advice[tc] = instances[ic].copy()
+                continue
             col = list(instances[ic][:TL])
             advice[tc][:TL] = col + [0] * (TL - len(col))
         return advice
@@ -803,6 +832,9 @@ def columns_to_lists(advice: List[list]) -> List[List[int]]:
     """columns with None for unassigned cells -> dense lists just long enough to hold the assigned rows (create_proof zero-pads)"""
     out = []
     for col in advice:
+        if not isinstance(col, list):          # a uint64 array of synthesize(arrays=True): every row of it is assigned
+            out.append(col)
+            continue
         m = len(col)
         if m and col[-1] is None:
             if col.count(None) == m:
@@ -817,21 +849,23 @@ def columns_to_lists(advice: List[list]) -> List[List[int]]:
     return out
 
 
-def build(PL, trace: T.Trace, k: int, keygen_from_empty_circuit: bool = False, dense: bool = True, with_prog: bool = True, **kw):
+def build(PL, trace: T.Trace, k: int, keygen_from_empty_circuit: bool = False, dense: bool = True, with_prog: bool = True,
+          arrays: bool = False, **kw):
     """The whole of `TinyRamCircuit { trace }` + program_instance: returns (circuit, fixed, copies, advice, instances) ready for
     plonk.keygen / plonk.create_proof at n = 2^k (reference: mock_prover_test, circuits/mod.rs:364-375, uses k = 2 + W / 2).
     with_prog=False builds the reference's ExeCircuit (no program table, `instances` is empty).
     keygen_from_empty_circuit: the fixed columns are those of `TinyRamCircuit::default()` (trace: None), which is what
     gen_proofs_and_verify hands keygen_vk / keygen_pk (test_utils.rs:22-25): the execution table's selectors are then all off.
-    dense=False leaves the fixed columns as FixedColumn (prefix, fill) pairs (large n)."""
+    dense=False leaves the fixed columns as FixedColumn (prefix, fill) pairs (large n).
+    arrays=True (the upload path of bench.py): columns that are cheap to make as uint64 numpy arrays come back as such."""
     circ = TinyRamCircuit(PL, trace.word_bits, trace.reg_count, with_prog=with_prog)
     n = 1 << k
-    fixed, copies, advice = circ.synthesize(trace, n, **kw)
+    fixed, copies, advice = circ.synthesize(trace, n, arrays=arrays, **kw)
     if keygen_from_empty_circuit:
         fixed, _, _ = circ.synthesize(None, n)
     instances = []
     if with_prog:
-        instances = program_instance(trace.prog, trace.word_bits, trace.reg_count)
+        instances = program_instance(trace.prog, trace.word_bits, trace.reg_count, arrays=arrays)
         circ.assign_instance(advice, instances)
     if dense:
         fixed = [f.dense(n) for f in fixed]
@@ -839,7 +873,8 @@ def build(PL, trace: T.Trace, k: int, keygen_from_empty_circuit: bool = False, d
 
 
 def device_columns(be, columns) -> list:
-    """Upload columns to plonk.GpuBackend vectors.  columns: lists of canonical ints (zero-padded to n) or FixedColumn.  Columns
+    """Upload columns to plonk.GpuBackend vectors.  columns: lists of canonical ints (zero-padded to n), uint64 arrays
+    (build(arrays=True)) or FixedColumn.  Columns
     whose values all fit 64 bits take a fast path: the u64 values go up as limb 0 and are brought to Montgomery form on the device
     (one multiplication by R^2 through trp_dev_field_op)."""
     import numpy as np
@@ -850,18 +885,32 @@ def device_columns(be, columns) -> list:
         prefix, fill = (col.prefix, col.fill) if isinstance(col, FixedColumn) else (col, 0)
         if len(prefix) > be.n:
             raise ValueError("column longer than the domain")
-        if (not prefix or max(prefix) < 1 << 64) and fill < 1 << 64:
+        arr = _column_u64(prefix) if fill < 1 << 64 else None
+        if arr is not None:
             v = torch.zeros((be.n, 4), dtype=torch.int64, device="cuda")       # only the assigned prefix crosses PCIe
             if fill:
                 v[:, 0] = int(np.uint64(fill).view(np.int64)) if fill >= 1 << 63 else fill
-            if prefix:
-                v[:len(prefix), 0] = torch.from_numpy(np.array(prefix, dtype=np.uint64).view(np.int64)).cuda()
+            if len(arr):
+                v[:len(arr), 0] = torch.from_numpy(arr.view(np.int64)).cuda()
             be._sync()
             be.ctx.check(be.lib.trp_dev_field_op(be.ctx.handle, 0, 2 | 16, v.data_ptr(), r2.data_ptr(), v.data_ptr(), be.n))
             be._sync()
         else:
-            v = be.vec(prefix)
+            v = be.vec(prefix.tolist() if isinstance(prefix, np.ndarray) else prefix)
             if fill:
                 v[len(prefix):] = be._dev(be._limbs([fill]))
         out.append(v)
     return out
+
+
+def _column_u64(prefix):
+    """the column as a contiguous uint64 array if every value fits 64 bits (device_columns' fast path), else None.  Columns that
+    build(arrays=True) already made as uint64 arrays pass through without the list round trip."""
+    import numpy as np
+    if isinstance(prefix, np.ndarray):
+        return np.ascontiguousarray(prefix) if prefix.dtype == np.uint64 else None
+    if not prefix:
+        return np.zeros(0, dtype=np.uint64)
+    if max(prefix) >= 1 << 64:
+        return None
+    return np.array(prefix, dtype=np.uint64)
