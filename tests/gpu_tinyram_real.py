@@ -1,7 +1,7 @@
 """A REAL plonk.create_proof of the reference's TinyRamCircuit (tiny-ram-halo2_b200/tinyram.py: the actual gates, lookups and
 witness, not the stand-in of tinyram_circuit.py) for a long trace, on one B200, checked by the oracle's independent verifier.
 BASELINE.json configs[3]: word size 32 (program / execution tables of 2^16 rows, up to 65 535 steps), k = 20.
-usage: python tests/gpu_tinyram_real.py [W] [k] [steps] [--no-verify] [--empty-keygen]"""
+usage: python tests/gpu_tinyram_real.py [W] [k] [steps] [--no-verify] [--empty-keygen] [--lists]"""
 import json
 import os
 import random
@@ -48,7 +48,8 @@ t0 = time.perf_counter()
 tr = programs.longest_loop(W, steps)                       # 2 set-up steps, (len(body) + 3) per pass, 1 Answer
 t_trace = time.perf_counter() - t0
 t0 = time.perf_counter()
-circ, fixed, copies, adv, inst = TR.build(PL, tr, k, dense=False, keygen_from_empty_circuit="--empty-keygen" in sys.argv)
+circ, fixed, copies, adv, inst = TR.build(PL, tr, k, dense=False, keygen_from_empty_circuit="--empty-keygen" in sys.argv,
+                                          arrays="--lists" not in sys.argv)       # uint64 array columns: the upload path of bench.py
 t_synth = time.perf_counter() - t0
 cs = circ.cs
 t0 = time.perf_counter()
@@ -83,6 +84,7 @@ res = {"circuit": "TinyRamCircuit (tinyram.py)", "word_bits": W, "k": k, "trace_
        "upload_s": round(t_upload, 3), "keygen_s": round(t_keygen, 3), "first_proof": runs[0], "second_proof": runs[1], "later_proofs_s": [r["create_proof_s"] for r in runs[2:]],
        "best_proof": min(runs, key=lambda r: r["create_proof_s"])}
 if verify:
+    inst = [[int(v) for v in col] for col in inst]         # the oracle's verifier wants Python ints
     t0 = time.perf_counter()
     res["verified"], res["verify_error"] = VU.verify(be, pk.vk, inst, proof)
     res["verify_s"] = round(time.perf_counter() - t0, 2)
