@@ -36,25 +36,37 @@ class VerifyError(Exception):
 
 
 # ---- transcript::Blake2bRead ------------------------------------------------------------------------------------------------------------
+_TS = {}                        # per modulus: (s, t, z^t) with q - 1 = 2^s t, z a non-residue
+
+
 def _sqrt(a: int, q: int) -> Optional[int]:
-    """a square root of a modulo the prime q (Tonelli-Shanks; the Pasta primes have 2-adicity 32), None for non-residues"""
+    """a square root of a modulo the prime q (Tonelli-Shanks; the Pasta primes have 2-adicity 32), None for non-residues.
+    One full-size exponentiation per call: w = a^((t-1)/2) gives a^((t+1)/2) = a w and a^t = a w^2; a non-residue shows as an
+    element of full order 2^s in the loop."""
     a %= q
     if a == 0:
         return 0
-    if pow(a, (q - 1) // 2, q) != 1:
-        return None
-    s, t = 0, q - 1
-    while t % 2 == 0:
-        s, t = s + 1, t // 2
-    z = 2
-    while pow(z, (q - 1) // 2, q) != q - 1:
-        z += 1
-    m, c, u, r = s, pow(z, t, q), pow(a, t, q), pow(a, (t + 1) // 2, q)
+    if q not in _TS:
+        s, t = 0, q - 1
+        while t % 2 == 0:
+            s, t = s + 1, t // 2
+        z = 2
+        while pow(z, (q - 1) // 2, q) != q - 1:
+            z += 1
+        _TS[q] = (s, t, pow(z, t, q))
+    m, t, c = _TS[q]
+    w = pow(a, (t - 1) // 2, q)
+    r = a * w % q
+    u = r * w % q
     while u != 1:
-        i, w = 0, u
-        while w != 1:
-            w, i = w * w % q, i + 1
-        b = pow(c, 1 << (m - i - 1), q)
+        i, v = 0, u
+        while v != 1:
+            v, i = v * v % q, i + 1
+            if i == m:
+                return None                      # u has order 2^m: a is not a square
+        b = c
+        for _ in range(m - i - 1):
+            b = b * b % q
         m, c, u, r = i, b * b % q, u * b * b % q, r * b % q
     return r
 
