@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accum_l1_seg_kernel(const uin
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t total = __ldg(off + nb);
   if ((uint64_t)t * L1 >= total) return;
-  const uint32_t e0 = t * L1, e1 = min(e0 + L1, total);
+  const uint32_t e0 = t * L1, e1 = (uint32_t)min((uint64_t)e0 + L1, (uint64_t)total);
   unsigned b = find_segment(off, nb, e0);              // the (non-empty) bucket holding entry e0
   uint32_t next = __ldg(off + b + 1);
   XYZZ<BPR> acc = xyzz_identity<BPR>();
