@@ -217,6 +217,10 @@ def test_real_proof_on_the_cpu_backend_verifies(mods):
     assert VM.verify_proof(C, be.params, pk.vk, inst, proof), VM.verify_proof.last_error
     other = TR.program_instance([T.Answer(T.Imm(0))], 8)
     assert not VM.verify_proof(C, be.params, pk.vk, other, proof)
+    import hashlib, json, os                 # the proof bytes are frozen too (fixed-seed blinding): tests/golden/proof_digests.json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "proof_digests.json")) as f:
+        want = json.load(f)["tinyram_answer_only_w8_k6_seed1_vesta"]
+    assert (len(proof), hashlib.sha256(proof).hexdigest(), hex(pk.vk.transcript_repr)) == (want["bytes"], want["sha256"], want["transcript_repr"])
     # the package's own verifier (verifier.py) on the same proof: BatchVerifier, then SingleVerifier (test_utils.rs:56-70)
     from tiny_ram_halo2_b200 import verifier as V
     bv = V.BatchVerifier()
