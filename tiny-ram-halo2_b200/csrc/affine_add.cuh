@@ -1,5 +1,6 @@
-// Affine point addition split around ONE shared inversion (Montgomery's trick), for the experimental batched-affine stage
-// of the MSM bucket accumulation (msm.cu, TRP_MSM_AFFINE=1).  P1 + P2 on y^2 = x^3 + 5 costs
+// Affine point addition split around ONE shared inversion (Montgomery's trick): the building block of a batched-affine stage of
+// the MSM bucket accumulation (DESIGN.md section 9 costs that stage; NO kernel uses this header yet -- it is exercised on the
+// host only, tests/test_ff_host.py).  P1 + P2 on y^2 = x^3 + 5 costs
 // 1 inversion + 2M + 1S in affine coordinates; with the inversion shared by a batch it is 5M + 1S + the batch's share,
 // against 8M + 2S for the mixed XYZZ add of ec.cuh.
 //
