@@ -1,14 +1,31 @@
 // build.rs -- compiles the CUDA sources of tiny-ram-halo2_b200/csrc for sm_100a with nvcc and links libtrp.
-// Mirrors tiny-ram-halo2_b200/csrc/Makefile.  UNTESTED in the build image (no rustc); kept compile-ready.
-use std::{env, path::PathBuf, process::Command};
+// The unit list is READ from csrc/Makefile's `OBJS :=` line, so the crate links exactly what the Makefile links
+// (tests/test_rust_shim_cpu.py checks that every listed unit exists).  Not run in the build image (no rustc).
+use std::{env, fs, path::PathBuf, process::Command};
 
 fn main() {
     let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("..");
     let csrc = root.join("tiny-ram-halo2_b200").join("csrc");
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
+    let makefile = fs::read_to_string(csrc.join("Makefile")).expect("csrc/Makefile");
+    println!("cargo:rerun-if-changed={}", csrc.join("Makefile").display());
+    let units: Vec<String> = makefile
+        .lines()
+        .find(|l| l.starts_with("OBJS :="))
+        .expect("csrc/Makefile has no OBJS := line")
+        .trim_start_matches("OBJS :=")
+        .split_whitespace()
+        .map(|o| o.trim_end_matches(".o").to_string())
+        .collect();
+    assert!(!units.is_empty());
+    for entry in fs::read_dir(&csrc).unwrap() {
+        let p = entry.unwrap().path();
+        if p.extension().map_or(false, |e| e == "cuh") { println!("cargo:rerun-if-changed={}", p.display()); }
+    }
+    println!("cargo:rerun-if-changed={}", root.join("include").join("tr_prover.h").display());
     let mut objs = Vec::new();
-    for unit in ["capi", "ntt", "msm", "quotient", "microbench"] {
+    for unit in &units {
         let src = csrc.join(format!("{unit}.cu"));
         let obj = out.join(format!("{unit}.o"));
         println!("cargo:rerun-if-changed={}", src.display());

@@ -2,56 +2,17 @@
 //! TinyRAM prover spends its time in (`arithmetic::best_multiexp`, `arithmetic::best_fft`, the
 //! `EvaluationDomain` transforms).  See INTEGRATION.md for how the halo2 fork calls these.
 //!
-//! UNTESTED: the build image has no Rust toolchain.  The C ABI underneath is what the parity tests exercise.
+//! NOT COMPILED in the build image (no Rust toolchain): the C ABI underneath is what the parity tests
+//! exercise.  What IS checked without rustc (tests/test_rust_shim_cpu.py): `ffi.rs` is regenerated from the header and
+//! diffed, every symbol it declares is exported by libtrp.so, and build.rs compiles the units the Makefile links.
 #![allow(non_camel_case_types)]
-use std::{ffi::CStr, os::raw::{c_char, c_int, c_uint, c_void}, ptr, sync::Mutex};
+use std::{ffi::CStr, os::raw::{c_int, c_void}, ptr, sync::Mutex};
 
 use group::{Curve, prime::PrimeCurveAffine};
 use pasta_curves::arithmetic::{CurveAffine, FieldExt};
 
-#[repr(C)] pub struct trp_ctx { _p: [u8; 0] }
-#[repr(C)] pub struct trp_bases { _p: [u8; 0] }
-#[repr(C)] pub struct trp_domain { _p: [u8; 0] }
-
-pub const TRP_CURVE_PALLAS: c_int = 0;
-pub const TRP_CURVE_VESTA: c_int = 1;
-
-extern "C" {
-    pub fn trp_ctx_create(out: *mut *mut trp_ctx, device: c_int, curve: c_int) -> c_int;
-    pub fn trp_ctx_destroy(ctx: *mut trp_ctx);
-    pub fn trp_last_error(ctx: *const trp_ctx) -> *const c_char;
-    pub fn trp_ctx_sync(ctx: *mut trp_ctx) -> c_int;
-    pub fn trp_bases_load(ctx: *mut trp_ctx, affine_xy: *const u64, n: usize, out: *mut *mut trp_bases) -> c_int;
-    pub fn trp_bases_free(b: *mut trp_bases);
-    pub fn trp_msm(ctx: *mut trp_ctx, bases: *const trp_bases, scalars: *const u64, n: usize, out: *mut u64) -> c_int;
-    pub fn trp_msm_batch(ctx: *mut trp_ctx, bases: *const trp_bases, scalars: *const u64, n: usize, m: usize, out: *mut u64) -> c_int;
-    pub fn trp_ntt(ctx: *mut trp_ctx, a: *mut u64, batch: usize, log_n: c_uint, omega: *const u64) -> c_int;
-    pub fn trp_domain_create(ctx: *mut trp_ctx, k: c_uint, j: c_uint, out: *mut *mut trp_domain) -> c_int;
-    pub fn trp_domain_free(d: *mut trp_domain);
-    pub fn trp_lagrange_to_coeff(d: *mut trp_domain, cols: *mut u64, batch: usize) -> c_int;
-    pub fn trp_coeff_to_extended(d: *mut trp_domain, coeff: *const u64, ext: *mut u64, batch: usize) -> c_int;
-    pub fn trp_extended_to_coeff(d: *mut trp_domain, ext: *mut u64, out_coeff: *mut u64, divide: c_int) -> c_int;
-    pub fn trp_quotient_eval(d: *mut trp_domain, prog: *const u32, prog_len: usize, consts: *const u64, n_consts: usize,
-                             cols: *const *const u64, n_cols: usize, out_ext: *mut u64) -> c_int;
-    // rows f1-f3 of the scope table: the callers either side of the hot kernels (host-pointer forms)
-    pub fn trp_batch_invert(ctx: *mut trp_ctx, which_field: c_int, a: *mut u64, n: usize) -> c_int;
-    pub fn trp_permutation_product(d: *mut trp_domain, values: *const *const u64, sigmas: *const *const u64, m: usize, beta: *const u64,
-                                   gamma: *const u64, delta_beta: *const u64, last_z: *const u64, z: *mut u64) -> c_int;
-    pub fn trp_lookup_product(d: *mut trp_domain, input: *const u64, table: *const u64, perm_input: *const u64, perm_table: *const u64,
-                              beta: *const u64, gamma: *const u64, z: *mut u64, n_out: usize) -> c_int;
-    pub fn trp_permute_expression_pair(ctx: *mut trp_ctx, input: *const u64, table: *const u64, rows: usize, perm_input: *mut u64,
-                                       perm_table: *mut u64, all_found: *mut c_int) -> c_int;
-    pub fn trp_eval_polynomial(ctx: *mut trp_ctx, which_field: c_int, coeffs: *const u64, n: usize, x: *const u64, out: *mut u64) -> c_int;
-    // device-resident openings (include/tr_prover.h): m separately allocated polynomials at one point / one linear combination of them
-    pub fn trp_dev_eval_polynomials_at(ctx: *mut trp_ctx, which_field: c_int, d_poly_ptrs: *const *const u64, n: usize, m: usize, x: *const u64, d_out: *mut u64) -> c_int;
-    pub fn trp_dev_linear_combination(ctx: *mut trp_ctx, which_field: c_int, d_poly_ptrs: *const *const u64, scalars: *const u64, n: usize, m: usize, d_out: *mut u64) -> c_int;
-    pub fn trp_compute_inner_product(ctx: *mut trp_ctx, which_field: c_int, a: *const u64, b: *const u64, n: usize, out: *mut u64) -> c_int;
-    pub fn trp_kate_division(ctx: *mut trp_ctx, which_field: c_int, coeffs: *const u64, n: usize, b: *const u64, q: *mut u64) -> c_int;
-    /// Params::new(k): g, g_lagrange (2^k affine points each, 8 x u64), w, u
-    pub fn trp_params_new(ctx: *mut trp_ctx, k: c_uint, g: *mut u64, g_lagrange: *mut u64, w: *mut u64, u: *mut u64) -> c_int;
-    pub fn trp_hash_to_curve(ctx: *mut trp_ctx, domain_prefix: *const c_char, messages: *const u8, msg_len: usize, n: usize, out: *mut u64) -> c_int;
-    pub fn trp_group_fft(ctx: *mut trp_ctx, points: *mut u64, log_n: c_uint, omega: *const u64, scale: *const u64) -> c_int;
-}
+mod ffi;          // GENERATED from include/tr_prover.h by rust/gen_bindings.py: every entry point, argument for argument
+pub use ffi::*;
 
 /// One context per (device, curve); halo2 calls are synchronous, so a process-wide handle behind a mutex is enough.
 pub struct Backend { ctx: *mut trp_ctx }

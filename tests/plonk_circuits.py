@@ -38,3 +38,17 @@ def standard(PL, with_lookup=True, wide_lookup=False):
         copies = [((A, c, 1), (A, c, 3)), ((I, pi, 0), (A, c, 2)), ((A, c, 3), (A, c, 1))]
     instances = [[adv[2][2]]]
     return cs, fixed, copies, adv, instances
+
+
+class StandardCircuit:
+    """`standard` as a subject of tiny_ram_halo2_b200.test_utils (the role of the reference's gadget circuits LogicCircuit /
+    SumCircuit / ShiftCircuit in its gen_proofs_and_verify_should_fail tests, e.g. /root/reference/src/circuits/logic.rs:515-527:
+    the advice is assigned independently of the public input and one cell is copy-constrained to it, so a wrong input is caught by
+    the permutation argument).  The empty circuit (`C::default()`) has the same fixed columns."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def build(self, PL, k, public_input=None, keygen_from_empty_circuit=False):
+        cs, fixed, copies, adv, inst = standard(PL, **self.kw)
+        return cs, fixed, copies, adv, (inst if public_input is None else [list(c) for c in public_input])

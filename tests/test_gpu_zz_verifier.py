@@ -1,9 +1,8 @@
 """GPU test of the product's own verifier (tiny-ram-halo2_b200/verifier.py) over plonk.GpuBackend: the reference's
 gen_proofs_and_verify flow end to end on the device (/root/reference/src/test_utils.rs:6-71) -- Params::new, keygen, two
 proofs of the real TinyRamCircuit, BatchVerifier, then SingleVerifier proof by proof -- held against the oracle's independent
-verifier.  The file sorts last on purpose: GpuBackend.fixed_points / ipa_s_vector / msm_points were written after this round's
-GPU budget was spent, so their FIRST device run is the driver's; the test is a non-strict xfail until that run is seen (the
-verifier's logic itself is covered on the CPU by tests/test_verifier_cpu.py)."""
+verifier (the verifier's logic itself is covered on the CPU by tests/test_verifier_cpu.py).  First device run: the driver's
+round-1 GPU tier, where it passed; the xfail it carried until then is gone."""
 import random
 
 import pytest
@@ -17,7 +16,6 @@ pytestmark = pytest.mark.gpu
 C = pm.Vesta
 
 
-@pytest.mark.xfail(strict=False, reason="first device run of the verifier's three GpuBackend methods (written with no GPU minutes left)")
 def test_gen_proofs_and_verify_on_the_device():
     import __graft_entry__ as ge
     pkg = ge.load_package()
@@ -75,10 +73,26 @@ def test_gen_proofs_and_verify_on_the_device():
     def backend_of(k_, degree):
         made.append(PL.GpuBackend(ctx, k_, degree))
         return made[-1]
+    import plonk_circuits
+    from tiny_ram_halo2_b200.lookup import ConstraintSystemFailure
+    wrong = TR.program_instance([T.Answer(T.Imm(0))], W)
     try:
         out = TU.gen_proofs_and_verify(backend_of, W, traces)
         assert len(out) == 2 and made[0].k == 2 + W // 2
-        TU.gen_proofs_and_verify_should_fail(backend_of, W, traces[0], TR.program_instance([T.Answer(T.Imm(0))], W), k=6)
+        # keys from the first circuit itself: the execution table's selectors are ON, every exe gate and lookup is live
+        assert len(TU.gen_proofs_and_verify(backend_of, W, traces, keygen_from_empty_circuit=False)) == 2
+        # test_utils.rs:73-119, proved WITH the wrong input and checked against the same: a circuit that constrains its instance
+        std = plonk_circuits.StandardCircuit()
+        right = plonk_circuits.standard(PL)[4]
+        TU.gen_proofs_and_verify_should_fail(backend_of, 8, std, [[right[0][0] + 1]])
+        with pytest.raises(AssertionError, match="Erroneously verified proof"):
+            TU.gen_proofs_and_verify_should_fail(backend_of, 8, std, right)
+        # TinyRamCircuit with another program as its public input: the program table is assigned from the instance, and the
+        # execution table's program-line lookup (gated by the ADVICE selector s_trace, prog.rs:170-192, so it is live even with the
+        # reference's keys from the empty circuit) has no match: create_proof itself fails (halo2: "Failed to create proof")
+        for from_empty in (False, True):
+            with pytest.raises(ConstraintSystemFailure):
+                TU.gen_proofs_and_verify_should_fail(backend_of, W, traces[0], wrong, k=6, keygen_from_empty_circuit=from_empty)
     finally:
         for b in made:
             b.close()

@@ -158,3 +158,31 @@ def test_copy_blocks_are_swaps_only_when_nothing_else_touches_them(PL):
     assert got == want
     with pytest.raises(ValueError):
         PL._split_disjoint_blocks(cs, n, [PL.CopyBlock((A, cols[0], 60), (A, cols[1], 0), 8)])
+
+
+def test_copy_blocks_nested_in_a_wide_block_take_the_general_path(PL):
+    """a wide block overlaps blocks that are not its neighbours in sorted order (A = rows 0..100, B = 10..20, C = 50..60 of one
+    column): none of the three may become a device-side swap, and the result must equal the cycle merge of the expanded pairs"""
+    cs = PL.ConstraintSystem()
+    cols = [cs.advice_column() for _ in range(5)]
+    A = PL.ADVICE
+    for c in cols: cs.enable_equality(A, c)
+    n = 128
+    copies = [PL.CopyBlock((A, cols[0], 0), (A, cols[1], 0), 100),
+              PL.CopyBlock((A, cols[0], 10), (A, cols[2], 0), 10),
+              PL.CopyBlock((A, cols[0], 50), (A, cols[3], 0), 10),
+              PL.CopyBlock((A, cols[4], 0), (A, cols[4], 64), 32)]      # untouched by the others: stays a swap
+    want = PL.permutation_mapping(cs, n, copies)
+    pairs, blocks = PL._split_disjoint_blocks(cs, n, list(copies))
+    assert blocks == [(4, 0, 4, 64, 32)]
+    got = PL.permutation_mapping(cs, n, pairs)
+    for (i, r, i2, r2, rows) in blocks:
+        for t in range(rows):
+            assert (i, r + t) not in got and (i2, r2 + t) not in got
+            got[(i, r + t)], got[(i2, r2 + t)] = (i2, r2 + t), (i, r + t)
+    assert got == want
+    # a single pair inside the wide block, far from any block start
+    copies2 = [PL.CopyBlock((A, cols[0], 0), (A, cols[1], 0), 100), PL.CopyBlock((A, cols[2], 5), (A, cols[3], 5), 4),
+               ((A, cols[0], 77), (A, cols[4], 3))]
+    pairs2, blocks2 = PL._split_disjoint_blocks(cs, n, list(copies2))
+    assert blocks2 == [(2, 5, 3, 5, 4)]

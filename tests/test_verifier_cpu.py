@@ -191,8 +191,18 @@ def test_reference_test_utils_flow(mods):
     rand = lambda: rnd.randrange(C.scalar.p)
     proofs = TU.gen_proofs_and_verify(backend_of, 8, [TP.answer_only(T, 8), TP.load_and_answer(T, 8, 1, 2)], with_prog=False, rand=rand)
     assert len(proofs) == 2 and made[0].k == 6 and len(proofs[0]) == len(proofs[1])
-    # a proof checked against a public input the circuit does not have is rejected; the same proof against its own is not
-    tr = TP.answer_only(T, 8)
-    TU.gen_proofs_and_verify_should_fail(backend_of, 8, tr, [[1]], with_prog=False, rand=rand, k=6)
+    # test_utils.rs:73-119 with a circuit that CONSTRAINS its public input (one advice cell, assigned independently, is copied from
+    # it): proved with the wrong input and checked against the same input -> rejected by the permutation argument; with the
+    # right one the helper must complain
+    std = plonk_circuits.StandardCircuit()
+    right = plonk_circuits.standard(PL)[4]
+    TU.gen_proofs_and_verify_should_fail(backend_of, 8, std, [[right[0][0] + 1]], rand=rand)
+    assert made[-1].k == 5
     with pytest.raises(AssertionError, match="Erroneously verified proof"):
-        TU.gen_proofs_and_verify_should_fail(backend_of, 8, tr, [], with_prog=False, rand=rand, k=6)
+        TU.gen_proofs_and_verify_should_fail(backend_of, 8, std, right, rand=rand)
+    assert len(TU.gen_proofs_and_verify(backend_of, 6, [std, std], rand=rand, public_inputs=[right, right])) == 2
+    with pytest.raises(V.VerifyError):
+        TU.gen_proofs_and_verify(backend_of, 6, [std, std], rand=rand, public_inputs=[right, [[0]]])
+    # the wrong NUMBER of instance columns is create_proof's own error (halo2: Error::InvalidInstances -> "Failed to create proof")
+    with pytest.raises(ValueError, match="InvalidInstances"):
+        TU.gen_proofs_and_verify_should_fail(backend_of, 8, TP.answer_only(T, 8), [[1]], with_prog=False, rand=rand, k=6)

@@ -277,9 +277,15 @@ def _split_disjoint_blocks(cs: ConstraintSystem, n: int, copies):
             spans.append((col_of[(kind, col)], r0, r0 + b.rows, bi))
     spans.sort()
     shared = set()
-    for (c0, lo0, hi0, b0), (c1, lo1, hi1, b1) in zip(spans, spans[1:]):
-        if c0 == c1 and lo1 < hi0:
-            shared.update((b0, b1))
+    cur_col, max_hi, owner = None, 0, None     # interval sweep per column: the running maximum `hi` and the block that set it
+    for c, lo, hi, b in spans:                  # (a wide span overlaps spans that are not its neighbours in sorted order)
+        if c != cur_col:
+            cur_col, max_hi, owner = c, hi, b
+            continue
+        if lo < max_hi:
+            shared.update((owner, b))
+        if hi > max_hi:
+            max_hi, owner = hi, b
     if pairs and blocks:
         import bisect
         starts = [(c, lo) for c, lo, _, _ in spans]
