@@ -72,8 +72,11 @@ int trp_prof_get(trp_ctx* ctx, int phase, double* total_ms, uint64_t* count);
 int trp_bases_load(trp_ctx* ctx, const uint64_t* affine_xy /* n x 8 */, size_t n, trp_bases** out);
 int trp_dev_bases_load(trp_ctx* ctx, const uint64_t* d_affine_xy, size_t n, trp_bases** out);
 /* flags: bit 0 = keep one bucket set per window (no precomputed table), bit 1 = force the precomputed
- * table of 2^(c*w) * P_i multiples (default: precompute when the table fits the memory budget). */
+ * table of 2^(c*w) * P_i multiples (default: precompute when the table fits the memory budget), bits 8..15 = window width c
+ * (0 = the library's choice for n).  The same bases may be loaded more than once with different widths: a prover whose columns
+ * are mostly zero (TinyRAM advice: 2^16 assigned rows of 2^20) wants a narrow table for those and a wide one for dense columns. */
 int trp_bases_load_ex(trp_ctx* ctx, const uint64_t* affine_xy, size_t n, int flags, trp_bases** out);
+int trp_dev_bases_load_ex(trp_ctx* ctx, const uint64_t* d_affine_xy, size_t n, int flags, trp_bases** out);
 size_t trp_bases_len(const trp_bases* b);
 /* out = { window bits c, number of windows, 1 if the multiples were precomputed } */
 int trp_bases_describe(const trp_bases* b, unsigned out[3]);
@@ -142,6 +145,12 @@ int trp_dev_quotient_eval(trp_domain* d, const uint32_t* program /* host */, siz
                           const uint64_t* consts /* host, n_consts x 4 */, size_t n_consts,
                           const uint64_t* const* d_cols /* host array of n_cols DEVICE pointers */, size_t n_cols,
                           int coset, uint64_t* d_out /* device, 2^extended_k x 4 */);
+/* The same over a SLICE of a coset's rows (SURVEY.md 8(e) item 3 refined: a coset's rows are split between the GPUs so that j - 1
+ * cosets load any number of devices evenly): the columns hold rows [row0 - halo_before, row0 + nrows + halo_after) of coset j
+ * (cyclic neighbours included by the caller), rotations must stay within the halo, d_out receives the nrows results contiguously. */
+int trp_dev_quotient_eval_rows(trp_domain* d, const uint32_t* program, size_t n_instr, unsigned n_regs, const uint64_t* consts,
+                               size_t n_consts, const uint64_t* const* d_cols, size_t n_cols, unsigned coset, size_t row0, size_t nrows,
+                               unsigned halo_before, unsigned halo_after, uint64_t* d_out /* device, nrows x 4 */);
 int trp_quotient_eval(trp_domain* d, const uint32_t* program, size_t n_instr, unsigned n_regs, const uint64_t* consts,
                       size_t n_consts, const uint64_t* const* cols /* n_cols HOST pointers, 2^extended_k x 4 each */,
                       size_t n_cols, uint64_t* out_ext /* host, 2^extended_k x 4 */);

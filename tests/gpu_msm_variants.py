@@ -1,16 +1,16 @@
-"""Ad-hoc (not a test): A/B of the opt-in MSM kernel variants against the default path on one B200.
+"""Ad-hoc (not a test): A/B of the MSM kernel variants on one B200 (results: profiles/msm_variants_r02.md).
 
-Each variant runs in its own process (the switches are read once per process): 8 columns x (2^K + 1) Vesta points, uniform
-scalars, device resident (bench.py's step), 5 timed steps with CUDA events; the normalised results must be byte-identical.
+Each variant runs in its own process (the switches are read once per process): B columns x (2^K + 1) Vesta points, device
+resident (bench.py's step), 5 timed steps with CUDA events; the normalised results must be byte-identical across variants.
 
-  python tests/gpu_msm_variants.py            # K = 20
-  K=16 python tests/gpu_msm_variants.py
+  python tests/gpu_msm_variants.py                  # K = 20, B = 8, uniform scalars
+  K=22 B=4 python tests/gpu_msm_variants.py
+  SHAPE=tinyram python tests/gpu_msm_variants.py    # 90 % {0,1}, 8 % < 2^32, 2 % uniform
+  SHAPE=sparse16 python tests/gpu_msm_variants.py   # what a real advice column looks like: tinyram-shaped values on the first 2^16
+                                                    # rows (the execution table), zero elsewhere, 6 uniform blinding rows at the end
 
-Variants: TRP_MSM_CALL=1 (field multiplication out of line in the level-1 accumulation), TRP_MSM_C=17..20 (wider windows: fewer
-bucket additions per scalar, more buckets to reduce) and TRP_MSM_REDUCE=2 (the two-level weighted bucket sum of
-csrc/bucket_reduce.cuh, which is what makes the wider windows affordable) and TRP_MSM_SEG=1 (level-1 tasks as aligned windows
-of the sorted entry list: no partial tasks, whatever the bucket sizes) -- DESIGN.md section 9.  K=22 / K=24 are where wider windows
-should pay most (set B=4 / B=1 columns to stay inside the scratch budget)."""
+Switches: TRP_MSM_SEG=0 (per-bucket level-1 tasks instead of aligned windows of the sorted entry list), TRP_MSM_C=c (window
+width), TRP_MSM_REDUCE=1/2 (one doubling chain per chunk / the two-level weighted bucket sum of csrc/bucket_reduce.cuh)."""
 import hashlib
 import json
 import os
@@ -18,11 +18,33 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-VARIANTS = ([("default", {}), ("fe_mul out of line", {"TRP_MSM_CALL": "1"}), ("two-level reduction", {"TRP_MSM_REDUCE": "2"})]
-            + [(f"c = {c}", {"TRP_MSM_C": str(c)}) for c in (17, 18, 19, 20)]
-            + [(f"c = {c}, two-level reduction", {"TRP_MSM_C": str(c), "TRP_MSM_REDUCE": "2"}) for c in (18, 19, 20)]
-            + [("segmented level 1", {"TRP_MSM_SEG": "1"})]
-            + [(f"c = {c}, segmented, two-level", {"TRP_MSM_C": str(c), "TRP_MSM_SEG": "1", "TRP_MSM_REDUCE": "2"}) for c in (18, 19, 20)])
+VARIANTS = ([("default", {}), ("per-bucket level-1 tasks", {"TRP_MSM_SEG": "0"})]
+            + [(f"c = {c}", {"TRP_MSM_C": str(c)}) for c in (13, 14, 15, 16, 17, 18, 19, 20, 21)]
+            + [(f"c = {c}, chunk-chain reduction", {"TRP_MSM_C": str(c), "TRP_MSM_REDUCE": "1"}) for c in (18,)]
+            + [(f"c = {c}, two-level reduction", {"TRP_MSM_C": str(c), "TRP_MSM_REDUCE": "2"}) for c in (16, 17)])
+
+
+def make_scalars(n, m, shape, seed=20):
+    """(m, n, 4) uint64 limbs + whether they are canonical small values that still need the Montgomery factor"""
+    import numpy as np
+    from tiny_ram_halo2_b200 import synthetic
+    if shape == "uniform":
+        return synthetic.random_scalars(n, seed, m), False
+    rng = np.random.Generator(np.random.PCG64(seed))
+    rows = n if shape == "tinyram" else (1 << 16)
+    a = np.zeros((m, n, 4), dtype=np.uint64)
+    kind = rng.random((m, rows))
+    a[:, :rows, 0] = np.where(kind < 0.9, rng.integers(0, 2, size=(m, rows), dtype=np.uint64),
+                              rng.integers(0, 1 << 32, size=(m, rows), dtype=np.uint64))
+    wide = kind >= 0.98
+    u = rng.integers(0, 1 << 64, size=(m, rows, 4), dtype=np.uint64)
+    u[..., 3] &= np.uint64((1 << 62) - 1)
+    a[:, :rows][wide] = u[wide]
+    if shape == "sparse16":
+        tail = rng.integers(0, 1 << 64, size=(m, 7, 4), dtype=np.uint64)       # blinding rows + the blind's slot
+        tail[..., 3] &= np.uint64((1 << 62) - 1)
+        a[:, n - 7:] = tail
+    return a, True
 
 
 def child():
@@ -44,7 +66,15 @@ def child():
     synthetic.device_points(ctx, n, d_pts.data_ptr())
     hb = ctypes.c_void_p()
     ctx.check(lib.trp_dev_bases_load(ctx.handle, d_pts.data_ptr(), n, ctypes.byref(hb)))
-    d_scalars = torch.from_numpy(synthetic.random_scalars(n, 20, m).view(np.int64)).cuda()
+    host, canonical = make_scalars(n, m, os.environ.get("SHAPE", "uniform"))
+    d_scalars = torch.from_numpy(host.view(np.int64)).cuda()
+    if canonical:                                   # canonical values -> Montgomery form: multiply by R^2 on the device
+        R2 = np.array([(pow(2, 512, 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001) >> (64 * i)) & (2**64 - 1)
+                       for i in range(4)], dtype=np.uint64)
+        d_r2 = torch.from_numpy(R2.view(np.int64)).cuda()
+        torch.cuda.synchronize()
+        ctx.check(lib.trp_dev_field_op(ctx.handle, 0, 2 | 16, d_scalars.data_ptr(), d_r2.data_ptr(), d_scalars.data_ptr(), m * n))
+        ctx.sync()
     d_out = torch.zeros((m, 12), dtype=torch.int64, device="cuda")
     ctx.prof_reset(); ctx.prof_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -201,45 +201,102 @@ def test_sharded_commitments_give_the_same_proof_world2_gloo():
     assert res[0][2] == res[1][2]
 
 
-def _coset_exchange_worker(rank, world, port, ncos, q):
-    """sharded_backend.ShardedGpuBackend's coset partition (which cosets a rank evaluates, how the results are exchanged), run
-    over gloo on CPU tensors with the device-specific parts stubbed out"""
-    import types
+def _row_exchange_worker(rank, world, port, q):
+    """the round-2 partitions of sharded_backend.ShardedGpuBackend over gloo on CPU tensors: block ownership + in-place
+    all_gather, the row-slice pack + all-to-all of the quotient, the chunk prefixes of the permutation argument, ShardedRng"""
     import torch
     import torch.distributed as dist
     import __graft_entry__ as ge
     ge.load_package()
-    from tiny_ram_halo2_b200 import sharded_backend as SB
+    from tiny_ram_halo2_b200 import parallel as PL, sharded_backend as SB
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        fake = types.SimpleNamespace(dist=dist, torch=torch, _sync=lambda: None)
-        mine = SB.ShardedGpuBackend._my_cosets(fake, ncos)
-        n = 16
-        want = torch.arange(ncos * n * 4, dtype=torch.int64).reshape(ncos, n, 4)
-        vals = torch.zeros_like(want)
-        for cs in mine:
-            vals[cs] = want[cs]                                 # this rank "evaluated" only its own cosets
-        got = SB.ShardedGpuBackend._exchange_cosets(fake, vals, mine)
+        ok = True
+        # 1. blocks + in-place all_gather: 7 columns, rank r fills its block only
+        n, ncols = 32, 7
+        want = torch.arange(ncols * n * 4, dtype=torch.int64).reshape(ncols, n, 4)
+        per, lo, hi = PL.block_range(ncols, world, rank)
+        buf = torch.full((per * world, n, 4), -1, dtype=torch.int64)
+        buf[lo:hi] = want[lo:hi]
+        PL.all_gather_blocks_inplace(buf, per, dist)
+        ok &= bool(torch.equal(buf[:ncols], want))
+        # 2. the quotient's exchange: every rank ends up with rows [row0 - H, row0 + S + H) (cyclic) of EVERY column
+        H = 3
+        row0, S = PL.row_slice_bounds(n, world, rank)
+        own = torch.zeros((max(per, 1), n, 4), dtype=torch.int64)
+        own[:hi - lo] = want[lo:hi]
+        send = torch.full((world, max(per, 1), S + 2 * H, 4), -7, dtype=torch.int64)
+        recv = torch.empty_like(send)
+        PL.pack_row_slices(own, hi - lo, n, world, H, H, send)
+        PL.exchange_row_slices(send, recv, dist)
+        flat = recv.view(world * max(per, 1), S + 2 * H, 4)
+        rows = (torch.arange(S + 2 * H) + row0 - H) % n
+        for c in range(ncols):
+            ok &= bool(torch.equal(flat[c], want[c][rows]))
+        # 3. ShardedRng: one stream on every rank, seeded by rank 0
+        p = 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001
+        rng = SB.ShardedRng(p, dist, "cpu")
+        mine = ([rng() for _ in range(5)], rng.vector(4).tolist(), rng.seed)
         every = [None] * world
         dist.all_gather_object(every, mine)
-        covered = sorted(c for m in every for c in m)
-        q.put((rank, bool(torch.equal(got, want)) and got.is_contiguous(), covered == list(range(ncos))))
+        ok &= all(e == every[0] for e in every) and all(0 <= v < p for v in mine[0]) and len(set(mine[0])) == 5
+        q.put((rank, ok))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,ncos", [(2, 5), (3, 5), (2, 1)])
-def test_coset_partition_and_exchange_gloo(world, ncos):
+@pytest.mark.parametrize("world", [2, 4])
+def test_round2_partitions_gloo(world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_coset_exchange_worker, args=(r, world, port, ncos, q)) for r in range(world)]
+    procs = [ctx.Process(target=_row_exchange_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert all(r[1] and r[2] for r in res), res
+    assert all(r[1] for r in res), res
+
+
+def test_chunk_prefixes_reproduce_the_chained_products():
+    """chunk i computed from 1 and scaled by the product of the earlier chunks' ends == the chain z_i[0] = z_{i-1}[u]"""
+    import random
+    import __graft_entry__ as ge
+    ge.load_package()
+    from tiny_ram_halo2_b200 import parallel as PL
+    p = 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001
+    rnd = random.Random(9)
+    u, chunks = 10, 4
+    ratios = [[rnd.randrange(1, p) for _ in range(u)] for _ in range(chunks)]
+    chained, start = [], 1
+    for r in ratios:
+        z = [start]
+        for x in r:
+            z.append(z[-1] * x % p)
+        chained.append(z); start = z[u]
+    local = []
+    for r in ratios:
+        z = [1]
+        for x in r:
+            z.append(z[-1] * x % p)
+        local.append(z)
+    pref = PL.chunk_prefixes([z[u] for z in local], p)
+    assert [[pref[i] * v % p for v in local[i]] for i in range(chunks)] == chained
+    assert PL.block_range(47, 8, 7) == (6, 42, 47) and PL.block_range(5, 8, 6) == (1, 5, 5) and PL.block_range(0, 2, 1) == (0, 0, 0)
+
+
+def test_sharded_rng_is_a_seeded_stream():
+    import __graft_entry__ as ge
+    ge.load_package()
+    from tiny_ram_halo2_b200 import sharded_backend as SB
+    p = 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001
+    a, b, c = SB.ShardedRng(p, seed=b"\x01" * 32), SB.ShardedRng(p, seed=b"\x01" * 32), SB.ShardedRng(p, seed=b"\x02" * 32)
+    xs = [a() for _ in range(4)]
+    assert xs == [b() for _ in range(4)] != [c() for _ in range(4)]
+    v = a.vector(8)
+    assert v.shape == (8, 4) and (v == b.vector(8)).all() and int(v[:, 3].max()) < 1 << 62
+    assert len(SB.ShardedRng(p).seed) == 32           # OS seed by default

@@ -20,13 +20,13 @@ _ERR_NAMES = {-1: "TRP_E_INVALID", -2: "TRP_E_CUDA", -3: "TRP_E_OOM", -4: "TRP_E
 EXPORTED_SYMBOLS = [
     "trp_ctx_create", "trp_ctx_destroy", "trp_last_error", "trp_ctx_set_stream", "trp_ctx_sync",
     "trp_ctx_launch_count", "trp_version", "trp_prof_enable", "trp_prof_reset", "trp_prof_get",
-    "trp_bases_load", "trp_dev_bases_load", "trp_bases_load_ex", "trp_bases_len", "trp_bases_describe", "trp_bases_free",
+    "trp_bases_load", "trp_dev_bases_load", "trp_bases_load_ex", "trp_dev_bases_load_ex", "trp_bases_len", "trp_bases_describe", "trp_bases_free",
     "trp_msm", "trp_msm_batch", "trp_dev_msm_batch", "trp_dev_points_progression", "trp_points_sum", "trp_dev_points_sum",
     "trp_ntt", "trp_dev_ntt",
     "trp_domain_create", "trp_domain_free", "trp_domain_extended_k", "trp_domain_constants",
     "trp_lagrange_to_coeff", "trp_dev_lagrange_to_coeff", "trp_coeff_to_lagrange",
     "trp_coeff_to_extended", "trp_dev_coeff_to_extended", "trp_extended_to_coeff", "trp_dev_extended_to_coeff",
-    "trp_dev_quotient_eval", "trp_quotient_eval", "trp_dev_coeff_to_coset", "trp_dev_cosets_to_coeff",
+    "trp_dev_quotient_eval", "trp_dev_quotient_eval_rows", "trp_quotient_eval", "trp_dev_coeff_to_coset", "trp_dev_cosets_to_coeff",
     "trp_field_op", "trp_dev_field_op", "trp_microbench",
     "trp_dev_batch_invert", "trp_batch_invert", "trp_dev_grand_product", "trp_grand_product",
     "trp_dev_permutation_product", "trp_permutation_product", "trp_dev_lookup_product", "trp_lookup_product",
@@ -82,6 +82,7 @@ def load_library():
     L.trp_bases_load.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
     L.trp_dev_bases_load.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
     L.trp_bases_load_ex.argtypes = [vp, vp, sz, i, ctypes.POINTER(vp)]
+    L.trp_dev_bases_load_ex.argtypes = [vp, vp, sz, i, ctypes.POINTER(vp)]
     L.trp_bases_len.argtypes = [vp]; L.trp_bases_len.restype = sz
     L.trp_bases_describe.argtypes = [vp, vp]
     L.trp_bases_free.argtypes = [vp]; L.trp_bases_free.restype = None
@@ -105,6 +106,7 @@ def load_library():
     L.trp_extended_to_coeff.argtypes = [vp, vp, vp, i]
     L.trp_dev_extended_to_coeff.argtypes = [vp, vp, vp, i]
     L.trp_dev_quotient_eval.argtypes = [vp, vp, sz, u, vp, sz, vp, sz, i, vp]
+    L.trp_dev_quotient_eval_rows.argtypes = [vp, vp, sz, u, vp, sz, vp, sz, u, sz, sz, u, u, vp]
     L.trp_quotient_eval.argtypes = [vp, vp, sz, u, vp, sz, vp, sz, vp]
     L.trp_dev_coeff_to_coset.argtypes = [vp, vp, vp, sz, u]
     L.trp_dev_cosets_to_coeff.argtypes = [vp, vp, u, vp, i]

@@ -209,7 +209,14 @@ int trp_dev_bases_load(trp_ctx* ctx, const uint64_t* d_affine_xy, size_t n, trp_
   if (n && !d_affine_xy) TRP_FAIL(ctx, TRP_E_INVALID, "d_affine_xy is NULL");
   return trp_bases_create(ctx, d_affine_xy, true, n, 0, out);
 }
-// flags: bit 0 = keep per-window bucket sets (no precomputed table), bit 1 = force the precomputed table
+// flags: bit 0 = keep per-window bucket sets (no precomputed table), bit 1 = force the precomputed table, bits 8..15 = window
+// width c (0 = the library's choice for n)
+int trp_dev_bases_load_ex(trp_ctx* ctx, const uint64_t* d_affine_xy, size_t n, int flags, trp_bases** out) {
+  if (!ctx) return TRP_E_INVALID;
+  Locked l(ctx);
+  if (n && !d_affine_xy) TRP_FAIL(ctx, TRP_E_INVALID, "d_affine_xy is NULL");
+  return trp_bases_create(ctx, d_affine_xy, true, n, flags, out);
+}
 int trp_bases_load_ex(trp_ctx* ctx, const uint64_t* affine_xy, size_t n, int flags, trp_bases** out) {
   if (!ctx) return TRP_E_INVALID;
   Locked l(ctx);

@@ -76,6 +76,9 @@ __device__ __forceinline__ void for_each_digit(const uint4* scalars, size_t i, s
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = 0;
   }
+  // a warp whose 32 scalars are all zero has nothing to sort (TinyRAM advice columns are zero outside the 2^16-row tables:
+  // 94 % of the warps at k = 20); the exit is warp-uniform, so the collectives inside f stay converged
+  if (!__any_sync(0xffffffffu, (v[0] | v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7]) != 0)) return;
   unsigned carry = 0;
   const unsigned half = 1u << (g.c - 1);
   for (unsigned w = 0; w < g.W; ++w) {
@@ -172,61 +175,13 @@ __global__ void __launch_bounds__(ACC_THREADS) msm_accum_l1_kernel(const uint32_
   store_xyzz(partials + 8 * (size_t)t, acc);
 }
 
-// UNMEASURED EXPERIMENT (TRP_MSM_CALL=1): the same level-1 task with the field multiplication OUT OF LINE.
-// The inlined loop body of msm_accum_l1_kernel is 72 KB of SASS (10 + 7 multiplications of ~3.8 KB each), beyond the 32 KB
-// L1.5 instruction cache, and ncu shows stall_no_instruction at 1.26 cycles per issue; with calls the loop is ~18 KB.  The
-// price is ~36 register moves per call (the ABI passes both operands in registers, no stack).  Same arithmetic, same result.
-template <class PR> __device__ __noinline__ Fe<PR> fe_mul_call(Fe<PR> a, Fe<PR> b) { return fe_mul(a, b); }
-template <class PR> __device__ __noinline__ XYZZ<PR> xyzz_dbl_affine_call(Affine<PR> q) { return xyzz_dbl_affine(q); }
-
-template <class PR> __device__ __forceinline__ void xyzz_add_mixed_call(XYZZ<PR>& p, const Affine<PR>& q) {   // ec.cuh xyzz_add_mixed
-  if (affine_is_identity(q)) return;
-  if (xyzz_is_identity(p)) { p.x = q.x; p.y = q.y; p.zz = fe_one<PR>(); p.zzz = fe_one<PR>(); return; }
-  Fe<PR> u2 = fe_mul_call(q.x, p.zz);
-  Fe<PR> s2 = fe_mul_call(q.y, p.zzz);
-  Fe<PR> pp_ = fe_sub(u2, p.x);
-  Fe<PR> r = fe_sub(s2, p.y);
-  if (fe_is_zero(pp_)) {
-    if (fe_is_zero(r)) p = xyzz_dbl_affine_call(q);
-    else p = xyzz_identity<PR>();
-    return;
-  }
-  Fe<PR> pp = fe_mul_call(pp_, pp_);
-  Fe<PR> ppp = fe_mul_call(pp_, pp);
-  Fe<PR> qv = fe_mul_call(p.x, pp);
-  Fe<PR> x3 = fe_sub(fe_sub(fe_mul_call(r, r), ppp), fe_dbl(qv));
-  Fe<PR> y3 = fe_sub(fe_mul_call(r, fe_sub(qv, x3)), fe_mul_call(p.y, ppp));
-  p.x = x3; p.y = y3;
-  p.zz = fe_mul_call(p.zz, pp);
-  p.zzz = fe_mul_call(p.zzz, ppp);
-}
-
-template <class BPR>
-__global__ void __launch_bounds__(ACC_THREADS) msm_accum_l1_call_kernel(const uint32_t* entries, const uint32_t* in_off,
-                                                                      const uint32_t* task_off, unsigned nb,
-                                                                      const uint4* bases, uint4* partials) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= __ldg(task_off + nb)) return;
-  unsigned b = find_segment(task_off, nb, t);
-  uint32_t j = t - __ldg(task_off + b);
-  uint32_t start = __ldg(in_off + b) + j * L1;
-  uint32_t end = min(start + L1, __ldg(in_off + b + 1));
-  XYZZ<BPR> acc = xyzz_identity<BPR>();
-  for (uint32_t e = start; e < end; ++e) {
-    uint32_t ent = __ldg(entries + e);
-    Affine<BPR> p = load_affine<BPR>(bases, ent & 0x7fffffffu);
-    if (ent >> 31) p.y = fe_neg(p.y);
-    xyzz_add_mixed_call(acc, p);
-  }
-  store_xyzz(partials + 8 * (size_t)t, acc);
-}
-
-// UNMEASURED EXPERIMENT (TRP_MSM_SEG=1): level-1 tasks cut the SORTED ENTRY LIST into aligned windows of L1
-// entries instead of cutting every bucket into tasks of its own, so every thread of a warp performs exactly L1 additions
-// whatever the bucket sizes are (today the last task of a bucket is partial: ~6 % idle lanes at 512 entries per bucket, ~30 % at
-// the 26 entries per bucket of c = 20).  A thread emits one partial per bucket its window meets: bucket b's partials are the
-// slots pbase[b] + (t - off[b] / L1), pbase = the scan of scan_input mode 2, which is exactly the per-bucket layout the upper
-// levels read.
+// DEFAULT level 1 since round 2 (TRP_MSM_SEG=0 selects msm_accum_l1_kernel above): tasks cut the SORTED ENTRY LIST into aligned
+// windows of L1 entries instead of cutting every bucket into tasks of its own, so every thread of a warp performs exactly L1
+// additions whatever the bucket sizes are (per-bucket tasks leave the last task of a bucket partial: ~6 % idle lanes at 512
+// entries per bucket, ~30 % at the 26 entries per bucket of c = 20).  A thread emits one partial per bucket its window meets:
+// bucket b's partials are the slots pbase[b] + (t - off[b] / L1), pbase = the scan of scan_input mode 2, which is exactly the
+// per-bucket layout the upper levels read.  Measured on B200 (profiles/msm_variants_r02.md): 8 x 2^20 uniform, c = 16:
+// accumulate 22.2 -> 21.3 ms; it is what makes wider windows pay (c = 20: 25.0 -> 18.0 ms).
 template <class BPR>
 __global__ void __launch_bounds__(ACC_THREADS) msm_accum_l1_seg_kernel(const uint32_t* entries, const uint32_t* off, const uint32_t* pbase,
                                                                      unsigned nb, const uint4* bases, uint4* partials) {
@@ -331,9 +286,11 @@ __global__ void __launch_bounds__(256) msm_reduce_sets_kernel(const uint4* chunk
   }
 }
 
-// UNMEASURED EXPERIMENT (TRP_MSM_REDUCE=2; the arithmetic is bucket_reduce.cuh, host-tested): chunks emit
-// their own weighted sum AND their total; the per-set kernel turns the totals into sum_ch ch * tot_ch by running sums inside a
-// thread's run of chunks and a (sum, weighted sum) tree across threads, instead of one doubling chain per chunk.
+// Two-level reduction (the arithmetic is bucket_reduce.cuh, host-tested; default for c >= 18, TRP_MSM_REDUCE=1/2 forces one
+// or the other): chunks emit their own weighted sum AND their total; the per-set kernel turns the totals into sum_ch ch * tot_ch
+// by running sums inside a thread's run of chunks and a (sum, weighted sum) tree across threads, instead of one doubling chain
+// per chunk.  Measured (profiles/msm_variants_r02.md, 8 x 2^20): c = 16 0.63 -> 1.22 ms (worse: few chunks per set), c = 18
+// 1.86 -> 1.77, c = 20 8.33 -> 3.95 ms.
 constexpr unsigned LOG_RED_S = 4;            // RED_S = 16
 constexpr int RED2_THREADS = 128;
 static_assert((1u << LOG_RED_S) == RED_S, "LOG_RED_S");
@@ -509,20 +466,27 @@ __global__ void __launch_bounds__(128) points_progression_kernel(Affine<BPR> p0,
   }
 }
 
-unsigned choose_c(size_t n) {
+// Window width.  Measured on B200 with the segmented level 1 (profiles/msm_variants_r02.md, 8 columns per batch):
+//   n = 2^20 uniform scalars:  c = 16 26.2 ms, c = 17 24.8 ms (best), c = 18 26.0, c = 20 28.1
+//   n = 2^22 uniform (4 columns): c = 16 51.0 ms, c = 18 47.5, c = 20 44.9 (best measured)
+//   n = 2^20, columns that are zero outside 2^16 rows (TinyRAM advice): c = 13 2.17 ms (best), c = 16 2.7, c = 17 3.3 -- the
+//   bucket reduction's 2^(c-1) buckets per column are all that is left there, so callers that know their columns are sparse
+//   ask for a narrow table (flags bits 8..15 of trp_bases_load_ex / trp_dev_bases_load_ex).
+unsigned choose_c(size_t n, unsigned requested = 0) {
   unsigned lg = 0;
   while (((size_t)2 << lg) <= n) ++lg;   // floor(log2 n) for n >= 1
   int c = (int)lg - 4;
   if (c < 4) c = 4;
   if (c > 16) c = 16;
-  // the default stops at 16 (best of the widths measured at 8 x 2^20, round 1); 17..22 are accepted from the environment for
-  // the sweep of DESIGN.md section 9 (fewer windows per scalar against 2^(c-1) buckets per column to reduce)
-  if (const char* e = getenv("TRP_MSM_C")) { int v = atoi(e); if (v >= 2 && v <= 22) c = v; }
+  if (lg >= 20) c = 17 + (int)(3 * (lg - 20)) / 2;      // 2^20: 17, 2^21: 18, 2^22: 20, 2^23: 21, 2^24: 23 -> capped
+  if (c > 22) c = 22;
+  if (requested >= 2 && requested <= 22) c = (int)requested;
+  else if (const char* e = getenv("TRP_MSM_C")) { int v = atoi(e); if (v >= 2 && v <= 22) c = v; }     // the A/B sweep
   return (unsigned)c;
 }
 
-bool seg_mode() {      // TRP_MSM_SEG=1: the segmented level-1 tasks (msm_accum_l1_seg_kernel)
-  static const bool on = [] { const char* e = getenv("TRP_MSM_SEG"); return e && atoi(e) == 1; }();
+bool seg_mode() {      // the segmented level-1 tasks (msm_accum_l1_seg_kernel) unless TRP_MSM_SEG=0
+  static const bool on = [] { const char* e = getenv("TRP_MSM_SEG"); return !(e && atoi(e) == 0); }();
   return on;
 }
 
@@ -595,13 +559,9 @@ int msm_chunk(trp_ctx* ctx, const trp_bases_impl* bs, const uint4* d_scalars, si
   {
     ProfScope ps(ctx, PROF_MSM_ACCUM_L1);
     unsigned gridl1 = (unsigned)((level_tasks[0] + ACC_THREADS - 1) / ACC_THREADS);
-    static const bool out_of_line = [] { const char* e = getenv("TRP_MSM_CALL"); return e && atoi(e) == 1; }();
     if (segmented)
       msm_accum_l1_seg_kernel<BPR><<<(unsigned)(((M + L1 - 1) / L1 + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(
           w.entries, w.offsets, w.task_off[0], (unsigned)NB, (const uint4*)bs->pub.d_xy, w.part[0]);
-    else if (out_of_line)
-      msm_accum_l1_call_kernel<BPR><<<gridl1, ACC_THREADS, 0, ctx->stream>>>(w.entries, w.offsets, w.task_off[0], (unsigned)NB,
-                                                                            (const uint4*)bs->pub.d_xy, w.part[0]);
     else
       msm_accum_l1_kernel<BPR><<<gridl1, ACC_THREADS, 0, ctx->stream>>>(w.entries, w.offsets, w.task_off[0], (unsigned)NB,
                                                                        (const uint4*)bs->pub.d_xy, w.part[0]);
@@ -623,7 +583,8 @@ int msm_chunk(trp_ctx* ctx, const trp_bases_impl* bs, const uint4* d_scalars, si
     unsigned chunks_per_set = g.B / RED_S ? g.B / RED_S : 1;
     unsigned total_sets = (unsigned)(g.nsets * mc);
     unsigned nchunks = total_sets * chunks_per_set;
-    static const bool two_level = [] { const char* e = getenv("TRP_MSM_REDUCE"); return e && atoi(e) == 2; }();
+    static const int reduce_env = [] { const char* e = getenv("TRP_MSM_REDUCE"); return e ? atoi(e) : 0; }();
+    const bool two_level = reduce_env == 2 || (reduce_env != 1 && g.c >= 18);
     if (two_level && g.B >= RED_S * (unsigned)RED2_THREADS) {
       // chunks per set = RED2_THREADS * 2^log_m * 2^log_g: at most 4 chunks per thread, the rest as blocks (B is a power of two)
       unsigned log_cps = 0;
@@ -677,7 +638,7 @@ int trp_bases_create(trp_ctx* ctx, const void* src, bool src_on_device, size_t n
   trp_bases_impl* b = new trp_bases_impl();
   b->pub.ctx = ctx; b->pub.n = n; b->pub.d_xy = nullptr;
   MsmGeom& g = b->g;
-  g.c = choose_c(n ? n : 1);
+  g.c = choose_c(n ? n : 1, ((unsigned)flags >> 8) & 0xff);
   g.W = (256 + g.c - 1) / g.c;
   g.B = 1u << (g.c - 1);
   g.stride = n;
@@ -686,6 +647,9 @@ int trp_bases_create(trp_ctx* ctx, const void* src, bool src_on_device, size_t n
   bool precomp = (flags & 1) ? false : ((flags & 2) ? true : (n * 64 * g.W <= budget));
   if ((size_t)g.W * n >= ((size_t)1 << 31)) precomp = false;
   if (n == 0 || g.W > PRECOMP_MAX_W) precomp = false;
+  if (!precomp && !(((unsigned)flags >> 8) & 0xff) && g.c > 16) {      // W separate bucket sets: the widths above 16 were
+    g.c = 16; g.W = (256 + g.c - 1) / g.c; g.B = 1u << (g.c - 1);          // measured with ONE shared set (precomputed table)
+  }
   g.precomp = precomp ? 1 : 0;
   g.nsets = precomp ? 1 : g.W;
   g.nb = g.nsets * g.B;
@@ -784,6 +748,7 @@ static trp_bases_impl transient_bases(trp_ctx* ctx, const void* d_xy, size_t n) 
   b.pub.ctx = ctx; b.pub.n = n; b.pub.d_xy = const_cast<void*>(d_xy);
   MsmGeom& g = b.g;
   g.c = choose_c(n ? n : 1);
+  if (g.c > 16) g.c = 16;                 // W separate bucket sets here: the widths above 16 were measured with ONE shared set
   g.W = (256 + g.c - 1) / g.c;
   g.B = 1u << (g.c - 1);
   g.stride = n;

@@ -39,6 +39,9 @@ struct QParams {
   const uint4* consts;
   const uint4* const* cols;
   unsigned rows_log, step, out_stride, out_off, x_stride, x_off, ext_log;
+  // row-slice mode (nrows > 0): the columns hold rows [row0 - halo_before, row0 + nrows + halo_after) of the coset (cyclic
+  // neighbours copied in by the caller), thread t evaluates coset row row0 + t and stores out[t]
+  unsigned row0, nrows, halo_before;
   const uint4* tw_ext;   // ext_omega^i, i < 2^(ext_log-1)
   uint4* out;
 };
@@ -48,9 +51,11 @@ __global__ void __launch_bounds__(128) quotient_vm_kernel(QParams p, Fe<PR> zeta
   extern __shared__ uint4 smem[];
   uint4* plane0 = smem;
   uint4* plane1 = smem + (size_t)p.n_regs * blockDim.x;
-  const unsigned rows = 1u << p.rows_log;
+  const bool slice = p.nrows != 0;
+  const unsigned rows = slice ? p.nrows : 1u << p.rows_log;
   const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned row = gid & (rows - 1);          // rows < blockDim: surplus threads recompute a valid row, never store
+  // surplus threads of the last block recompute a valid row and never store
+  const unsigned row = slice ? (gid < rows ? gid : rows - 1) : (gid & (rows - 1));
   const bool live = gid < rows;
   const unsigned tid = threadIdx.x, bd = blockDim.x;
   auto rd = [&](unsigned reg) -> Fe<PR> {
@@ -67,7 +72,8 @@ __global__ void __launch_bounds__(128) quotient_vm_kernel(QParams p, Fe<PR> zeta
     const uint4 ins = __ldg(p.prog + pc);
     switch (ins.x) {
       case Q_LOAD: {
-        unsigned idx = (row + (unsigned)((int)ins.w * (int)p.step)) & (rows - 1);
+        unsigned idx = slice ? (unsigned)((int)(row + p.halo_before) + (int)ins.w)
+                             : ((row + (unsigned)((int)ins.w * (int)p.step)) & (rows - 1));
         const uint4* col = p.cols[ins.z];
         wr(ins.y, fe_load<PR>(col + 2 * (size_t)idx));
         break;
@@ -80,7 +86,7 @@ __global__ void __launch_bounds__(128) quotient_vm_kernel(QParams p, Fe<PR> zeta
       case Q_SQR: wr(ins.y, fe_sqr(rd(ins.z))); break;
       case Q_DBL: wr(ins.y, fe_dbl(rd(ins.z))); break;
       case Q_COSETX: {
-        unsigned g = row * p.x_stride + p.x_off;
+        unsigned g = (row + p.row0) * p.x_stride + p.x_off;
         unsigned half = 1u << (p.ext_log - 1);
         Fe<PR> w = fe_load_ro<PR>(p.tw_ext + 2 * (size_t)(g & (half - 1)));
         if (g & half) w = fe_neg(w);
@@ -120,7 +126,7 @@ int validate_program(trp_ctx* ctx, const uint32_t* prog, size_t n_instr, unsigne
 
 // d_cols_dev: device array of column pointers; everything else already validated
 int launch_vm(trp_domain* d, const uint4* d_prog, size_t n_instr, unsigned n_regs, const uint4* d_consts,
-              const uint4* const* d_cols_dev, int coset, uint4* d_out) {
+              const uint4* const* d_cols_dev, int coset, uint4* d_out, unsigned row0 = 0, unsigned nrows = 0, unsigned halo_before = 0) {
   trp_ctx* ctx = d->ctx;
   QParams p;
   p.prog = d_prog; p.n_instr = (unsigned)n_instr; p.n_regs = n_regs; p.consts = d_consts; p.cols = d_cols_dev;
@@ -133,6 +139,8 @@ int launch_vm(trp_domain* d, const uint4* d_prog, size_t n_instr, unsigned n_reg
     p.rows_log = d->k; p.step = 1; p.x_stride = period; p.x_off = (unsigned)coset;
     p.out_stride = contiguous ? 1 : period; p.out_off = contiguous ? 0 : (unsigned)coset;
   }
+  p.row0 = row0; p.nrows = nrows; p.halo_before = halo_before;
+  if (nrows) { p.out_stride = 1; p.out_off = 0; }
   const void* tw = nullptr;
   TRP_TRY(trp_get_powers(ctx, d->field, d->ext_k, d->ext_omega, &tw));
   p.tw_ext = (const uint4*)tw;
@@ -141,7 +149,7 @@ int launch_vm(trp_domain* d, const uint4* d_prog, size_t n_instr, unsigned n_reg
   while (threads > 32 && (size_t)n_regs * threads * 32 > 200 * 1024) threads >>= 1;
   size_t smem = (size_t)n_regs * threads * 32;
   if (smem > 200 * 1024) TRP_FAIL(ctx, TRP_E_INVALID, "quotient program needs %u registers (max %u)", n_regs, 200 * 1024 / (32 * 32));
-  const size_t rows = (size_t)1 << p.rows_log;
+  const size_t rows = nrows ? (size_t)nrows : (size_t)1 << p.rows_log;
   unsigned blocks = (unsigned)((rows + threads - 1) / threads);
   auto go = [&](auto tag) -> int {
     typedef decltype(tag) PR;
@@ -280,6 +288,35 @@ int trp_dev_quotient_eval(trp_domain* d, const uint32_t* program, size_t n_instr
   size_t b_prog = ws_align(n_instr * 16), b_c = ws_align((n_consts ? n_consts : 1) * 32);
   return launch_vm(d, (const uint4*)w, n_instr, n_regs, (const uint4*)(w + b_prog), (const uint4* const*)(w + b_prog + b_c), coset,
                    (uint4*)d_out);
+}
+
+// Row-slice form of the coset evaluation (the multi-GPU quotient: a coset's rows are split between the devices): the columns
+// hold the coset's rows [row0 - halo_before, row0 + nrows + halo_after) (cyclic), the program may rotate by -halo_before ..
+// +halo_after rows, d_out receives the nrows results.
+int trp_dev_quotient_eval_rows(trp_domain* d, const uint32_t* program, size_t n_instr, unsigned n_regs, const uint64_t* consts,
+                               size_t n_consts, const uint64_t* const* d_cols, size_t n_cols, unsigned coset, size_t row0, size_t nrows,
+                               unsigned halo_before, unsigned halo_after, uint64_t* d_out) {
+  if (!d) return TRP_E_INVALID;
+  trp_ctx* ctx = d->ctx;
+  Locked l(ctx);
+  if (!program || !n_instr || !d_out || (n_consts && !consts) || (n_cols && !d_cols)) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
+  if (n_regs == 0 || coset >= (1u << (d->ext_k - d->k))) TRP_FAIL(ctx, TRP_E_INVALID, "bad register count or coset index");
+  const size_t n = (size_t)1 << d->k;
+  if (nrows == 0 || row0 >= n || nrows > n - row0) TRP_FAIL(ctx, TRP_E_INVALID, "row slice [%zu, %zu) is outside the coset", row0, row0 + nrows);
+  TRP_TRY(validate_program(ctx, program, n_instr, n_regs, n_consts, n_cols));
+  for (size_t i = 0; i < n_instr; ++i)
+    if (program[4 * i] == Q_LOAD) {
+      const int rot = (int)program[4 * i + 3];
+      if (rot < -(int)halo_before || rot > (int)halo_after)
+        TRP_FAIL(ctx, TRP_E_INVALID, "quotient program rotates by %d rows, the slice carries -%u .. +%u", rot, halo_before, halo_after);
+    }
+  for (size_t c = 0; c < n_cols; ++c) if (!d_cols[c]) TRP_FAIL(ctx, TRP_E_INVALID, "column %zu is NULL", c);
+  char* after = nullptr;
+  TRP_TRY(stage_tables(ctx, program, n_instr, consts, n_consts, d_cols, n_cols, 0, &after));
+  char* w = (char*)ctx->ws;
+  size_t b_prog = ws_align(n_instr * 16), b_c = ws_align((n_consts ? n_consts : 1) * 32);
+  return launch_vm(d, (const uint4*)w, n_instr, n_regs, (const uint4*)(w + b_prog), (const uint4* const*)(w + b_prog + b_c), (int)coset,
+                   (uint4*)d_out, (unsigned)row0, (unsigned)nrows, halo_before);
 }
 
 // host-pointer form over the whole extended domain (what poly::Evaluator::evaluate returns): columns are uploaded,

@@ -141,3 +141,68 @@ def all_gather_column_blocks(local, n_cols: int, block_slots: int, dist):
         dist.all_gather(list(gathered.unbind(0)), blk)
         g0, g1 = s0 * world, min(s1 * world, n_cols)
         yield g0, gathered.transpose(0, 1).reshape(((s1 - s0) * world,) + tuple(local.shape[1:]))[:g1 - g0].contiguous()
+
+
+# ---- round 2: every heavy phase of create_proof divided between the devices (sharded_backend.ShardedGpuBackend) -----------------
+def block_range(count: int, world: int, rank: int) -> Tuple[int, int, int]:
+    """(per, lo, hi): items are owned in contiguous blocks of per = ceil(count / world); rank owns [lo, hi) (possibly empty)"""
+    per = -(-count // world) if count else 0
+    lo = min(rank * per, count)
+    return per, lo, min(lo + per, count)
+
+
+def all_gather_blocks_inplace(buf, per: int, dist):
+    """buf: (>= per * world, ...) tensor whose block [rank * per, (rank + 1) * per) this rank has filled; after the call every
+    rank holds every block (NCCL / gloo in-place all-gather: the send buffer is the rank's slot of the receive buffer)"""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if per == 0 or world == 1:
+        return buf
+    out = buf[:per * world]
+    dist.all_gather_into_tensor(out, out[rank * per:(rank + 1) * per])
+    return buf
+
+
+def row_slice_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """rows of a size-n coset a rank evaluates in the row-split quotient: [rank * n / world, (rank + 1) * n / world)"""
+    if n % world:
+        raise ValueError("the number of devices must divide the domain size")
+    s = n // world
+    return rank * s, s
+
+
+def pack_row_slices(own, count: int, n: int, world: int, halo_before: int, halo_after: int, send):
+    """own: (>= count, n, ...) full-length columns; send: (world, per, S + halo_before + halo_after, ...).  Fills
+    send[d, :count] with rows [d * S - halo_before, (d + 1) * S + halo_after) (cyclic) of the first `count` columns: what
+    device d needs of these columns to evaluate its rows with rotations in [-halo_before, +halo_after]."""
+    s = n // world
+    width = s + halo_before + halo_after
+    if halo_before > n or halo_after > n:
+        raise ValueError("halo larger than the domain")
+    for d in range(world):
+        lo = d * s - halo_before
+        pos = 0
+        while pos < width:                                   # at most three contiguous pieces (wrap at either end)
+            src = (lo + pos) % n
+            run = min(width - pos, n - src)
+            send[d, :count, pos:pos + run].copy_(own[:count, src:src + run])
+            pos += run
+    return send
+
+
+def exchange_row_slices(send, recv, dist):
+    """all-to-all of the packed slices: recv[src] = the (per, S + halo, ...) block device `src` packed for this rank"""
+    if dist is None or dist.get_world_size() == 1:
+        recv.copy_(send)
+        return recv
+    dist.all_to_all_single(recv, send)
+    return recv
+
+
+def chunk_prefixes(ends: Sequence[int], p: int) -> List[int]:
+    """permutation grand products computed chunk by chunk, each from 1: chunk i of the chained argument is
+    prefix_i * local_i with prefix_i = prod_{j < i} local_j[last usable row] (halo2 starts chunk i at z_{i-1}[u])"""
+    out, acc = [], 1
+    for e in ends:
+        out.append(acc)
+        acc = acc * e % p
+    return out

@@ -522,9 +522,13 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
             raise ValueError(f"{what} column longer than the usable rows")
         return B.vec(col)
 
+    # instance / advice / permuted lookup columns are often mostly zero (a circuit that uses a fraction of its rows): backends that
+    # keep a narrow MSM table for such columns take the hint (they check the density themselves)
+    sparse_kw = {"sparse": True} if getattr(B, "accepts_sparse_hint", False) else {}
+
     # ---- instance columns: commit (not written, only absorbed) -------------------------------------------------------------
     inst_values = [column(c, "InstanceTooLarge: instance") for c in instances]
-    for cm in B.commit_lagrange_many(inst_values, [1] * len(inst_values)):
+    for cm in B.commit_lagrange_many(inst_values, [1] * len(inst_values), **sparse_kw):
         transcript.common_point(cm)
     to_coeff_many = getattr(B, "lagrange_to_coeff_many", lambda vs: [B.lagrange_to_coeff(v) for v in vs])
     inst_polys = to_coeff_many(inst_values)
@@ -536,7 +540,7 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     for v in adv_values:
         B.set_rows(v, usable, [rand() for _ in range(usable, n)])
     adv_blinds = [rand() for _ in adv_values]
-    for cm in B.commit_lagrange_many(adv_values, adv_blinds):
+    for cm in B.commit_lagrange_many(adv_values, adv_blinds, **sparse_kw):
         transcript.write_point(cm)
     adv_polys = to_coeff_many(adv_values)
     adv_cosets = [B.coeff_to_extended(c) for c in adv_polys]
@@ -546,19 +550,22 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     # ---- lookups: commit_permuted -------------------------------------------------------------------------------------------------
     theta = transcript.squeeze_challenge_scalar()
     lookups = []
-    for inputs, tables in cs.lookups:
-        ci, ct = B.compress(inputs, theta, values_of), B.compress(tables, theta, values_of)
-        pi, pt = B.permute_expression_pair(ci, ct, usable)
-        B.set_rows(pi, usable, [rand() for _ in range(bf + 1)])
-        B.set_rows(pt, usable, [rand() for _ in range(bf + 1)])
-        L = {"ci": ci, "ct": ct, "pi": pi, "pt": pt}
-        for name in ("pi", "pt"):
-            L[name + "_blind"] = rand()
-        lookups.append(L)
+    if hasattr(B, "lookups_commit_permuted"):      # a backend that divides the lookups between devices; same draws in the same order
+        lookups = B.lookups_commit_permuted(cs.lookups, theta, values_of, usable, bf, rand)
+    else:
+        for inputs, tables in cs.lookups:
+            ci, ct = B.compress(inputs, theta, values_of), B.compress(tables, theta, values_of)
+            pi, pt = B.permute_expression_pair(ci, ct, usable)
+            B.set_rows(pi, usable, [rand() for _ in range(bf + 1)])
+            B.set_rows(pt, usable, [rand() for _ in range(bf + 1)])
+            L = {"ci": ci, "ct": ct, "pi": pi, "pt": pt}
+            for name in ("pi", "pt"):
+                L[name + "_blind"] = rand()
+            lookups.append(L)
     for L, pi_poly, pt_poly in zip(lookups, *[to_coeff_many([L[nm] for L in lookups]) for nm in ("pi", "pt")]):
         L["pi_poly"], L["pt_poly"] = pi_poly, pt_poly
     # the commitments do not feed the RNG, so they are computed as one batch and written in halo2's order
-    for cm in B.commit_lagrange_many([L[nm] for L in lookups for nm in ("pi", "pt")], [L[nm + "_blind"] for L in lookups for nm in ("pi", "pt")]):
+    for cm in B.commit_lagrange_many([L[nm] for L in lookups for nm in ("pi", "pt")], [L[nm + "_blind"] for L in lookups for nm in ("pi", "pt")], **sparse_kw):
         transcript.write_point(cm)
     tick("lookups_permuted")
 
@@ -578,9 +585,12 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     for S, poly in zip(perm_sets, to_coeff_many([S["z"] for S in perm_sets])):
         S["poly"] = poly
         S["coset"] = B.coeff_to_extended(poly)
-    for L in lookups:
-        L["z"] = B.lookup_product(L["ci"], L["ct"], L["pi"], L["pt"], beta, gamma, bf, rand)
-        L["z_blind"] = rand()
+    if hasattr(B, "lookup_products"):
+        B.lookup_products(lookups, beta, gamma, bf, rand)
+    else:
+        for L in lookups:
+            L["z"] = B.lookup_product(L["ci"], L["ct"], L["pi"], L["pt"], beta, gamma, bf, rand)
+            L["z_blind"] = rand()
     for cm in B.commit_lagrange_many([L["z"] for L in lookups], [L["z_blind"] for L in lookups]):
         transcript.write_point(cm)
     for L, poly in zip(lookups, to_coeff_many([L["z"] for L in lookups])):
@@ -782,6 +792,15 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
 
 
 # ---- the product backend: libtrp.so, device resident ----------------------------------------------------------------------------------
+_PROVER_STREAMS = {}
+
+
+def _prover_stream(torch, device):
+    if device not in _PROVER_STREAMS:
+        _PROVER_STREAMS[device] = torch.cuda.Stream(device=device)
+    return _PROVER_STREAMS[device]
+
+
 class GpuBackend:
     """Backend of keygen / create_proof over the CUDA library.  Every polynomial is a torch int64 tensor (n, 4) of Montgomery
     limbs in HBM and every operation is a trp_dev_* entry point of include/tr_prover.h; the host sees scalars and points only.
@@ -801,6 +820,14 @@ class GpuBackend:
         self.q = _perm._MODULUS[1 - ctx.curve]
         self.R, self.Rq = (1 << 256) % self.p, (1 << 256) % self.q
         self.Rinv, self.Rqinv = pow(self.R, -1, self.p), pow(self.Rq, -1, self.q)
+        # ONE stream for torch's kernels, the library's kernels and NCCL: the ctx is pointed at a torch stream that is made this
+        # thread's current stream, so everything the prover enqueues is ordered by the stream itself and the host only waits
+        # when it reads a result (.cpu()).  (Round 1 kept the library on its own non-blocking stream and fenced every call
+        # with a device-wide synchronize: ~3 000 fences per proof at k = 20.)
+        torch.cuda.synchronize()
+        self.stream = _prover_stream(torch, ctx.device)        # one per process and device, shared by every backend and ctx
+        torch.cuda.set_stream(self.stream)
+        ctx.set_stream(self.stream.cuda_stream)
         self.params = params if params is not None else Params.new(ctx, k)
         self.dom = EvaluationDomain(ctx, cs_degree, k)
         self.extended_k = self.dom.extended_k
@@ -808,11 +835,19 @@ class GpuBackend:
         self.omega_inv = pow(self.omega, -1, self.p)
         self.delta = pow(5, 1 << 32, self.p)
         self.ipa_params = _ipa.IpaParams(ctx, k, self.params.g_points, self.params.w, self.params.u)
+        # a second, NARROW window table over g_lagrange ++ [w] for columns that are mostly zero (TinyRAM's instance / advice /
+        # permuted lookup columns use 2^16 of the 2^20 rows): what is left of such an MSM is the bucket reduction, whose cost is
+        # the 2^(c-1) buckets (profiles/msm_variants_r02.md: c = 13 2.17 ms per 8 columns against 3.3 ms at the dense c = 17)
+        self._gl_sparse = None
+        if k >= 18:
+            from .arithmetic import Bases
+            self._gl_sparse = Bases(ctx, np.concatenate([self.params.g_lagrange_points, self.params.w.reshape(1, 8)]), 13 << 8)
         self.ev = P.new_evaluator(ctx)
         self._static, self._static_keep = {}, []
         self.static_budget_bytes = 48 << 30
         self._arena, self._arena_used, self._arena_slot, self._arena_on, self._coset_buf = None, 0, {}, False, None
         self.leaves_are_coefficients = True       # coeff_to_extended keeps coefficient form (cosets are expanded in quotient())
+        self.accepts_sparse_hint = True
 
     def close(self):
         """release the library-side handles (MSM tables of the opening, the domain); torch tensors follow Python's lifetime"""
@@ -847,7 +882,11 @@ class GpuBackend:
         return f((self.n if rows is None else rows, 4), dtype=self.torch.int64, device="cuda")
 
     def _sync(self):
-        self.torch.cuda.synchronize()     # device-wide: orders torch's stream and the ctx stream
+        """kept as the marker of every torch <-> library hand-over; a no-op since both run on self.stream"""
+        return None
+
+    def _wait(self):
+        self.stream.synchronize()
 
     def _point(self, d_jac):
         self._sync()
@@ -960,23 +999,34 @@ class GpuBackend:
     def commit_lagrange(self, v, blind): return self._commit(self.params.g_lagrange, v, blind)
     def commit(self, v, blind): return self._commit(self.params.g, v, blind)
 
-    def _commit_many(self, bases, vecs, blinds, batch=32):
-        """several commitments over the same bases as batched MSMs (trp_dev_msm_batch processes the columns concurrently)"""
-        t, n, out = self.torch, self.n, []
+    def _commit_many(self, bases, vecs, blinds, batch=32, sparse=False):
+        """several commitments over the same bases as batched MSMs (trp_dev_msm_batch processes the columns concurrently).
+        sparse: the caller expects mostly-zero columns; batches whose non-zero rows are below 10 % go to the narrow table."""
+        t, n, results = self.torch, self.n, []
+        if len(vecs) > batch:                        # equal batches (33 columns: 17 + 16, not 32 + 1)
+            nb = -(-len(vecs) // batch)
+            batch = -(-len(vecs) // nb)
         for b0 in range(0, len(vecs), batch):
             vs, bs = vecs[b0:b0 + batch], blinds[b0:b0 + batch]
             stage = t.empty((len(vs), n + 1, 4), dtype=t.int64, device="cuda")
             for i, v in enumerate(vs):
                 stage[i, :n] = v
             stage[:, n] = self._dev(self._limbs(bs))
+            use = bases
+            if sparse and self._gl_sparse is not None and bases is self.params.g_lagrange:
+                if int((stage != 0).any(dim=-1).sum()) * 10 <= len(vs) * n:
+                    use = self._gl_sparse
             res = t.zeros((len(vs), 12), dtype=t.int64, device="cuda")
-            self._sync()
-            self.ctx.check(self.lib.trp_dev_msm_batch(self.ctx.handle, bases.handle, stage.data_ptr(), n + 1, len(vs), res.data_ptr()))
-            self._sync()
-            out.extend(self._point(res[i]) for i in range(len(vs)))
+            self.ctx.check(self.lib.trp_dev_msm_batch(self.ctx.handle, use.handle, stage.data_ptr(), n + 1, len(vs), res.data_ptr()))
+            results.append(res)
+        out = []
+        if results:                                  # ONE device -> host read for the whole call
+            jac = t.cat(results).cpu().numpy().view(self.np.uint64).reshape(-1, 3, 4)
+            for j in jac:
+                out.append(None if not j[2].any() else tuple(self._ints(j[:2], self.q, self.Rqinv)))
         return out
 
-    def commit_lagrange_many(self, vecs, blinds): return self._commit_many(self.params.g_lagrange, vecs, blinds)
+    def commit_lagrange_many(self, vecs, blinds, sparse=False): return self._commit_many(self.params.g_lagrange, vecs, blinds, sparse=sparse)
     def commit_many(self, vecs, blinds): return self._commit_many(self.params.g, vecs, blinds)
 
     # -- the verifier's three extras (verifier.py): the fixed points, the challenges' s vector, a variable-base MSM
@@ -1018,6 +1068,7 @@ class GpuBackend:
     #    k = 20).  Polynomials made outside a proof (keygen) never come from the arena.
     def begin_proof(self, n_polys):
         t = self.torch
+        n_polys += self._arena_padding()
         if self._arena is None or self._arena.shape[0] < n_polys:
             self._arena = None
             self._arena = t.empty((n_polys, self.n, 4), dtype=t.int64, device="cuda")
@@ -1025,6 +1076,9 @@ class GpuBackend:
 
     def end_proof(self):
         self._arena_on = False            # the views handed out stay valid until the next begin_proof
+
+    def _arena_padding(self):
+        return 0
 
     def lagrange_to_coeff(self, v):
         if self._arena_on and self._arena_used < self._arena.shape[0]:
@@ -1100,23 +1154,14 @@ class GpuBackend:
         buf = self._coset_buf[:ncols]
         vals = t.empty((ncos, n, 4), dtype=t.int64, device="cuda")
         self._sync()
-        mine = self._my_cosets(ncos)
-        for cs in mine:
+        for cs in range(ncos):
             self.ctx.check(self.lib.trp_dev_coeff_to_coset(self.dom.handle, coeff.data_ptr(), buf.data_ptr(), ncols, cs))
             ptrs = [buf[slot[i]].data_ptr() if i in slot else self._static[id(c)][cs].data_ptr() for i, c in enumerate(ext_polys)]
             self.ev.evaluate_device(prog, self.dom, ptrs, vals[cs].data_ptr(), coset=cs | Q_CONTIGUOUS)
-        vals = self._exchange_cosets(vals, mine)
         h = t.empty((ncos, n, 4), dtype=t.int64, device="cuda")
         self.ctx.check(self.lib.trp_dev_cosets_to_coeff(self.dom.handle, vals.data_ptr(), ncos, h.data_ptr(), 1))
         self._sync()
         return [h[i] for i in range(ncos)]
-
-    # hooks of the multi-GPU backend (sharded_backend.py): which cosets this process evaluates, and the exchange of the results
-    def _my_cosets(self, ncos):
-        return list(range(ncos))
-
-    def _exchange_cosets(self, vals, mine):
-        return vals
 
     def eval_polynomial(self, v, x):
         out = self._new(1)

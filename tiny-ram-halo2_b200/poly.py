@@ -295,5 +295,17 @@ class Evaluator:
                                                           len(prog.consts), colp, len(d_col_ptrs), coset, d_out_ptr))
 
 
+    def evaluate_device_rows(self, prog: Program, domain, d_col_ptrs, d_out_ptr, coset: int, row0: int, nrows: int,
+                             halo_before: int, halo_after: int):
+        """Row-slice form (trp_dev_quotient_eval_rows): the columns hold rows [row0 - halo_before, row0 + nrows + halo_after)
+        of size-n coset ``coset``; the nrows results go to d_out_ptr contiguously."""
+        consts = _to_mont_limbs(prog.consts, self.modulus)
+        colp = (ctypes.c_void_p * max(len(d_col_ptrs), 1))(*d_col_ptrs)
+        code = np.ascontiguousarray(prog.code)
+        self.ctx.check(self.ctx.lib.trp_dev_quotient_eval_rows(domain.handle, ptr(code), len(code), prog.n_regs, ptr(consts),
+                                                               len(prog.consts), colp, len(d_col_ptrs), coset, row0, nrows,
+                                                               halo_before, halo_after, d_out_ptr))
+
+
 def new_evaluator(ctx) -> Evaluator:
     return Evaluator(ctx)

@@ -1,25 +1,33 @@
 """plonk.create_proof on several GPUs of one box (BASELINE.json configs[4]): one process per GPU, every process
-runs the SAME host logic on the same witness with the same RNG, so the transcript is replicated and no rank waits for
-another's challenges; the two heavy, naturally sharded parts of the path are divided:
+runs the SAME host logic on the same witness with the same RNG stream (ShardedRng: rank 0's OS seed, broadcast), so the
+transcript is replicated and no rank waits for another's challenges.  The COMPUTE of every heavy phase is divided, the RESULTS
+are replicated, so that the host logic above never has to know where a polynomial lives:
 
   * commitments (best_multiexp): the columns of every commit_lagrange_many / commit_many batch go round-robin over the ranks
-    (parallel.shard_columns), the 64-byte affine results are all_gathered -- advice / lookup / grand-product / h-piece / key
-    commitments;
-  * the quotient: rank r evaluates cosets r, r + G, ... of the j - 1 that determine h(X) (coset NTT of every per-proof
-    polynomial + the quotient program), the n-value results are all_gathered (parallel.all_gather_columns) and every rank
-    recovers h(X).
+    (parallel.shard_columns), the 64-byte affine results are all_gathered;
+  * lagrange_to_coeff: a batch's columns are owned in contiguous blocks, each rank transforms its block inside the proof's
+    polynomial arena and ONE in-place all_gather fills the other blocks (k = 20: 15.5 GiB per proof over NVLink);
+  * lookups: lookup i (compress, permute_expression_pair, later its grand product) belongs to rank i // ceil(L / G); the permuted
+    columns and the Z columns are all_gathered in place;
+  * the permutation argument: every chunk's grand product is computed from 1 by its owner, the chunk-end values are
+    all_gathered (a few scalars) and each chunk is scaled by the product of its predecessors' ends -- exactly the chain
+    z_i[0] = z_{i-1}[u] halo2 builds sequentially -- then the Z columns are all_gathered;
+  * the quotient: every rank expands ITS block of coefficient columns on a coset (one size-n NTT per column), an all-to-all
+    hands rank r the rows [r n / G - halo, (r + 1) n / G + halo) of every column, rank r runs the quotient program on its n / G
+    rows (trp_dev_quotient_eval_rows) -- so j - 1 = 5 cosets load 2, 4 or 8 devices evenly, NTTs and program alike -- and the
+    n-value results are all_gathered; every rank recovers h(X).  Key-material cosets are cached per rank as row slices.
 
-Everything else (iNTTs, lookup permutation, grand-product scans, openings, the IPA) is replicated: it needs the whole column
-set on every rank, which this backend has by construction (k <= 20 fits one B200; the streamed exchange for k = 22 is
-sharded_model.py's).  The proof bytes are identical on every rank and identical to the one-GPU proof.
+Replicated: openings' evaluations, multiopen's linear combinations, Kate divisions and the IPA (every rank holds every
+coefficient polynomial after the all_gathers).  The proof bytes are identical on every rank and identical to the one-GPU proof.
 
 ShardedCommits is a mixin over any backend of plonk.create_proof, so the commit partition is tested on CPU over gloo with the
-oracle's PythonBackend (tests/test_parallel_cpu.py); ShardedGpuBackend adds the coset partition of plonk.GpuBackend."""
+oracle's PythonBackend (tests/test_parallel_cpu.py); the exchange helpers (parallel.py) are gloo-tested on CPU tensors."""
 from __future__ import annotations
 
 import numpy as np
 
 from . import parallel
+from . import poly as P
 from .plonk import GpuBackend
 
 
@@ -55,34 +63,244 @@ class ShardedCommits:
             out.append((int.from_bytes(row[1:33].tobytes(), "little"), int.from_bytes(row[33:65].tobytes(), "little")) if row[0] else None)
         return out
 
-    def commit_lagrange_many(self, vecs, blinds):
-        return self._sharded_points(super().commit_lagrange_many, vecs, blinds)
+    def commit_lagrange_many(self, vecs, blinds, **kw):
+        return self._sharded_points(lambda v, b: super(ShardedCommits, self).commit_lagrange_many(v, b, **kw), vecs, blinds)
 
     def commit_many(self, vecs, blinds):
         return self._sharded_points(super().commit_many, vecs, blinds)
 
 
+class ShardedRng:
+    """The caller's RNG of a multi-GPU create_proof: every rank must draw the SAME stream.  Rank 0 takes 32 bytes from the OS,
+    the seed is broadcast, and the stream is AES-256-CTR keyed by it (a CSPRNG; `cryptography` is in the image): rand() reads
+    64 bytes and reduces them mod p (pasta's Field::random = from_u512 of eight next_u64), vector(n) takes n x 32 bytes with the
+    top two bits cleared, used as Montgomery limbs (uniform below 2^254: 2^-128 from uniform mod p)."""
+
+    def __init__(self, p: int, dist=None, device="cpu", seed: bytes = None):
+        import os
+        import torch
+        if seed is None:
+            seed = os.urandom(32)
+        if dist is not None and dist.get_world_size() > 1:
+            t = torch.tensor(list(seed), dtype=torch.uint8, device=device)
+            dist.broadcast(t, src=0)
+            seed = bytes(t.cpu().tolist())
+        from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+        self.seed, self.p = seed, p
+        self._enc = Cipher(algorithms.AES(seed), modes.CTR(b"\0" * 16)).encryptor()
+        self.draws = 0
+
+    def _bytes(self, k):
+        return self._enc.update(b"\0" * k)
+
+    def __call__(self):
+        self.draws += 1
+        return int.from_bytes(self._bytes(64), "little") % self.p
+
+    def vector(self, n):
+        a = np.frombuffer(self._bytes(32 * n), dtype=np.uint64).reshape(n, 4).copy()
+        a[:, 3] &= np.uint64((1 << 62) - 1)
+        self.draws += n
+        return a
+
+
 class ShardedGpuBackend(ShardedCommits, GpuBackend):
     """plonk.GpuBackend on this process's GPU + the partitions above over `dist` (an initialised NCCL process group)"""
     comm_device = "cuda"
+    HALO = 16                              # rows kept either side of a row slice (rotations of +-16 rows: TinyRAM needs -6 .. +1)
 
     def __init__(self, ctx, k, cs_degree, dist=None, params=None):
+        self.dist = dist if (dist is not None and dist.get_world_size() > 1) else None
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.rank = self.dist.get_rank() if self.dist else 0
         super().__init__(ctx, k, cs_degree, params=params)
-        self.dist = dist
+        if self.world > 1 and self.n % self.world:
+            raise ValueError("the number of GPUs must divide 2^k")
+        self._xbuf = {}                    # persistent exchange buffers
 
-    def _my_cosets(self, ncos):
-        d = self.dist
-        if d is None or d.get_world_size() == 1:
-            return list(range(ncos))
-        return parallel.shard_cosets(ncos, d.get_world_size(), d.get_rank())
-
-    def _exchange_cosets(self, vals, mine):
-        d = self.dist
-        if d is None or d.get_world_size() == 1:
-            return vals
+    # -- small helpers ------------------------------------------------------------------------------------------------------------
+    def _buf(self, name, shape):
         t = self.torch
-        local = vals[mine] if mine else t.zeros((0,) + tuple(vals.shape[1:]), dtype=vals.dtype, device=vals.device)
-        self._sync()                      # the library's stream wrote vals; NCCL runs on torch's
-        out = parallel.all_gather_columns(local.contiguous(), vals.shape[0], d).contiguous()
-        self._sync()
+        cur = self._xbuf.get(name)
+        if cur is None or tuple(cur.shape) != tuple(shape):
+            self._xbuf[name] = None
+            cur = self._xbuf[name] = t.empty(shape, dtype=t.int64, device="cuda")
+        return cur
+
+    def _arena_padding(self):
+        return self.world                  # the in-place all_gather of a batch writes whole blocks
+
+    def close(self):
+        self._xbuf.clear()
+        super().close()
+
+    # -- lagrange_to_coeff: blocks of columns, one in-place all_gather --------------------------------------------------------------
+    def lagrange_to_coeff_many(self, vs):
+        k = len(vs)
+        if self.world == 1 or not self._arena_on or k < self.world:
+            return super().lagrange_to_coeff_many(vs)
+        per, lo, hi = parallel.block_range(k, self.world, self.rank)
+        first = self._arena_used
+        if first + per * self.world > self._arena.shape[0]:
+            return super().lagrange_to_coeff_many(vs)
+        out = []
+        for i, v in enumerate(vs):
+            c = self._arena[first + i]
+            self._arena_slot[id(c)] = (first + i, c)
+            if lo <= i < hi:
+                c.copy_(v)
+            out.append(c)
+        self._arena_used += k
+        if hi > lo:
+            self.ctx.check(self.lib.trp_dev_lagrange_to_coeff(self.dom.handle, self._arena[first + lo].data_ptr(), hi - lo))
+        parallel.all_gather_blocks_inplace(self._arena[first:first + per * self.world], per, self.dist)
         return out
+
+    # -- lookups: owned in blocks -------------------------------------------------------------------------------------------------------
+    def lookups_commit_permuted(self, lookups, theta, values_of, usable, bf, rand):
+        L = len(lookups)
+        draws = []
+        for _ in range(L):                 # plonk.create_proof's order: A' rows, S' rows, then the two blinds, lookup by lookup
+            a_rows = [rand() for _ in range(bf + 1)]
+            s_rows = [rand() for _ in range(bf + 1)]
+            draws.append((a_rows, s_rows, rand(), rand()))
+        per, lo, hi = parallel.block_range(L, self.world, self.rank)
+        perm = self.torch.empty((max(per * self.world, 1), 2, self.n, 4), dtype=self.torch.int64, device="cuda")
+        out, failure = [], None
+        for li, (inputs, tables) in enumerate(lookups):
+            d = {"pi": perm[li, 0], "pt": perm[li, 1], "pi_blind": draws[li][2], "pt_blind": draws[li][3], "ci": None, "ct": None}
+            if lo <= li < hi and failure is None:
+                try:
+                    d["ci"], d["ct"] = self.compress(inputs, theta, values_of), self.compress(tables, theta, values_of)
+                    pi, pt = self.permute_expression_pair(d["ci"], d["ct"], usable)
+                except ValueError as e:                       # ConstraintSystemFailure: an input value absent from the table
+                    failure = e
+                    continue
+                self.set_rows(pi, usable, draws[li][0])
+                self.set_rows(pt, usable, draws[li][1])
+                perm[li, 0].copy_(pi); perm[li, 1].copy_(pt)
+            out.append(d)
+        if self.world > 1 and L:
+            # a failed lookup is seen by its owner only: agree on the outcome before anybody enters the bulk collective
+            ok = self.torch.tensor([0 if failure is not None else 1], dtype=self.torch.int32, device="cuda")
+            self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                from .lookup import ConstraintSystemFailure
+                raise failure if failure is not None else ConstraintSystemFailure("lookup input value not present in the table (on another rank)")
+            parallel.all_gather_blocks_inplace(perm, per, self.dist)
+        elif failure is not None:
+            raise failure
+        return out
+
+    def lookup_products(self, lookups, beta, gamma, bf, rand):
+        L = len(lookups)
+        draws = []
+        for _ in range(L):
+            rows = [rand() for _ in range(bf)]
+            draws.append((rows, rand()))
+        per, lo, hi = parallel.block_range(L, self.world, self.rank)
+        zs = self.torch.empty((max(per * self.world, 1), self.n, 4), dtype=self.torch.int64, device="cuda")
+        for li, d in enumerate(lookups):
+            if lo <= li < hi:
+                self.ctx.check(self.lib.trp_dev_lookup_product(self.dom.handle, d["ci"].data_ptr(), d["ct"].data_ptr(), d["pi"].data_ptr(),
+                                                               d["pt"].data_ptr(), self._m(beta), self._m(gamma), zs[li].data_ptr(), self.n - bf))
+                self.set_rows(zs[li], self.n - bf, draws[li][0])
+            d["z"], d["z_blind"] = zs[li], draws[li][1]
+        if self.world > 1 and L:
+            parallel.all_gather_blocks_inplace(zs, per, self.dist)
+
+    # -- permutation argument: chunks from 1, scaled by the product of their predecessors' ends ---------------------------------------------
+    def permutation_commit(self, values, sigmas, beta, gamma, chunk_len, blinding_factors, rand, after_chunk):
+        if self.world == 1:
+            return super().permutation_commit(values, sigmas, beta, gamma, chunk_len, blinding_factors, rand, after_chunk)
+        from ._lib import ptr
+        n, p, ct, t, bf = self.n, self.p, self.ct, self.torch, blinding_factors
+        starts = list(range(0, len(values), chunk_len))
+        C = len(starts)
+        per, lo, hi = parallel.block_range(C, self.world, self.rank)
+        zs = t.empty((per * self.world, n, 4), dtype=t.int64, device="cuda")
+        rows = []
+        for ci in range(C):                # halo2's draw order: a chunk's blinding rows, then (after_chunk) its blind
+            rows.append([rand() for _ in range(bf)])
+            after_chunk(zs[ci])
+        u = n - (bf + 1)
+        ends = t.zeros((per * self.world, 4), dtype=t.int64, device="cuda")
+        for ci in range(lo, hi):
+            cols = list(range(starts[ci], min(starts[ci] + chunk_len, len(values))))
+            dbeta = self._limbs([pow(self.delta, c, p) * beta % p for c in cols])
+            vptr = (ct.c_void_p * len(cols))(*[values[c].data_ptr() for c in cols])
+            sptr = (ct.c_void_p * len(cols))(*[sigmas[c].data_ptr() for c in cols])
+            self.ctx.check(self.lib.trp_dev_permutation_product(self.dom.handle, vptr, sptr, len(cols), self._m(beta), self._m(gamma), ptr(dbeta),
+                                                                None, zs[ci].data_ptr()))
+            ends[ci].copy_(zs[ci][u])
+        parallel.all_gather_blocks_inplace(ends, per, self.dist)
+        pref = parallel.chunk_prefixes(self._ints(ends[:C].cpu().numpy().view(self.np.uint64)), p)
+        for ci in range(lo, hi):
+            if pref[ci] != 1:
+                d_s = self._dev(self._limbs([pref[ci]]))
+                self.ctx.check(self.lib.trp_dev_field_op(self.ctx.handle, 0, 2 | 16, zs[ci].data_ptr(), d_s.data_ptr(), zs[ci].data_ptr(), u + 1))
+            self.set_rows(zs[ci], n - bf, rows[ci])
+        parallel.all_gather_blocks_inplace(zs, per, self.dist)
+        return [zs[ci] for ci in range(C)]
+
+    # -- key material: each rank keeps its ROW SLICE (with halo) of the j - 1 cosets -------------------------------------------------------
+    def _slice_rows(self):
+        row0, S = parallel.row_slice_bounds(self.n, self.world, self.rank)
+        t = self.torch
+        idx = (t.arange(S + 2 * self.HALO, device="cuda") + (row0 - self.HALO)) % self.n
+        return row0, S, idx
+
+    def coeff_to_extended_static(self, c):
+        if self.world == 1:
+            return super().coeff_to_extended_static(c)
+        ncos = self.j - 1
+        row0, S, idx = self._slice_rows()
+        held = sum(v.numel() for v in self._static.values()) * 8
+        if held + ncos * (S + 2 * self.HALO) * 32 > self.static_budget_bytes:
+            return c
+        full = self._buf("static_full", (self.n, 4))
+        vals = self.torch.empty((ncos, S + 2 * self.HALO, 4), dtype=self.torch.int64, device="cuda")
+        for cs in range(ncos):
+            self.ctx.check(self.lib.trp_dev_coeff_to_coset(self.dom.handle, c.data_ptr(), full.data_ptr(), 1, cs))
+            vals[cs] = full[idx]
+        self._static[id(c)] = vals
+        self._static_keep.append(c)
+        return c
+
+    # -- the quotient: NTTs by column block, program by row slice --------------------------------------------------------------------------
+    def quotient(self, ast, ext_polys):
+        if self.world == 1:
+            return super().quotient(ast, ext_polys)
+        t, n, ncos, G, H = self.torch, self.n, self.j - 1, self.world, self.HALO
+        prog = P.compile_ast(ast, self.p)
+        dyn = [i for i, c in enumerate(ext_polys) if id(c) not in self._static]
+        in_arena = [self._arena_slot.get(id(ext_polys[i])) for i in dyn]
+        if dyn and all(a is not None and a[1] is ext_polys[i] for a, i in zip(in_arena, dyn)):
+            coeff = self._arena[:self._arena_used]
+            slot = {i: a[0] for a, i in zip(in_arena, dyn)}
+        else:
+            coeff = t.stack([ext_polys[i] for i in dyn]) if dyn else t.empty((0, n, 4), dtype=t.int64, device="cuda")
+            slot = {i: s_ for s_, i in enumerate(dyn)}
+        ncols = coeff.shape[0]
+        per, lo, hi = parallel.block_range(ncols, G, self.rank)
+        row0, S, _ = self._slice_rows()
+        width = S + 2 * H
+        own = self._buf("q_own", (max(per, 1), n, 4))
+        send = self._buf("q_send", (G, max(per, 1), width, 4))
+        recv = self._buf("q_recv", (G, max(per, 1), width, 4))
+        flat = recv.view(G * max(per, 1), width, 4)
+        local = t.empty((ncos, S, 4), dtype=t.int64, device="cuda")
+        for cs in range(ncos):
+            if hi > lo:
+                self.ctx.check(self.lib.trp_dev_coeff_to_coset(self.dom.handle, coeff[lo].data_ptr(), own.data_ptr(), hi - lo, cs))
+                parallel.pack_row_slices(own, hi - lo, n, G, H, H, send)
+            if ncols:
+                parallel.exchange_row_slices(send, recv, self.dist)
+            ptrs = [flat[slot[i]].data_ptr() if i in slot else self._static[id(c)][cs].data_ptr() for i, c in enumerate(ext_polys)]
+            self.ev.evaluate_device_rows(prog, self.dom, ptrs, local[cs].data_ptr(), cs, row0, S, H, H)
+        gathered = t.empty((G, ncos, S, 4), dtype=t.int64, device="cuda")
+        self.dist.all_gather_into_tensor(gathered, local)
+        vals = gathered.permute(1, 0, 2, 3).reshape(ncos, n, 4).contiguous()
+        h = t.empty((ncos, n, 4), dtype=t.int64, device="cuda")
+        self.ctx.check(self.lib.trp_dev_cosets_to_coeff(self.dom.handle, vals.data_ptr(), ncos, h.data_ptr(), 1))
+        return [h[i] for i in range(ncos)]
