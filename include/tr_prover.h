@@ -65,6 +65,9 @@ const char* trp_version(void);
 int trp_prof_enable(trp_ctx* ctx, int on);
 int trp_prof_reset(trp_ctx* ctx);
 int trp_prof_get(trp_ctx* ctx, int phase, double* total_ms, uint64_t* count);
+/* algorithmic work of the spans timed so far: phase 4 = radix-2 butterflies (columns x N/2 x stages of every pass launched),
+ * phase 1 = bucket additions if no digit were zero (n x windows x columns), phase 5 = rows evaluated by the quotient program */
+int trp_prof_get_work(trp_ctx* ctx, int phase, double* work);
 
 /* ---- MSM: halo2_proofs::arithmetic::best_multiexp(coeffs, bases) -> C::Curve ---------------------------
  * and poly::commitment::Params::{commit, commit_lagrange} which append blind * w and call it.
@@ -228,6 +231,15 @@ int trp_dev_kate_division(trp_ctx* ctx, int which_field, const uint64_t* d_coeff
 int trp_kate_division(trp_ctx* ctx, int which_field, const uint64_t* coeffs, size_t n, const uint64_t b[4], uint64_t* q);
 /* IPA round: a[i] += a[i + half] * u, i < half  (p' with u^-1, b with u) */
 int trp_dev_fold(trp_ctx* ctx, int which_field, uint64_t* d_a, size_t half, const uint64_t u[4]);
+/* The IPA round without collapsing the generators: after j rounds G'_i = sum_t s_t G_{t cur + i} (cur = n / 2^j, s = the 2^j
+ * products of the round challenges), so L_j = <p'_hi, G'_lo> and R_j = <p'_lo, G'_hi> are fixed-base MSMs over the ORIGINAL
+ * generators with the scalars p'[.] * s_t.  Writes the two scalar columns for the base indices [lo, lo + count) (a rank's slice of
+ * the generators when the point range is split between devices): d_out[b - lo] for L_j, d_out[col_stride + b - lo] for R_j.
+ * d_p: the cur live entries of p'; d_s: n / cur entries. */
+int trp_dev_ipa_round_scalars(trp_ctx* ctx, int which_field, const uint64_t* d_p, const uint64_t* d_s, size_t cur, size_t lo, size_t count,
+                              size_t col_stride, uint64_t* d_out);
+/* d_out[2 t] = d_s[t], d_out[2 t + 1] = d_s[t] * u, t < m: the s vector after a round with challenge u (d_out must not alias d_s) */
+int trp_dev_ipa_s_double(trp_ctx* ctx, int which_field, const uint64_t* d_s, size_t m, const uint64_t u[4], uint64_t* d_out);
 /* parallel_generator_collapse: g[i] = g[i] + [u] g[i + half], i < half, normalised affine points (identity = 0,0); u Montgomery */
 int trp_dev_generator_collapse(trp_ctx* ctx, uint64_t* d_g /* 2 * half affine points */, size_t half, const uint64_t u[4]);
 /* best_multiexp over caller-owned DEVICE bases (no precomputed table): the round MSMs over the collapsing G' */

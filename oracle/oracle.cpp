@@ -299,6 +299,9 @@ static inline size_t bitrev(size_t n, unsigned l) {
 }
 
 template <class Mod>
+static void recursive_butterfly(Fe<Mod>* a, size_t n, size_t tw_chunk, const Fe<Mod>* tw, unsigned par_levels);
+
+template <class Mod>
 static void fft_inplace(Fe<Mod>* a, Fe<Mod> omega, unsigned log_n, int threads) {
   typedef Fe<Mod> F;
   size_t n = (size_t)1 << log_n;
@@ -306,22 +309,39 @@ static void fft_inplace(Fe<Mod>* a, Fe<Mod> omega, unsigned log_n, int threads) 
   std::vector<F> tw(std::max<size_t>(n / 2, 1));
   tw[0] = F::one();
   for (size_t i = 1; i < n / 2; ++i) tw[i] = tw[i - 1] * omega;
-  size_t chunk = 2, tchunk = n / 2;
-  for (unsigned s = 0; s < log_n; ++s) {
-    size_t half = chunk / 2;
-    // butterflies of one stage are independent: split the n/2 butterflies over threads
-    parallel_for(n / 2, threads, [&](size_t lo, size_t hi, int) {
-      for (size_t b = lo; b < hi; ++b) {
-        size_t blk = b / half, i = b % half;
-        F* x = a + blk * chunk + i;
-        F* y = x + half;
-        F t = i == 0 ? *y : (*y) * tw[i * tchunk];
-        F u = *x;
-        *x = u + t; *y = u - t;
-      }
-    });
-    chunk *= 2; tchunk /= 2;
+  // halo2_proofs 0.2.0 best_fft: serial when log_n <= log2(threads), else recursive_butterfly_arithmetic -- the two halves of
+  // the (bit-reversed) array are transformed independently (rayon::join; here std::thread down to log2(threads) levels), then
+  // combined with one butterfly pass; the recursion keeps the working set of the lower levels in cache
+  unsigned log_threads = 0;
+  while ((2 << log_threads) <= (threads > 0 ? threads : 1)) ++log_threads;
+  recursive_butterfly<Mod>(a, n, 1, tw.data(), log_n > log_threads ? log_threads : 0);
+}
+
+template <class Mod>
+static void recursive_butterfly(Fe<Mod>* a, size_t n, size_t tw_chunk, const Fe<Mod>* tw, unsigned par_levels) {
+  typedef Fe<Mod> F;
+  if (n == 1) return;
+  if (n == 2) { F t = a[1]; a[1] = a[0] - t; a[0] = a[0] + t; return; }
+  const size_t half = n / 2;
+  if (par_levels > 0) {
+    std::thread left([&] { recursive_butterfly<Mod>(a, half, tw_chunk * 2, tw, par_levels - 1); });
+    recursive_butterfly<Mod>(a + half, half, tw_chunk * 2, tw, par_levels - 1);
+    left.join();
+  } else {
+    recursive_butterfly<Mod>(a, half, tw_chunk * 2, tw, 0);
+    recursive_butterfly<Mod>(a + half, half, tw_chunk * 2, tw, 0);
   }
+  // combine: halo2 does this pass on the joining thread; the upper log2(threads) passes are split over the threads here as its
+  // rayon scheduler would steal them
+  auto pass = [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; ++i) {
+      F t = i == 0 ? a[half] : a[half + i] * tw[i * tw_chunk];
+      F u = a[i];
+      a[i] = u + t; a[half + i] = u - t;
+    }
+  };
+  if (par_levels > 0 && half >= 4096) parallel_for(half, 1 << par_levels, [&](size_t lo, size_t hi, int) { pass(lo, hi); });
+  else pass(0, half);
 }
 
 template <class Mod>
@@ -515,6 +535,86 @@ void orc_extended_to_coeff(int field, unsigned j, unsigned k, u64* ext, u64* out
     memcpy(out, ext, 32 * n * d.qdeg);
   });
 }
+// ---- pieces of the SAMPLED create_proof baseline (bench.py --impl reference / cpu_baseline) ---------------
+// poly::Evaluator::evaluate on the CPU: an interpreter of the straight-line program of include/tr_prover.h (the lowering of halo2's
+// Ast that the GPU kernel runs), rows split over the threads as halo2 splits its chunks.  The sample's columns hold col_rows
+// (a power of two) values and are indexed modulo it, so a 2^14-row sample of a 709-leaf program fits the host; COSETX takes
+// its value from xs[row mod col_rows].
+void orc_quotient_vm(int field, const uint32_t* prog, size_t n_instr, unsigned n_regs, const u64* consts, const u64* const* cols,
+                     size_t col_rows, const u64* xs, size_t rows, u64* out, int threads) {
+  DISPATCH_FIELD(field, {
+    typedef Fe<Mod> F;
+    const size_t mask = col_rows - 1;
+    parallel_for(rows, threads, [&](size_t lo, size_t hi, int) {
+      std::vector<F> r(n_regs);
+      for (size_t row = lo; row < hi; ++row) {
+        for (size_t pc = 0; pc < n_instr; ++pc) {
+          const uint32_t op = prog[4 * pc], d = prog[4 * pc + 1], a = prog[4 * pc + 2], b = prog[4 * pc + 3];
+          switch (op) {
+            case 0: r[d] = F::load(cols[a] + 4 * ((row + (size_t)(int64_t)(int32_t)b) & mask)); break;
+            case 1: r[d] = F::load(consts + 4 * a); break;
+            case 2: r[d] = r[a] + r[b]; break;
+            case 3: r[d] = r[a] - r[b]; break;
+            case 4: r[d] = r[a] * r[b]; break;
+            case 5: r[d] = r[a].neg(); break;
+            case 6: r[d] = r[a].sqr(); break;
+            case 7: r[d] = r[a].dbl(); break;
+            case 8: r[d] = F::load(xs + 4 * (row & mask)); break;
+            case 9: r[a].store(out + 4 * row); break;
+            case 10: r[d] = r[a] * F::load(consts + 4 * b); break;
+            case 11: r[d] = r[a] + F::load(consts + 4 * b); break;
+            default: r[d] = r[a] - F::load(consts + 4 * b); break;
+          }
+        }
+      }
+    });
+  });
+}
+// arithmetic::eval_polynomial(poly, point): Horner per thread chunk, chunks combined with powers of x^chunk (halo2's evaluate
+// does the same split under rayon)
+void orc_eval_polynomial(int field, const u64* coeffs, size_t n, const u64* x_mont, int threads, u64* out) {
+  DISPATCH_FIELD(field, {
+    typedef Fe<Mod> F;
+    const F x = F::load(x_mont);
+    const size_t T = (size_t)(threads > 0 ? threads : 1);
+    const size_t chunk = (n + T - 1) / T;
+    std::vector<F> part(T, F::zero());
+    parallel_for(T, threads, [&](size_t lo, size_t hi, int) {
+      for (size_t t = lo; t < hi; ++t) {
+        size_t a = t * chunk, b = std::min(n, a + chunk);
+        F acc = F::zero();
+        for (size_t i = b; i-- > a;) acc = acc * x + F::load(coeffs + 4 * i);
+        part[t] = acc;
+      }
+    });
+    u64 e[1] = {(u64)chunk};
+    const F step = x.pow(e, 1);
+    F acc = F::zero();
+    for (size_t t = T; t-- > 0;) acc = acc * step + part[t];
+    acc.store(out);
+  });
+}
+// parallel_generator_collapse of one IPA round: g[i] = g[i] + [u] g[i + half] (one variable-base scalar multiplication per pair)
+void orc_generator_collapse(int curve, u64* g_affine, size_t half, const u64* u_canon, int threads) {
+  auto run = [&](auto tag) {
+    typedef decltype(tag) Mod;
+    parallel_for(half, threads, [&](size_t lo, size_t hi, int) {
+      std::vector<Jac<Mod>> tmp(hi - lo);
+      for (size_t i = lo; i < hi; ++i) {
+        Aff<Mod> a = load_affine<Mod>(g_affine + 8 * i), b = load_affine<Mod>(g_affine + 8 * (i + half));
+        Jac<Mod> acc = Jac<Mod>::identity();
+        for (int bit = 254; bit >= 0; --bit) {
+          acc = acc.dbl();
+          if ((u_canon[bit >> 6] >> (bit & 63)) & 1) acc = acc.add_affine(b);
+        }
+        tmp[i - lo] = acc.add_affine(a);
+      }
+      for (size_t i = lo; i < hi; ++i) store_affine<Mod>(g_affine + 8 * i, tmp[i - lo].to_affine());
+    });
+  };
+  if (curve == 0) run(ModP()); else run(ModQ());
+}
+
 unsigned orc_domain_info(int field, unsigned j, unsigned k, u64* omega, u64* ext_omega) {
   unsigned ek = 0;
   DISPATCH_FIELD(field, { Domain<Mod> d(j, k); d.omega.store(omega); d.ext_omega.store(ext_omega); ek = d.ext_k; });

@@ -197,3 +197,34 @@ def random_field_mont(field, n, seed):
         filled += len(cand)
     # a uniform canonical value re-read as Montgomery form is still uniform; no conversion needed
     return out
+
+
+# ---- pieces of the sampled create_proof baseline (bench.py's CPU legs) -------------------------------------------------------
+def quotient_vm(field, code, n_regs, consts_mont, cols, col_rows, xs, rows, threads=None):
+    """the straight-line quotient program (include/tr_prover.h instruction set) interpreted on the CPU for `rows` rows;
+    cols: list of (col_rows, 4) Montgomery arrays indexed modulo col_rows; xs: (col_rows, 4) values COSETX reads"""
+    code = np.ascontiguousarray(code, dtype=np.uint32).reshape(-1, 4)
+    consts = _u64(consts_mont)
+    cols = [_u64(c) for c in cols]
+    assert col_rows & (col_rows - 1) == 0 and all(c.size == 4 * col_rows for c in cols)
+    tab = (ctypes.c_void_p * max(len(cols), 1))(*[c.ctypes.data for c in cols])
+    xs = _u64(xs)
+    out = np.zeros((rows, 4), dtype=np.uint64)
+    lib().orc_quotient_vm(field, code.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(code)), ctypes.c_uint(n_regs), _p(consts), tab,
+                          ctypes.c_size_t(col_rows), _p(xs), ctypes.c_size_t(rows), _p(out), threads or hw_threads())
+    return out
+
+
+def eval_polynomial(field, coeffs, x_mont, threads=None):
+    coeffs = _u64(coeffs)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_eval_polynomial(field, _p(coeffs), ctypes.c_size_t(coeffs.size // 4), _p(_u64(x_mont)), threads or hw_threads(), _p(out))
+    return out
+
+
+def generator_collapse(curve, g_affine, u_canon_limbs, threads=None):
+    """one round of parallel_generator_collapse: returns g_lo + [u] g_hi (half the points)"""
+    g = _u64(g_affine).copy()
+    half = g.size // 16
+    lib().orc_generator_collapse(curve, _p(g), ctypes.c_size_t(half), _p(_u64(u_canon_limbs)), threads or hw_threads())
+    return g.reshape(-1, 8)[:half]

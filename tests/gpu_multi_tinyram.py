@@ -91,6 +91,15 @@ if "--verify" in sys.argv and rank == 0:
     t0 = time.perf_counter()
     res["verified"], res["verify_error"] = VU.verify(be, pk.vk, inst, proof)
     res["verify_s"] = round(time.perf_counter() - t0, 2)
+if "--pverify" in sys.argv:                 # the package's own verifier on the device, on every rank (replicated)
+    from tiny_ram_halo2_b200 import verifier as V
+    t0 = time.perf_counter()
+    try:
+        V.verify_proof(be, pk.vk, V.SingleVerifier(be), TR.device_columns(be, inst), V.Blake2bRead(proof, C.base.p, p))
+        res["product_verifier_accepts"] = True
+    except V.VerifyError as e:
+        res["product_verifier_accepts"] = False; res["product_verifier_error"] = str(e)
+    res["product_verify_s"] = round(time.perf_counter() - t0, 2)
 if "--check" in sys.argv:
     be.close(); del be, pk
     torch.cuda.empty_cache()
@@ -105,5 +114,5 @@ if rank == 0:
     print(json.dumps(res))
 if d is not None:
     d.destroy_process_group()
-ok = res["proof_identical_on_all_ranks"] and res.get("verified", True) and res.get("bit_exact_vs_single_gpu", True)
+ok = res["proof_identical_on_all_ranks"] and res.get("verified", True) and res.get("bit_exact_vs_single_gpu", True) and res.get("product_verifier_accepts", True)
 sys.exit(0 if ok else 1)

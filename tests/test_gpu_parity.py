@@ -214,3 +214,68 @@ def test_point_range_split_and_points_sum(pkg, ctxs):
         assert np.array_equal(affine_of(curve, out), want)
     ctx.check(ctx.lib.trp_points_sum(ctx.handle, None, 0, ptr(out)))
     assert not out.any()
+
+
+# ---- the upper half of BASELINE.json configs[1] / configs[2]: 2^22 and 2^24, compared with the oracle byte for byte ---------
+_LARGE = {}
+
+
+def _large_msm_case(log_n):
+    """inputs and the oracle's answer, computed once per size (the oracle's best_multiexp takes ~10-40 s on the host cores)"""
+    if log_n not in _LARGE:
+        n = (1 << log_n) + 1                                   # commit_lagrange shape: n + 1 with the blind's base
+        pts = make_points(O.VESTA, n)
+        sc = scalars_uniform(O.VESTA, n, 20 + log_n)
+        sc[n // 2:n // 2 + 1000] = scalars_tinyram(O.VESTA, 1000, 41)         # a run of 0/1 and small scalars inside the uniform ones
+        _LARGE.clear()                                         # one size at a time: 2^24 points are 1 GiB on the host
+        _LARGE[log_n] = (pts, sc, O.msm(O.VESTA, sc, pts))
+    return _LARGE[log_n]
+
+
+@pytest.mark.parametrize("log_n,flags", [(22, 2), (22, 1), (24, 2), (24, 1)])
+def test_best_multiexp_2_22_2_24(pkg, ctxs, log_n, flags):
+    """flags 2 = precomputed window multiples (the default table), 1 = one bucket set per window (no table)"""
+    ctx = ctxs[O.VESTA]
+    pts, sc, want = _large_msm_case(log_n)
+    bases = pkg.Bases(ctx, pts, flags)
+    try:
+        info = bases.describe()
+        assert info["precomputed"] == (flags == 2)
+        assert np.array_equal(affine_of(O.VESTA, pkg.best_multiexp(ctx, sc, bases)), want), info
+    finally:
+        bases.free()
+
+
+@pytest.mark.parametrize("log_n", [22, 24])
+def test_best_fft_2_22_2_24(pkg, ctxs, log_n):
+    ctx = ctxs[O.VESTA]
+    omega = O.to_mont(O.FP, O.ints_to_limbs([pm.Fp.root_of_unity(log_n)]))[0]
+    a = O.random_field_mont(O.FP, 1 << log_n, 30 + log_n)
+    got = pkg.best_fft(ctx, a, omega, log_n)
+    want = O.fft(O.FP, a, log_n, omega)
+    assert np.array_equal(got, want)
+    # and back: the inverse transform with omega^-1, scaled by 2^-log_n, returns the input (size-independent property)
+    omega_inv = O.field_op(O.FP, "inv", omega.reshape(1, 4))[0]
+    back = pkg.best_fft(ctx, got, omega_inv, log_n)
+    ninv = O.to_mont(O.FP, O.ints_to_limbs([pow(1 << log_n, -1, O.MODULUS[O.FP])]))
+    assert np.array_equal(O.field_op(O.FP, "mul", back, np.repeat(ninv, 1 << log_n, axis=0)), a)
+
+
+@pytest.mark.parametrize("k", [20, 22])
+def test_domain_transforms_k20_k22(pkg, ctxs, k):
+    """lagrange_to_coeff / coeff_to_extended / extended_to_coeff at the proof sizes of configs[3] / configs[4] (extended domains
+    of 2^23 and 2^25 values), each against the oracle"""
+    ctx = ctxs[O.VESTA]
+    j = 6
+    dom = pkg.EvaluationDomain(ctx, j, k)
+    n = 1 << k
+    col = O.random_field_mont(O.FP, n, 50 + k).reshape(1, n, 4)
+    coeff = dom.lagrange_to_coeff(col)
+    assert np.array_equal(coeff, O.lagrange_to_coeff(O.FP, j, k, col).reshape(1, n, 4))
+    ext = dom.coeff_to_extended(coeff)
+    assert np.array_equal(ext, O.coeff_to_extended(O.FP, j, k, coeff))
+    back = dom.extended_to_coeff(ext[0])
+    assert np.array_equal(back[:n], coeff[0]) and not back[n:].any()
+    h = O.random_field_mont(O.FP, 1 << dom.extended_k, 60 + k)
+    assert np.array_equal(dom.extended_to_coeff(h, divide_by_vanishing_poly=True), O.extended_to_coeff(O.FP, j, k, h, divide=True))
+    dom.free()

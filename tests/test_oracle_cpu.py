@@ -119,3 +119,40 @@ def test_oracle_thread_count_invariance_and_tinyram_scalars():
     a = O.random_field_mont(O.FP, 1 << 12, 1)
     om = mont(O.FP, [pm.Fp.root_of_unity(12)])[0]
     assert np.array_equal(O.fft(O.FP, a, 12, om, threads=1), O.fft(O.FP, a, 12, om, threads=8))
+
+
+def test_sampler_primitives_against_the_python_model():
+    """the three routines the sampled create_proof baseline adds to the C++ oracle (quotient-program interpreter, Horner
+    evaluation, one generator-collapse round) against the big-int model"""
+    import __graft_entry__ as ge
+    ge.load_package()
+    from tiny_ram_halo2_b200 import poly as P
+    import random
+    p = O.MODULUS[O.FP]
+    rnd = random.Random(4)
+    rows = 16
+    cols_int = [[rnd.randrange(p) for _ in range(rows)] for _ in range(3)]
+    A, B, C = P.Poly(0), P.Poly(1), P.Poly(2)
+    ast = (A * B - C.with_rotation(1)) * 7 + P.LinearTerm(3) * A.with_rotation(-1) + B * B + 5
+    prog = P.compile_ast(ast, p)
+    xs_int = [rnd.randrange(p) for _ in range(rows)]
+    mont = lambda v: O.to_mont(O.FP, O.ints_to_limbs(v))
+    got = O.limbs_to_ints(O.from_mont(O.FP, O.quotient_vm(O.FP, prog.code, prog.n_regs, mont(prog.consts), [mont(c) for c in cols_int], rows,
+                                                             mont(xs_int), rows, threads=3)))
+    want = [((cols_int[0][r] * cols_int[1][r] - cols_int[2][(r + 1) % rows]) * 7 + 3 * xs_int[r] * cols_int[0][(r - 1) % rows]
+             + cols_int[1][r] ** 2 + 5) % p for r in range(rows)]
+    assert got == want
+    coeffs = [rnd.randrange(p) for _ in range(1000)]
+    x = rnd.randrange(p)
+    for threads in (1, 7):
+        got = O.limbs_to_ints(O.from_mont(O.FP, O.eval_polynomial(O.FP, mont(coeffs), mont([x])[0], threads=threads).reshape(1, 4)))[0]
+        assert got == sum(c * pow(x, i, p) for i, c in enumerate(coeffs)) % p
+    V = pm.Vesta
+    pts = [V.mul(rnd.randrange(1, V.scalar.p), V.G) for _ in range(6)]
+    u = rnd.randrange(V.scalar.p)
+    qm = lambda v: O.to_mont(O.FQ, O.ints_to_limbs(v))
+    g = np.stack([np.concatenate([qm([x_])[0], qm([y_])[0]]) for x_, y_ in pts])
+    got = O.generator_collapse(O.VESTA, g, O.ints_to_limbs([u])[0], threads=2)
+    for i in range(3):
+        wx, wy = V.add(pts[i], V.mul(u, pts[i + 3]))
+        assert O.limbs_to_ints(O.from_mont(O.FQ, got[i].reshape(2, 4))) == [wx, wy]

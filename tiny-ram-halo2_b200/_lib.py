@@ -19,7 +19,7 @@ _ERR_NAMES = {-1: "TRP_E_INVALID", -2: "TRP_E_CUDA", -3: "TRP_E_OOM", -4: "TRP_E
 # every symbol include/tr_prover.h declares (tests check that the library exports them all)
 EXPORTED_SYMBOLS = [
     "trp_ctx_create", "trp_ctx_destroy", "trp_last_error", "trp_ctx_set_stream", "trp_ctx_sync",
-    "trp_ctx_launch_count", "trp_version", "trp_prof_enable", "trp_prof_reset", "trp_prof_get",
+    "trp_ctx_launch_count", "trp_version", "trp_prof_enable", "trp_prof_reset", "trp_prof_get", "trp_prof_get_work",
     "trp_bases_load", "trp_dev_bases_load", "trp_bases_load_ex", "trp_dev_bases_load_ex", "trp_bases_len", "trp_bases_describe", "trp_bases_free",
     "trp_msm", "trp_msm_batch", "trp_dev_msm_batch", "trp_dev_points_progression", "trp_points_sum", "trp_dev_points_sum",
     "trp_ntt", "trp_dev_ntt",
@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "trp_dev_permutation_product", "trp_permutation_product", "trp_dev_lookup_product", "trp_lookup_product",
     "trp_dev_permute_expression_pair", "trp_permute_expression_pair",
     "trp_dev_eval_polynomials", "trp_dev_eval_polynomials_at", "trp_dev_linear_combination", "trp_eval_polynomial", "trp_dev_inner_products", "trp_compute_inner_product", "trp_dev_powers",
-    "trp_dev_kate_division", "trp_kate_division", "trp_dev_fold", "trp_dev_generator_collapse", "trp_dev_msm_var",
+    "trp_dev_kate_division", "trp_kate_division", "trp_dev_fold", "trp_dev_ipa_round_scalars", "trp_dev_ipa_s_double", "trp_dev_generator_collapse", "trp_dev_msm_var",
     "trp_dev_hash_to_curve", "trp_hash_to_curve", "trp_dev_group_fft", "trp_group_fft", "trp_params_new", "trp_dev_params_new",
 ]
 
@@ -79,6 +79,7 @@ def load_library():
     L.trp_prof_enable.argtypes = [vp, i]
     L.trp_prof_reset.argtypes = [vp]
     L.trp_prof_get.argtypes = [vp, i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
+    L.trp_prof_get_work.argtypes = [vp, i, ctypes.POINTER(ctypes.c_double)]
     L.trp_bases_load.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
     L.trp_dev_bases_load.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
     L.trp_bases_load_ex.argtypes = [vp, vp, sz, i, ctypes.POINTER(vp)]
@@ -133,6 +134,8 @@ def load_library():
     L.trp_dev_kate_division.argtypes = [vp, i, vp, sz, vp, vp]
     L.trp_kate_division.argtypes = [vp, i, vp, sz, vp, vp]
     L.trp_dev_fold.argtypes = [vp, i, vp, sz, vp]
+    L.trp_dev_ipa_round_scalars.argtypes = [vp, i, vp, vp, sz, sz, sz, sz, vp]
+    L.trp_dev_ipa_s_double.argtypes = [vp, i, vp, sz, vp, vp]
     L.trp_dev_generator_collapse.argtypes = [vp, vp, sz, vp]
     L.trp_dev_msm_var.argtypes = [vp, vp, vp, sz, sz, vp]
     L.trp_dev_hash_to_curve.argtypes = [vp, ctypes.c_char_p, vp, sz, i, ctypes.c_uint64, sz, vp]
@@ -184,6 +187,23 @@ class Context:
     def sync(self):
         self.check(self.lib.trp_ctx_sync(self.handle))
 
+    _TORCH_STREAMS = {}
+
+    def bind_torch_stream(self):
+        """Make torch and this ctx share ONE CUDA stream (one per process and device, made torch's current stream): code that
+        mixes torch tensor operations with trp_dev_* calls is then ordered by the stream itself -- no fences between the two.
+        Returns the torch stream.  (A ctx starts on its own non-blocking stream, which torch's streams do not synchronise with.)"""
+        import torch
+        st = Context._TORCH_STREAMS.get(self.device)
+        if st is None:
+            torch.cuda.synchronize(self.device)
+            st = Context._TORCH_STREAMS[self.device] = torch.cuda.Stream(device=self.device)
+        if torch.cuda.current_stream(self.device) != st:
+            torch.cuda.synchronize(self.device)
+            torch.cuda.set_stream(st)
+        self.set_stream(st.cuda_stream)
+        return st
+
     @property
     def launches(self) -> int:
         return int(self.lib.trp_ctx_launch_count(self.handle))
@@ -215,6 +235,15 @@ class Context:
             ms, cnt = ctypes.c_double(), ctypes.c_uint64()
             self.check(self.lib.trp_prof_get(self.handle, idx, ctypes.byref(ms), ctypes.byref(cnt)))
             out[name] = (ms.value, int(cnt.value))
+        return out
+
+    def prof_work(self):
+        """{phase: algorithmic units of the timed spans} (trp_prof_get_work)"""
+        out = {}
+        for idx, name in enumerate(self.PROF_PHASES):
+            w = ctypes.c_double()
+            self.check(self.lib.trp_prof_get_work(self.handle, idx, ctypes.byref(w)))
+            out[name] = w.value
         return out
 
     def close(self):

@@ -195,6 +195,13 @@ int trp_prof_get(trp_ctx* ctx, int phase, double* total_ms, uint64_t* count) {
   if (count) *count = ctx->prof_count[phase];
   return TRP_OK;
 }
+int trp_prof_get_work(trp_ctx* ctx, int phase, double* work) {
+  if (!ctx || phase < 0 || phase >= PROF_NPHASES || !work) return TRP_E_INVALID;
+  Locked l(ctx);
+  trp_prof_collect(ctx);
+  *work = ctx->prof_work[phase];
+  return TRP_OK;
+}
 
 // ---- MSM ---------------------------------------------------------------------------------------------------
 int trp_bases_load(trp_ctx* ctx, const uint64_t* affine_xy, size_t n, trp_bases** out) {

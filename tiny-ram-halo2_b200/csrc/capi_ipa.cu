@@ -141,6 +141,26 @@ int trp_dev_fold(trp_ctx* ctx, int which_field, uint64_t* d_a, size_t half, cons
   return trp_fold_impl(ctx, field_id(ctx, which_field), d_a, half, u);
 }
 
+int trp_dev_ipa_round_scalars(trp_ctx* ctx, int which_field, const uint64_t* d_p, const uint64_t* d_s, size_t cur, size_t lo, size_t count,
+                              size_t col_stride, uint64_t* d_out) {
+  if (!ctx) return TRP_E_INVALID;
+  Locked l(ctx);
+  if (count == 0) return TRP_OK;
+  if (!d_p || !d_s || !d_out) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
+  if (cur < 2 || (cur & (cur - 1)) || col_stride < count) TRP_FAIL(ctx, TRP_E_INVALID, "cur must be a power of two >= 2 and col_stride >= count");
+  unsigned cur_log = 0;
+  while (((size_t)1 << cur_log) < cur) ++cur_log;
+  return trp_ipa_round_scalars_impl(ctx, field_id(ctx, which_field), d_p, d_s, cur_log, lo, count, col_stride, d_out);
+}
+
+int trp_dev_ipa_s_double(trp_ctx* ctx, int which_field, const uint64_t* d_s, size_t m, const uint64_t u[4], uint64_t* d_out) {
+  if (!ctx) return TRP_E_INVALID;
+  Locked l(ctx);
+  if (m == 0) return TRP_OK;
+  if (!d_s || !u || !d_out || d_s == d_out) TRP_FAIL(ctx, TRP_E_INVALID, "NULL or aliased buffer");
+  return trp_ipa_s_double_impl(ctx, field_id(ctx, which_field), d_s, m, u, d_out);
+}
+
 int trp_dev_kate_division(trp_ctx* ctx, int which_field, const uint64_t* d_coeffs, size_t n, const uint64_t b[4], uint64_t* d_q) {
   if (!ctx) return TRP_E_INVALID;
   Locked l(ctx);

@@ -18,7 +18,7 @@ struct TwiddleTable {
 
 // optional per-phase device timing (CUDA events on the ctx stream); used by bench.py for the live roofline number
 enum ProfPhase { PROF_MSM_SORT = 0, PROF_MSM_ACCUM_L1, PROF_MSM_LEVELS, PROF_MSM_REDUCE, PROF_NTT_PASS, PROF_QUOTIENT, PROF_PRODUCTS, PROF_LOOKUP_SORT, PROF_NPHASES };
-struct ProfSpan { int phase; cudaEvent_t e0, e1; };
+struct ProfSpan { int phase; cudaEvent_t e0, e1; double work; };
 
 struct trp_ctx {
   bool prof_on = false;
@@ -26,6 +26,7 @@ struct trp_ctx {
   std::vector<cudaEvent_t> prof_pool;
   double prof_ms[PROF_NPHASES] = {};
   uint64_t prof_count[PROF_NPHASES] = {};
+  double prof_work[PROF_NPHASES] = {};    // algorithmic units of the timed spans (ntt: butterflies; msm level 1: sorted entries' upper bound; quotient: rows)
   int device = 0;
   int curve = 0;
   cudaStream_t own_stream = nullptr;
@@ -99,9 +100,9 @@ struct trp_domain {
 
 struct ProfScope {
   trp_ctx* ctx; int idx;
-  ProfScope(trp_ctx* c, int phase) : ctx(c), idx(-1) {
+  ProfScope(trp_ctx* c, int phase, double work = 0) : ctx(c), idx(-1) {
     if (!c->prof_on) return;
-    ProfSpan s; s.phase = phase;
+    ProfSpan s; s.phase = phase; s.work = work;
     for (cudaEvent_t* e : {&s.e0, &s.e1}) {
       if (!c->prof_pool.empty()) { *e = c->prof_pool.back(); c->prof_pool.pop_back(); }
       else cudaEventCreate(e);
@@ -118,7 +119,7 @@ inline void trp_prof_collect(trp_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& s : ctx->prof_spans) {
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, s.e0, s.e1) == cudaSuccess) { ctx->prof_ms[s.phase] += ms; ctx->prof_count[s.phase]++; }
+    if (cudaEventElapsedTime(&ms, s.e0, s.e1) == cudaSuccess) { ctx->prof_ms[s.phase] += ms; ctx->prof_count[s.phase]++; ctx->prof_work[s.phase] += s.work; }
     ctx->prof_pool.push_back(s.e0); ctx->prof_pool.push_back(s.e1);
   }
   ctx->prof_spans.clear();
@@ -187,6 +188,9 @@ int trp_eval_polys_impl(trp_ctx* ctx, int field, const void* d_polys, size_t str
 int trp_inner_products_impl(trp_ctx* ctx, int field, const void* d_a, size_t a_stride, const void* d_b, size_t b_stride, size_t n, size_t m,
                             void* d_out, void* ws);
 int trp_fold_impl(trp_ctx* ctx, int field, void* d_a, size_t half, const uint64_t u[4]);
+int trp_ipa_round_scalars_impl(trp_ctx* ctx, int field, const void* d_p, const void* d_s, unsigned cur_log, size_t lo, size_t count,
+                                size_t col_stride, void* d_out);
+int trp_ipa_s_double_impl(trp_ctx* ctx, int field, const void* d_s, size_t m, const uint64_t u[4], void* d_out);
 int trp_powers_impl(trp_ctx* ctx, int field, const uint64_t x[4], size_t n, void* d_out);
 size_t trp_kate_ws_bytes(size_t n);
 int trp_kate_division_impl(trp_ctx* ctx, int field, const void* d_coeffs, size_t n, const uint64_t b[4], const uint64_t b_inv[4],

@@ -122,6 +122,34 @@ __global__ void fold_kernel(uint4* a, size_t half, Fe<PR> u) {
   fe_store(a + 2 * i, fe_add(fe_load<PR>(a + 2 * i), fe_mul(fe_load<PR>(a + 2 * (i + half)), u)));
 }
 
+// The IPA round WITHOUT collapsing the generators.  After j rounds halo2's G'_i is sum_t s_t G_{t cur + i}
+// (cur = n / 2^j entries alive, s = the 2^j products of the challenges so far), so the round's
+//   L_j = <p'_hi, G'_lo> = sum_{t, i < half} p'[half + i] s_t G_{t cur + i},   R_j = <p'_lo, G'_hi> = sum_{t, i < half} p'[i] s_t G_{t cur + half + i}
+// are ONE fixed-base MSM each over the ORIGINAL generators (the resident window table): no parallel_generator_collapse (n / 2^(j+1)
+// variable-base scalar multiplications per round) and no doubling chain per round.  This kernel writes the two scalar columns
+// for the base indices [lo, lo + count): out[0][b - lo], out[1][b - lo].
+template <class PR>
+__global__ void ipa_round_scalars_kernel(const uint4* p, const uint4* s, unsigned cur_log, size_t lo, size_t count, size_t col_stride, uint4* out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  const size_t b = lo + idx, cur = (size_t)1 << cur_log, half = cur >> 1;
+  const size_t t = b >> cur_log, i = b & (cur - 1);
+  const bool low = i < half;
+  const Fe<PR> prod = fe_mul(fe_load<PR>(p + 2 * (low ? half + i : i - half)), fe_load_ro<PR>(s + 2 * t));
+  const Fe<PR> zero = fe_zero<PR>();
+  fe_store(out + 2 * idx, low ? prod : zero);
+  fe_store(out + 2 * (col_stride + idx), low ? zero : prod);
+}
+// s'[2 t] = s[t], s'[2 t + 1] = s[t] * u: G'_next[i] = G'_cur[i] + [u] G'_cur[i + half] in terms of the original generators
+template <class PR>
+__global__ void ipa_s_double_kernel(const uint4* s, size_t m, Fe<PR> u, uint4* out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const Fe<PR> v = fe_load<PR>(s + 2 * t);
+  fe_store(out + 4 * t, v);
+  fe_store(out + 4 * t + 2, fe_mul(v, u));
+}
+
 // out[i] = x^i, i < n
 template <class PR>
 __global__ void powers_kernel(uint4* out, size_t n, Fe<PR> x) {
@@ -268,6 +296,25 @@ int trp_fold_impl(trp_ctx* ctx, int field, void* d_a, size_t half, const uint64_
   unsigned blocks = (unsigned)((half + 255) / 256);
   if (field == 0) fold_kernel<FpParams><<<blocks, 256, 0, ctx->stream>>>((uint4*)d_a, half, fe_from_limbs<FpParams>(u));
   else fold_kernel<FqParams><<<blocks, 256, 0, ctx->stream>>>((uint4*)d_a, half, fe_from_limbs<FqParams>(u));
+  TRP_LAUNCHED(ctx);
+  return TRP_OK;
+}
+
+int trp_ipa_round_scalars_impl(trp_ctx* ctx, int field, const void* d_p, const void* d_s, unsigned cur_log, size_t lo, size_t count,
+                                size_t col_stride, void* d_out) {
+  if (count == 0) return TRP_OK;
+  unsigned blocks = (unsigned)((count + 255) / 256);
+  if (field == 0) ipa_round_scalars_kernel<FpParams><<<blocks, 256, 0, ctx->stream>>>((const uint4*)d_p, (const uint4*)d_s, cur_log, lo, count, col_stride, (uint4*)d_out);
+  else ipa_round_scalars_kernel<FqParams><<<blocks, 256, 0, ctx->stream>>>((const uint4*)d_p, (const uint4*)d_s, cur_log, lo, count, col_stride, (uint4*)d_out);
+  TRP_LAUNCHED(ctx);
+  return TRP_OK;
+}
+
+int trp_ipa_s_double_impl(trp_ctx* ctx, int field, const void* d_s, size_t m, const uint64_t u[4], void* d_out) {
+  if (m == 0) return TRP_OK;
+  unsigned blocks = (unsigned)((m + 255) / 256);
+  if (field == 0) ipa_s_double_kernel<FpParams><<<blocks, 256, 0, ctx->stream>>>((const uint4*)d_s, m, fe_from_limbs<FpParams>(u), (uint4*)d_out);
+  else ipa_s_double_kernel<FqParams><<<blocks, 256, 0, ctx->stream>>>((const uint4*)d_s, m, fe_from_limbs<FqParams>(u), (uint4*)d_out);
   TRP_LAUNCHED(ctx);
   return TRP_OK;
 }

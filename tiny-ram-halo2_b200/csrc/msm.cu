@@ -557,7 +557,7 @@ int msm_chunk(trp_ctx* ctx, const trp_bases_impl* bs, const uint4* d_scalars, si
     TRP_TRY(run_scan(ctx, w.offsets, w.task_off[0], nullptr, w.block_sums, w.total, NB, segmented ? 2 : 1, L1));
   }
   {
-    ProfScope ps(ctx, PROF_MSM_ACCUM_L1);
+    ProfScope ps(ctx, PROF_MSM_ACCUM_L1, (double)M);      // work = entries if no digit were zero (n * windows * columns): an upper bound
     unsigned gridl1 = (unsigned)((level_tasks[0] + ACC_THREADS - 1) / ACC_THREADS);
     if (segmented)
       msm_accum_l1_seg_kernel<BPR><<<(unsigned)(((M + L1 - 1) / L1 + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(

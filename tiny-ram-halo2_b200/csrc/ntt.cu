@@ -343,7 +343,7 @@ int ntt_run(trp_ctx* ctx, const void* d_src, void* d_dst, size_t batch, unsigned
     // register-blocked kernel, radix-4 groups by default (measured on B200 at 8 x 2^20: radix 4 1.53 ms, radix 8 1.61 ms --
     // 117 registers cost a CTA per SM --, one stage per barrier 1.58 ms); TRP_NTT_RADIX=8 / 2 select the other two
     static const int radix_log = [] { const char* e = getenv("TRP_NTT_RADIX"); int v = e ? atoi(e) : 4; return v == 2 ? 1 : v == 8 ? 3 : 2; }();
-    ProfScope ps(ctx, PROF_NTT_PASS);
+    ProfScope ps(ctx, PROF_NTT_PASS, (double)batch * (double)(N >> 1) * (double)p.s);      // work = radix-2 butterflies of this pass
     if (p.s == 0 || radix_log == 1) {
       if (smem > 48 * 1024)
         TRP_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32u << TILE_LOG_MAX)));

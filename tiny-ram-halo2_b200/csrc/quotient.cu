@@ -157,7 +157,7 @@ int launch_vm(trp_domain* d, const uint4* d_prog, size_t n_instr, unsigned n_reg
     for (int i = 0; i < 4; ++i) { zeta.v[2 * i] = (uint32_t)d->g_coset[i]; zeta.v[2 * i + 1] = (uint32_t)(d->g_coset[i] >> 32); }
     if (smem > 48 * 1024)
       TRP_CUDA(ctx, cudaFuncSetAttribute(quotient_vm_kernel<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    ProfScope ps(ctx, PROF_QUOTIENT);
+    ProfScope ps(ctx, PROF_QUOTIENT, (double)rows);      // work = rows evaluated (x the program's multiplications, known to the caller)
     quotient_vm_kernel<PR><<<blocks, threads, smem, ctx->stream>>>(p, zeta);
     TRP_LAUNCHED(ctx);
     return TRP_OK;

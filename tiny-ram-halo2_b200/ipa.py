@@ -1,7 +1,9 @@
 """Mirror of halo2_proofs::poly::commitment::prover::create_proof (poly/commitment/prover.rs, halo2_proofs 0.2.0): the
 inner-product-argument opening that ends every create_proof of the reference (/root/reference/src/test_utils.rs:41,96).
 Every vector stays on the GPU; per round the host sees two points (L_j, R_j) and one challenge, exactly what the
-transcript needs.  Also mirrors arithmetic::{eval_polynomial, compute_inner_product, kate_division}.
+transcript needs.  The rounds never collapse the generators: L_j and R_j are fixed-base MSMs over the ORIGINAL generators'
+resident window table with the scalars p'[.] * s_t (trp_dev_ipa_round_scalars), which removes halo2's
+parallel_generator_collapse from the prover altogether (measured at k = 20 on one B200: 165 ms -> see profiles/ipa_r02.md).  Also mirrors arithmetic::{eval_polynomial, compute_inner_product, kate_division}.
 
 Device memory is held in torch tensors (int64 views of the 4 x u64 limbs); the arithmetic is libtrp.so's."""
 from __future__ import annotations
@@ -40,52 +42,88 @@ def kate_division(ctx, a, b):
 
 
 class IpaParams:
-    """The part of poly::commitment::Params the opening needs: g (n points), w, u; g ++ [w] is also loaded as MSM bases with
-    the precomputed window table (Params::commit of the blinding polynomial S)."""
+    """The part of poly::commitment::Params the opening needs: g (n points), w, u.  g ++ [u, w] is loaded as MSM bases with the
+    precomputed window table: Params::commit of the blinding polynomial S and every round's L_j / R_j run over it."""
 
     def __init__(self, ctx, k, g, w, u):
         import torch
         self.ctx, self.k, self.n = ctx, k, 1 << k
+        ctx.bind_torch_stream()              # torch tensor operations and trp_dev_* calls are mixed below: one stream for both
         g = as_u64(g).reshape(-1, 8)
         if len(g) != self.n:
             raise ValueError("g must hold 2^k points")
         self.w, self.u = as_u64(w).reshape(8), as_u64(u).reshape(8)
+        self.g_host = g
         self.d_g = torch.from_numpy(g.view(np.int64)).cuda()
         self.d_uw = torch.from_numpy(np.stack([self.u, self.w]).view(np.int64)).cuda()
-        h = ctypes.c_void_p()
-        gw = torch.from_numpy(np.concatenate([g, self.w.reshape(1, 8)]).view(np.int64)).cuda()
-        torch.cuda.synchronize()
-        ctx.check(ctx.lib.trp_dev_bases_load(ctx.handle, gw.data_ptr(), self.n + 1, ctypes.byref(h)))
-        ctx.sync()
-        self.h_gw = h
+        self._tables = {}
+        self.h_guw = self.table(0, 1)
+
+    def table(self, rank, world):
+        """window table over g[lo:hi] ++ [u, w], [lo, hi) = rank's slice of the generators (the whole range for world = 1)"""
+        import torch
+        key = (rank, world)
+        if key not in self._tables:
+            lo, hi = rank * self.n // world, (rank + 1) * self.n // world
+            pts = torch.cat([self.d_g.reshape(self.n, 8)[lo:hi], self.d_uw.reshape(2, 8)])
+            h = ctypes.c_void_p()
+            torch.cuda.current_stream().synchronize()
+            self.ctx.check(self.ctx.lib.trp_dev_bases_load(self.ctx.handle, pts.data_ptr(), hi - lo + 2, ctypes.byref(h)))
+            self.ctx.sync()
+            self._tables[key] = h
+        return self._tables[key]
 
     def free(self):
-        if getattr(self, "h_gw", None) and getattr(self.ctx, "handle", None):
-            self.ctx.lib.trp_bases_free(self.h_gw)
-        self.h_gw = None
+        if getattr(self.ctx, "handle", None):
+            for h in getattr(self, "_tables", {}).values():
+                self.ctx.lib.trp_bases_free(h)
+        self._tables = {}
+        self.h_guw = None
 
 
-def create_proof(params: IpaParams, rand, transcript, p_poly, p_blind, x_3, rand_vector=None):
+def create_proof(params: IpaParams, rand, transcript, p_poly, p_blind, x_3, rand_vector=None, dist=None, trace=None):
     """poly::commitment::prover::create_proof(params, rng, transcript, p_poly, p_blind, x_3).
 
     p_poly: (n, 4) Montgomery host array or a cuda int64 tensor (coefficient form); p_blind, x_3: canonical ints.
     rand() draws one canonical scalar; rand_vector(n), if given, draws n at once as an (n, 4) Montgomery array (the
     coefficients of the blinding polynomial S).  transcript: write_point((8,) affine Montgomery limbs),
     write_scalar(int), squeeze_challenge_scalar() -> int.  Nothing is returned: like halo2, the proof is what was written
-    to the transcript."""
+    to the transcript.
+
+    Round j (cur = n / 2^j live entries of p' and b, s = the 2^j challenge products):
+        L_j = sum_b colL[b] G_b + [z <p'_hi, b_lo>] U + [l_rand] W,   colL[t cur + i] = p'[half + i] s_t  (i < half), 0 otherwise
+        R_j = sum_b colR[b] G_b + [z <p'_lo, b_hi>] U + [r_rand] W,   colR[t cur + half + i] = p'[i] s_t
+    as ONE batch of two fixed-base MSMs over the table of g ++ [u, w]; then p' and b are folded and s doubles.  These are the
+    group elements halo2 computes from its collapsed G' (G'_i = sum_t s_t G_{t cur + i}), so the transcript is identical.
+
+    dist (an initialised process group, every rank calling with the same inputs): each large MSM's POINT RANGE is split --
+    rank r owns the generators [r n / G, (r + 1) n / G) (its own window table) and the partial sums are all_gathered and added
+    (trp_dev_points_sum), best_multiexp's own combination step; p', b and s (a few MiB) stay replicated."""
     import torch
     ctx, lib, n, k = params.ctx, params.ctx.lib, params.n, params.k
+    ctx.bind_torch_stream()
     p = _MODULUS[ctx.curve]
     R = (1 << 256) % p
     Rinv = pow(R, -1, p)
     mont = lambda v: _limbs(v % p * R % p)
     unmont = lambda l: _to_int(l) * Rinv % p
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+    import time as _time
+
+    def mark(label):                        # development aid (tests/gpu_ipa_trace.py): drain the stream and take a timestamp
+        if trace is not None:
+            torch.cuda.synchronize()
+            trace.append((label, _time.perf_counter()))
+
+    mark("start")
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    if n % world:
+        raise ValueError("the number of ranks must divide n")
 
     def evaluate(d_poly, x):
         out = torch.zeros(4, dtype=torch.int64, device="cuda")
         ctx.check(lib.trp_dev_eval_polynomials(ctx.handle, 0, d_poly.data_ptr(), n, n, 1, ptr(mont(x)), out.data_ptr()))
-        ctx.sync()
         return unmont(out.cpu().numpy().view(np.uint64))
 
     def set_elem(d_vec, i, v):
@@ -94,75 +132,86 @@ def create_proof(params: IpaParams, rand, transcript, p_poly, p_blind, x_3, rand
     d_p = p_poly if hasattr(p_poly, "data_ptr") else dev(as_u64(p_poly))
     if d_p.numel() != 4 * n:
         raise ValueError("p_poly.len() != params.n")
-    torch.cuda.synchronize()
+    # this rank's slice of the generators (all of them on one GPU) and its table
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    cnt = hi - lo
+    table = params.table(rank, world)
+    cols = torch.zeros((2, cnt + 2, 4), dtype=torch.int64, device="cuda")       # scalars of g[lo:hi] ++ [u, w], one column per point
+    d_pt = torch.zeros((2, 12), dtype=torch.int64, device="cuda")
+    gathered = torch.zeros((world, 2, 12), dtype=torch.int64, device="cuda") if world > 1 else None
+
+    def msm_pair(m):
+        """the m columns of `cols` over the (sliced) table, partial sums combined: -> m affine points as (8,) limb arrays"""
+        ctx.check(lib.trp_dev_msm_batch(ctx.handle, table, cols.data_ptr(), cnt + 2, m, d_pt.data_ptr()))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.reshape(-1), d_pt.reshape(-1))
+            for c_ in range(m):
+                part = gathered[:, c_].contiguous()
+                ctx.check(lib.trp_dev_points_sum(ctx.handle, part.data_ptr(), world, d_pt[c_].data_ptr()))
+        return [r_[:8].copy() for r_ in d_pt[:m].cpu().numpy().view(np.uint64)]
+
     # random polynomial S with a root at x_3
     s_host = rand_vector(n) if rand_vector else np.stack([mont(rand()) for _ in range(n)])
+    mark("draw S")
     d_s = dev(as_u64(s_host))
-    torch.cuda.synchronize()
+    mark("upload S")
     s0 = unmont(as_u64(s_host)[0])
     s_at_x3 = evaluate(d_s, x_3)
     set_elem(d_s, 0, s0 - s_at_x3)
     s_poly_blind = rand()
-    # params.commit(&s_poly, s_poly_blind)
-    d_sc = torch.cat([d_s.reshape(n, 4), dev(mont(s_poly_blind)).reshape(1, 4)])
-    d_pt = torch.zeros((4, 12), dtype=torch.int64, device="cuda")
-    torch.cuda.synchronize()
-    ctx.check(lib.trp_dev_msm_batch(ctx.handle, params.h_gw, d_sc.data_ptr(), n + 1, 1, d_pt.data_ptr()))
-    ctx.sync()
-    transcript.write_point(d_pt[0].cpu().numpy().view(np.uint64)[:8].copy())
+    # params.commit(&s_poly, s_poly_blind): over this rank's slice, the blind's term on rank 0
+    cols[0, :cnt] = d_s.reshape(n, 4)[lo:hi]
+    if rank == 0:
+        cols[0, cnt + 1] = dev(mont(s_poly_blind))
+    transcript.write_point(msm_pair(1)[0])
+    mark("commit S")
     xi = transcript.squeeze_challenge_scalar()
     z = transcript.squeeze_challenge_scalar()
     # P' = P - [v] G_0 + [xi] S
     d_pp = torch.empty_like(d_s)
-    d_xi = dev(mont(xi))          # must outlive the kernel that reads it: the library's stream is invisible to torch's allocator
-    torch.cuda.synchronize()
+    d_xi = dev(mont(xi))
     ctx.check(lib.trp_dev_field_op(ctx.handle, 0, 2 | 16, d_s.data_ptr(), d_xi.data_ptr(), d_pp.data_ptr(), n))
     ctx.check(lib.trp_dev_field_op(ctx.handle, 0, 0, d_pp.data_ptr(), d_p.data_ptr(), d_pp.data_ptr(), n))
-    ctx.sync()
     v = evaluate(d_pp, x_3)
-    ctx.sync()
     pp0 = unmont(d_pp.reshape(n, 4)[0].cpu().numpy().view(np.uint64))
     set_elem(d_pp.reshape(n, 4), 0, pp0 - v)
     f = (s_poly_blind * xi + p_blind) % p
-    d_b = torch.empty((n, 4), dtype=torch.int64, device="cuda")
-    # G' ++ [U, W]: L_j and R_j are computed as ONE batch of two MSMs over (G'_lo | G'_hi | U | W) with the scalar columns
-    # (p'_hi | 0 | z <p'_hi, b_lo> | l_rand) and (0 | p'_lo | z <p'_lo, b_hi> | r_rand): one launch sequence per round
-    # instead of four MSMs and two point additions (zero scalars cost nothing: zero digits are never sorted into buckets)
-    d_g = torch.cat([params.d_g, params.d_uw])
-    d_sc = torch.zeros((2, n + 2, 4), dtype=torch.int64, device="cuda")
-    d_ip = torch.zeros((2, 4), dtype=torch.int64, device="cuda")
-    torch.cuda.synchronize()
-    ctx.check(lib.trp_dev_powers(ctx.handle, 0, ptr(mont(x_3)), n, d_b.data_ptr()))
     d_pp = d_pp.reshape(n, 4)
+    d_b = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    ctx.check(lib.trp_dev_powers(ctx.handle, 0, ptr(mont(x_3)), n, d_b.data_ptr()))
+    d_z = dev(mont(z))
+    d_ip = torch.zeros((2, 4), dtype=torch.int64, device="cuda")
+    s_cur = dev(mont(1)).reshape(1, 4)
+    s_next = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    s_bufs = [torch.empty((n, 4), dtype=torch.int64, device="cuda"), s_next]
+    mark("P' and v")
+    cur = n
     for j in range(k):
-        half = 1 << (k - j - 1)
-        cur = 2 * half
+        half = cur // 2
         el = 32 * half                      # bytes per half vector of scalars
         ctx.check(lib.trp_dev_inner_products(ctx.handle, 0, d_pp.data_ptr() + el, 0, d_b.data_ptr(), 0, half, 1, d_ip[0].data_ptr()))
         ctx.check(lib.trp_dev_inner_products(ctx.handle, 0, d_pp.data_ptr(), 0, d_b.data_ptr() + el, 0, half, 1, d_ip[1].data_ptr()))
-        ctx.sync()
-        value_l, value_r = (unmont(r) for r in d_ip.cpu().numpy().view(np.uint64))
         l_rand, r_rand = rand(), rand()
-        cols = d_sc.reshape(-1)[:2 * (cur + 2) * 4].reshape(2, cur + 2, 4)
-        cols.zero_()
-        cols[0, :half] = d_pp[half:cur]
-        cols[1, half:cur] = d_pp[:half]
-        cols[:, cur:] = dev(np.stack([mont(value_l * z), mont(l_rand), mont(value_r * z), mont(r_rand)])).reshape(2, 2, 4)
-        torch.cuda.synchronize()
-        ctx.check(lib.trp_dev_msm_var(ctx.handle, d_g.data_ptr(), cols.data_ptr(), cur + 2, 2, d_pt.data_ptr()))
-        ctx.sync()
-        pts = [r[:8].copy() for r in d_pt[:2].cpu().numpy().view(np.uint64)]
+        ctx.check(lib.trp_dev_ipa_round_scalars(ctx.handle, 0, d_pp.data_ptr(), s_cur.data_ptr(), cur, lo, cnt, cnt + 2, cols.data_ptr()))
+        if rank == 0:                       # [z <p', b>] U + [rand] W: one rank adds them (the values never visit the host)
+            ctx.check(lib.trp_dev_field_op(ctx.handle, 0, 2 | 16, d_ip.data_ptr(), d_z.data_ptr(), d_ip.data_ptr(), 2))
+            cols[:, cnt] = d_ip
+            cols[:, cnt + 1] = dev(np.stack([mont(l_rand), mont(r_rand)]))
+        else:
+            cols[:, cnt:] = 0
+        pts = msm_pair(2)
+        mark(f"round {cur}")
         transcript.write_point(pts[0])
         transcript.write_point(pts[1])
         u_j = transcript.squeeze_challenge_scalar()
         u_j_inv = pow(u_j, -1, p)
         ctx.check(lib.trp_dev_fold(ctx.handle, 0, d_pp.data_ptr(), half, ptr(mont(u_j_inv))))
         ctx.check(lib.trp_dev_fold(ctx.handle, 0, d_b.data_ptr(), half, ptr(mont(u_j))))
-        ctx.check(lib.trp_dev_generator_collapse(ctx.handle, d_g.data_ptr(), half, ptr(mont(u_j))))
-        ctx.sync()
-        d_g[half:half + 2] = params.d_uw    # U, W follow the collapsed generators
+        nxt = s_bufs[j & 1]
+        ctx.check(lib.trp_dev_ipa_s_double(ctx.handle, 0, s_cur.data_ptr(), n // cur, ptr(mont(u_j)), nxt.data_ptr()))
+        s_cur = nxt
         f = (f + l_rand * u_j_inv + r_rand * u_j) % p
-    ctx.sync()
+        cur = half
     c = unmont(d_pp[0].cpu().numpy().view(np.uint64))
     transcript.write_scalar(c)
     transcript.write_scalar(f)

@@ -505,14 +505,18 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     if len(instances) != cs.num_instance or len(advice) != cs.num_advice:
         raise ValueError("InvalidInstances / wrong number of advice columns")
     transcript.common_scalar(vk.transcript_repr)
+    if hasattr(rand, "prefetch"):              # the two bulk draws of a proof (random polynomial, the opening's S) on a worker thread
+        rand.prefetch(n, 2)
     if hasattr(B, "begin_proof"):              # instance + advice + (A', S', Z) per lookup + one Z per permutation chunk
         chunks = -(-len(cs.permutation) // (vk.cs_degree - 2)) if cs.permutation else 0
         B.begin_proof(cs.num_instance + cs.num_advice + 3 * len(cs.lookups) + chunks)
     import time as _time
     _t = [_time.perf_counter()]
 
-    def tick(name):                            # wall-clock per phase (the backend's work is synchronous at this level)
-        if timings is not None:
+    def tick(name):                            # wall-clock per phase; an asynchronous backend is drained first so that the
+        if timings is not None:                # time lands in the phase that enqueued the work (a handful of waits per proof)
+            if hasattr(B, "_wait"):
+                B._wait()
             now = _time.perf_counter()
             timings[name] = timings.get(name, 0.0) + now - _t[0]
             _t[0] = now
@@ -537,8 +541,12 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
 
     # ---- advice columns --------------------------------------------------------------------------------------------------------
     adv_values = [column(c, "advice") for c in advice]
-    for v in adv_values:
-        B.set_rows(v, usable, [rand() for _ in range(usable, n)])
+    adv_rows = [[rand() for _ in range(usable, n)] for _ in adv_values]
+    if hasattr(B, "set_rows_many"):            # one upload for all columns' blinding rows
+        B.set_rows_many(adv_values, usable, adv_rows)
+    else:
+        for v, rows_ in zip(adv_values, adv_rows):
+            B.set_rows(v, usable, rows_)
     adv_blinds = [rand() for _ in adv_values]
     for cm in B.commit_lagrange_many(adv_values, adv_blinds, **sparse_kw):
         transcript.write_point(cm)
@@ -792,15 +800,6 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
 
 
 # ---- the product backend: libtrp.so, device resident ----------------------------------------------------------------------------------
-_PROVER_STREAMS = {}
-
-
-def _prover_stream(torch, device):
-    if device not in _PROVER_STREAMS:
-        _PROVER_STREAMS[device] = torch.cuda.Stream(device=device)
-    return _PROVER_STREAMS[device]
-
-
 class GpuBackend:
     """Backend of keygen / create_proof over the CUDA library.  Every polynomial is a torch int64 tensor (n, 4) of Montgomery
     limbs in HBM and every operation is a trp_dev_* entry point of include/tr_prover.h; the host sees scalars and points only.
@@ -824,10 +823,7 @@ class GpuBackend:
         # thread's current stream, so everything the prover enqueues is ordered by the stream itself and the host only waits
         # when it reads a result (.cpu()).  (Round 1 kept the library on its own non-blocking stream and fenced every call
         # with a device-wide synchronize: ~3 000 fences per proof at k = 20.)
-        torch.cuda.synchronize()
-        self.stream = _prover_stream(torch, ctx.device)        # one per process and device, shared by every backend and ctx
-        torch.cuda.set_stream(self.stream)
-        ctx.set_stream(self.stream.cuda_stream)
+        self.stream = ctx.bind_torch_stream()                  # one per process and device, shared by every backend and ctx
         self.params = params if params is not None else Params.new(ctx, k)
         self.dom = EvaluationDomain(ctx, cs_degree, k)
         self.extended_k = self.dom.extended_k
@@ -916,6 +912,18 @@ class GpuBackend:
         if len(values):
             v[start:start + len(values)] = self._dev(self._limbs(values))
         return v
+
+    def set_rows_many(self, vs, start, values):
+        """vs[i][start : start + len(values[i])] = values[i] with ONE host -> device copy"""
+        flat = [x for vals in values for x in vals]
+        if not flat:
+            return
+        d = self._dev(self._limbs(flat))
+        off = 0
+        for v, vals in zip(vs, values):
+            if vals:
+                v[start:start + len(vals)] = d[off:off + len(vals)]
+                off += len(vals)
 
     def random_vec(self, rand):
         bulk = getattr(rand, "vector", None)           # optional bulk draw: (n, 4) Montgomery limbs
@@ -1276,4 +1284,8 @@ class GpuBackend:
             def squeeze_challenge_scalar(self): return transcript.squeeze_challenge_scalar()
 
         self._sync()
-        self._ipa.create_proof(self.ipa_params, rand, _Adapter(), p_poly, p_blind, x_3, rand_vector=getattr(rand, "vector", None))
+        self._ipa.create_proof(self.ipa_params, rand, _Adapter(), p_poly, p_blind, x_3, rand_vector=getattr(rand, "vector", None),
+                               dist=self._ipa_dist())
+
+    def _ipa_dist(self):
+        return None                       # sharded_backend.ShardedGpuBackend divides the opening's rounds between its ranks

@@ -24,6 +24,8 @@ ShardedCommits is a mixin over any backend of plonk.create_proof, so the commit 
 oracle's PythonBackend (tests/test_parallel_cpu.py); the exchange helpers (parallel.py) are gloo-tested on CPU tensors."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import parallel
@@ -72,9 +74,12 @@ class ShardedCommits:
 
 class ShardedRng:
     """The caller's RNG of a multi-GPU create_proof: every rank must draw the SAME stream.  Rank 0 takes 32 bytes from the OS,
-    the seed is broadcast, and the stream is AES-256-CTR keyed by it (a CSPRNG; `cryptography` is in the image): rand() reads
-    64 bytes and reduces them mod p (pasta's Field::random = from_u512 of eight next_u64), vector(n) takes n x 32 bytes with the
-    top two bits cleared, used as Montgomery limbs (uniform below 2^254: 2^-128 from uniform mod p)."""
+    the seed is broadcast, and the stream is AES-256-CTR keyed by it (a CSPRNG; `cryptography` is in the image).
+    rand() reads 64 bytes of the scalar stream (counter block 0 onwards) and reduces them mod p -- pasta's Field::random =
+    from_u512 of eight next_u64.  vector(n), the bulk draw of a random polynomial, is draw number i of its own stream (nonce
+    i + 1): n x 32 bytes with the top two bits cleared, used as Montgomery limbs (uniform below 2^254, 2^-128 from uniform mod p).
+    Bulk draws do not depend on how many scalars were drawn before them, so prefetch(n, count) can produce the next `count` of
+    them on a worker thread while the GPU is busy (32 MiB of keystream per polynomial at k = 20)."""
 
     def __init__(self, p: int, dist=None, device="cpu", seed: bytes = None):
         import os
@@ -85,23 +90,45 @@ class ShardedRng:
             t = torch.tensor(list(seed), dtype=torch.uint8, device=device)
             dist.broadcast(t, src=0)
             seed = bytes(t.cpu().tolist())
-        from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
         self.seed, self.p = seed, p
-        self._enc = Cipher(algorithms.AES(seed), modes.CTR(b"\0" * 16)).encryptor()
+        self._enc = self._stream(0)
+        self._buf, self._off = b"", 0
         self.draws = 0
+        self._vec_index = 0
+        self._pending = {}
+        self._pool = None
 
-    def _bytes(self, k):
-        return self._enc.update(b"\0" * k)
+    def _stream(self, nonce: int):
+        from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+        return Cipher(algorithms.AES(self.seed), modes.CTR(nonce.to_bytes(8, "big") + b"\0" * 8)).encryptor()
 
     def __call__(self):
         self.draws += 1
-        return int.from_bytes(self._bytes(64), "little") % self.p
+        if self._off + 64 > len(self._buf):                  # keystream in 64 KiB blocks (a proof draws ~2 800 scalars)
+            self._buf, self._off = self._enc.update(bytes(1 << 16)), 0
+        v = int.from_bytes(self._buf[self._off:self._off + 64], "little") % self.p
+        self._off += 64
+        return v
+
+    def _make_vector(self, index: int, n: int):
+        a = np.frombuffer(self._stream(index + 1).update(bytes(32 * n)), dtype=np.uint64).reshape(n, 4).copy()
+        a[:, 3] &= np.uint64((1 << 62) - 1)
+        return a
+
+    def prefetch(self, n: int, count: int):
+        from concurrent.futures import ThreadPoolExecutor
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(max_workers=1)
+        for i in range(self._vec_index, self._vec_index + count):
+            if (i, n) not in self._pending:
+                self._pending[(i, n)] = self._pool.submit(self._make_vector, i, n)
 
     def vector(self, n):
-        a = np.frombuffer(self._bytes(32 * n), dtype=np.uint64).reshape(n, 4).copy()
-        a[:, 3] &= np.uint64((1 << 62) - 1)
+        i = self._vec_index
+        self._vec_index += 1
         self.draws += n
-        return a
+        fut = self._pending.pop((i, n), None)
+        return fut.result() if fut is not None else self._make_vector(i, n)
 
 
 class ShardedGpuBackend(ShardedCommits, GpuBackend):
@@ -133,6 +160,10 @@ class ShardedGpuBackend(ShardedCommits, GpuBackend):
     def close(self):
         self._xbuf.clear()
         super().close()
+
+    def _ipa_dist(self):
+        w = self.world
+        return self.dist if (w > 1 and w & (w - 1) == 0 and w <= self.n and os.environ.get("TRP_IPA_SHARDED", "1") != "0") else None
 
     # -- lagrange_to_coeff: blocks of columns, one in-place all_gather --------------------------------------------------------------
     def lagrange_to_coeff_many(self, vs):
@@ -272,7 +303,6 @@ class ShardedGpuBackend(ShardedCommits, GpuBackend):
         if self.world == 1:
             return super().quotient(ast, ext_polys)
         t, n, ncos, G, H = self.torch, self.n, self.j - 1, self.world, self.HALO
-        prog = P.compile_ast(ast, self.p)
         dyn = [i for i, c in enumerate(ext_polys) if id(c) not in self._static]
         in_arena = [self._arena_slot.get(id(ext_polys[i])) for i in dyn]
         if dyn and all(a is not None and a[1] is ext_polys[i] for a, i in zip(in_arena, dyn)):
@@ -286,18 +316,32 @@ class ShardedGpuBackend(ShardedCommits, GpuBackend):
         row0, S, _ = self._slice_rows()
         width = S + 2 * H
         own = self._buf("q_own", (max(per, 1), n, 4))
-        send = self._buf("q_send", (G, max(per, 1), width, 4))
-        recv = self._buf("q_recv", (G, max(per, 1), width, 4))
-        flat = recv.view(G * max(per, 1), width, 4)
+        send = [self._buf(f"q_send{b}", (G, max(per, 1), width, 4)) for b in (0, 1)]
+        recv = [self._buf(f"q_recv{b}", (G, max(per, 1), width, 4)) for b in (0, 1)]
         local = t.empty((ncos, S, 4), dtype=t.int64, device="cuda")
+        prog = None
+
+        def run_program(cs, handle):
+            if handle is not None:
+                handle.wait()                              # the prover's stream waits for the exchange of this coset
+            flat = recv[cs & 1].view(G * max(per, 1), width, 4)
+            ptrs = [flat[slot[i]].data_ptr() if i in slot else self._static[id(c)][cs].data_ptr() for i, c in enumerate(ext_polys)]
+            self.ev.evaluate_device_rows(prog, self.dom, ptrs, local[cs].data_ptr(), cs, row0, S, H, H)
+
+        # software pipeline over the cosets: the all-to-all of coset c runs on NCCL's stream while this rank's NTTs of coset c + 1
+        # run on the prover's stream; the program of coset c follows.  The program is compiled (host) while the first NTTs run.
+        pending = None
         for cs in range(ncos):
             if hi > lo:
                 self.ctx.check(self.lib.trp_dev_coeff_to_coset(self.dom.handle, coeff[lo].data_ptr(), own.data_ptr(), hi - lo, cs))
-                parallel.pack_row_slices(own, hi - lo, n, G, H, H, send)
-            if ncols:
-                parallel.exchange_row_slices(send, recv, self.dist)
-            ptrs = [flat[slot[i]].data_ptr() if i in slot else self._static[id(c)][cs].data_ptr() for i, c in enumerate(ext_polys)]
-            self.ev.evaluate_device_rows(prog, self.dom, ptrs, local[cs].data_ptr(), cs, row0, S, H, H)
+                parallel.pack_row_slices(own, hi - lo, n, G, H, H, send[cs & 1])
+            handle = self.dist.all_to_all_single(recv[cs & 1], send[cs & 1], async_op=True) if ncols else None
+            if prog is None:
+                prog = P.compile_ast(ast, self.p)
+            if pending is not None:
+                run_program(*pending)
+            pending = (cs, handle)
+        run_program(*pending)
         gathered = t.empty((G, ncos, S, 4), dtype=t.int64, device="cuda")
         self.dist.all_gather_into_tensor(gathered, local)
         vals = gathered.permute(1, 0, 2, 3).reshape(ncos, n, 4).contiguous()

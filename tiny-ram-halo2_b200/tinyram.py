@@ -914,3 +914,53 @@ def _column_u64(prefix):
     if max(prefix) >= 1 << 64:
         return None
     return np.array(prefix, dtype=np.uint64)
+
+
+class HostWitness:
+    """A proof's witness columns (instance + advice as synthesize() returns them) packed once into PINNED host memory, in the
+    form that crosses PCIe: columns whose values fit 64 bits as u64 prefixes (the rows the circuit assigns), the few wide ones
+    as 4 x u64 canonical limbs.  upload(be) is the per-proof host -> device step of the end-to-end path: two asynchronous
+    copies, a scatter per column on the device and ONE multiplication by R^2 over the whole block (Montgomery form).
+    bytes = what a proof sends over PCIe (bench.py's e2e.h2d_bytes_per_step)."""
+
+    def __init__(self, be, columns):
+        import numpy as np
+        torch = be.torch
+        self.n, self.ncols = be.n, len(columns)
+        narrow, wide, self.meta = [], [], []
+        off_n = off_w = 0
+        for col in columns:
+            if isinstance(col, FixedColumn):
+                raise ValueError("witness columns only (fixed columns are key material)")
+            if len(col) > be.n:
+                raise ValueError("column longer than the domain")
+            arr = _column_u64(col)
+            if arr is not None:
+                self.meta.append((0, off_n, len(arr))); narrow.append(arr); off_n += len(arr)
+            else:
+                vals = col.tolist() if isinstance(col, np.ndarray) else col
+                limbs = np.frombuffer(b"".join((v % be.p).to_bytes(32, "little") for v in vals), dtype=np.uint64).reshape(len(vals), 4)
+                self.meta.append((1, off_w, len(vals))); wide.append(limbs); off_w += len(vals)
+        cat = lambda parts, shape: np.concatenate(parts) if parts else np.zeros(shape, dtype=np.uint64)
+        self.narrow = torch.from_numpy(cat(narrow, (0,)).view(np.int64)).pin_memory()
+        self.wide = torch.from_numpy(cat(wide, (0, 4)).view(np.int64).reshape(-1, 4)).pin_memory()
+        self.bytes = self.narrow.numel() * 8 + self.wide.numel() * 8
+
+    def upload(self, be, out=None):
+        """-> (ncols, n, 4) device block of Montgomery columns (views of it are plonk.GpuBackend vectors)"""
+        torch = be.torch
+        d_n = self.narrow.cuda(non_blocking=True)
+        d_w = self.wide.cuda(non_blocking=True)
+        if out is None:
+            out = torch.empty((self.ncols, self.n, 4), dtype=torch.int64, device="cuda")
+        out.zero_()
+        for c, (kind, off, ln) in enumerate(self.meta):
+            if not ln:
+                continue
+            if kind == 0:
+                out[c, :ln, 0] = d_n[off:off + ln]
+            else:
+                out[c, :ln] = d_w[off:off + ln]
+        r2 = be._dev(be._limbs([be.R]))
+        be.ctx.check(be.lib.trp_dev_field_op(be.ctx.handle, 0, 2 | 16, out.data_ptr(), r2.data_ptr(), out.data_ptr(), self.ncols * self.n))
+        return out
