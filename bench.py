@@ -52,7 +52,7 @@ DTYPE = "u32x8 (255-bit Montgomery)"
 
 
 def _config(extra=None):
-    c = {"workload": WORKLOAD, "k": K_LOG, "word_bits": WORD_BITS, "curve": "vesta", "rng": "AES-256-CTR keyed by an OS seed (rank 0's, broadcast)",
+    c = {"workload": WORKLOAD, "k": K_LOG, "word_bits": WORD_BITS, "curve": "vesta", "rng": "AES-256-CTR keyed by an OS seed (rank 0's, broadcast); random polynomials = a 32-byte key of that stream expanded on the device (BLAKE2b counter mode)",
          "l2_policy": "inputs larger than L2 (15.5 GiB of per-proof polynomials at k = 20)"}
     if extra:
         c.update(extra)
@@ -553,7 +553,9 @@ def measure_extras(pkg, ctx, stream, peaks, peak_src, int_peak_tmacs):
     e2e_ms = (time.perf_counter() - t0) / steps * 1e3
     acc_ms, acc_launches = prof["msm_accum_l1"]
     per_launch_ms = acc_ms / max(acc_launches, 1)
-    macs = m * n * windows * FMUL_PER_MIXED_ADD * MACS_PER_FMUL
+    # windows that actually receive digits: ceil(255 / c) (scalars are 255 bits; a 16th window at c = 17 only takes carries)
+    live_windows = min(windows, -(-255 // c_bits))
+    macs = m * n * live_windows * FMUL_PER_MIXED_ADD * MACS_PER_FMUL
     traffic, traffic_src = _traffic_from_profiles("msm_accum_l1", "ncu_accum_r*.json")
     out["msm"] = {"workload": f"{m} columns x (2^{K_LOG}+1) Vesta points, uniform Fp scalars, one resident base table (BASELINE.json configs[1])",
                   "Mpts_per_s": m * n / ms / 1e3, "ms_per_step": ms, "window_bits": c_bits, "windows": windows, "precomputed_bases": precomp,
@@ -562,7 +564,7 @@ def measure_extras(pkg, ctx, stream, peaks, peak_src, int_peak_tmacs):
                   "roofline": {"bound": "int32-pipe", "kernel": "msm_accum_l1_seg_kernel", "achieved": macs / (per_launch_ms * 1e-3) / 1e12,
                                "peak": int_peak_tmacs, "unit": "TMAC/s", "frac": macs / (per_launch_ms * 1e-3) / 1e12 / int_peak_tmacs,
                                "launch_ms": per_launch_ms, "traffic": traffic, "traffic_source": traffic_src,
-                               "model": f"cols*n*W*{FMUL_PER_MIXED_ADD} Fmul x {MACS_PER_FMUL} MAC, cols={m}, W={windows}, c={c_bits}",
+                               "model": f"cols*n*W*{FMUL_PER_MIXED_ADD} Fmul x {MACS_PER_FMUL} MAC, cols={m}, W={live_windows} windows with digits (table has {windows}), c={c_bits}",
                                "phase_ms_per_step": {k: round(v[0] / steps, 3) for k, v in prof.items() if v[1]}}}
     try:
         sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -266,6 +266,12 @@ int trp_group_fft(trp_ctx* ctx, uint64_t* points, unsigned log_n, const uint64_t
 int trp_params_new(trp_ctx* ctx, unsigned k, uint64_t* g, uint64_t* g_lagrange, uint64_t w[8], uint64_t u[8]);
 int trp_dev_params_new(trp_ctx* ctx, unsigned k, uint64_t* d_g, uint64_t* d_g_lagrange, uint64_t* d_wu /* w then u: 2 x 8 */);
 
+/* Bulk random field elements from a 32-byte key drawn from the caller's RNG: d_out[i] = Field::random over the byte stream
+ * BLAKE2b-512(key ++ u64_le(first_counter + i)), i.e. pasta_curves' from_u512 of the 64-byte digest, Montgomery form.  The random
+ * polynomials of create_proof (vanishing::Argument::commit, the IPA's S) draw 2^k scalars each from the caller's RNG in halo2; a
+ * device-resident prover expands a seed here instead (deterministic, the same on every GPU of a multi-GPU proof). */
+int trp_dev_random_field(trp_ctx* ctx, int which_field, const uint8_t key[32], uint64_t first_counter, size_t n, uint64_t* d_out);
+
 /* ---- glue / debug: elementwise field kernels over the ctx's scalar (field=0) or base (field=1) field ----
  * op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 sqr(a).  Host pointers.  Used by parity tests of K1 and by K7 callers. */
 int trp_field_op(trp_ctx* ctx, int which_field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);

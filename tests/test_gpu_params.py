@@ -157,3 +157,21 @@ def test_hash_to_curve_argument_errors(pkg, ctxs):
         pkg.hash_to_curve(ctx, "p")([b"a", b"bc"])
     with pytest.raises(ValueError):
         pkg.Params.new(ctx, 32)
+
+
+def test_random_field_is_blake2b_from_u512():
+    """trp_dev_random_field: out[i] = from_u512(BLAKE2b-512(key ++ u64_le(first + i))) in Montgomery form, both fields"""
+    import hashlib
+    import __graft_entry__ as ge
+    import torch
+    pkg = ge.load_package()
+    for curve, field in ((pkg.VESTA, O.FP), (pkg.PALLAS, O.FQ)):
+        ctx = pkg.Context(0, curve)
+        ctx.bind_torch_stream()
+        key, first, n = bytes(range(7, 39)), (1 << 40) + 5, 1000
+        out = torch.zeros((n, 4), dtype=torch.int64, device="cuda")
+        ctx.check(ctx.lib.trp_dev_random_field(ctx.handle, 0, key, first, n, out.data_ptr()))
+        got = O.limbs_to_ints(O.from_mont(field, out.cpu().numpy().view(np.uint64)))
+        p = O.MODULUS[field]
+        want = [int.from_bytes(hashlib.blake2b(key + (first + i).to_bytes(8, "little"), digest_size=64).digest(), "little") % p for i in range(n)]
+        assert got == want

@@ -279,3 +279,37 @@ def test_domain_transforms_k20_k22(pkg, ctxs, k):
     h = O.random_field_mont(O.FP, 1 << dom.extended_k, 60 + k)
     assert np.array_equal(dom.extended_to_coeff(h, divide_by_vanishing_poly=True), O.extended_to_coeff(O.FP, j, k, h, divide=True))
     dom.free()
+
+
+def test_tma_staged_ntt_pass_matches_the_default(pkg):
+    """the opt-in TMA-staged pass kernel (TRP_NTT_TMA=1: cp.async.bulk.tensor + mbarrier tile loads, csrc/ntt.cu) against the
+    oracle, in a subprocess because the switch is read once per process: forward NTTs of 2^11 .. 2^20 (two- and three-level pass
+    plans), lagrange_to_coeff, the zero-padded coeff_to_extended and a coset transform through the device entry points"""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import numpy as np
+        from util import O, pm
+        import __graft_entry__ as ge
+        pkg = ge.load_package()
+        ctx = pkg.Context(0, pkg.VESTA)
+        for log_n in (11, 13, 16, 20):
+            omega = O.to_mont(O.FP, O.ints_to_limbs([pm.Fp.root_of_unity(log_n)]))[0]
+            a = O.random_field_mont(O.FP, 2 << log_n, 90 + log_n).reshape(2, 1 << log_n, 4)
+            got = pkg.best_fft(ctx, a, omega, log_n)
+            for b in range(2):
+                assert np.array_equal(got[b], O.fft(O.FP, a[b], log_n, omega)), log_n
+        for j, k in ((6, 11), (6, 14), (3, 12)):
+            dom = pkg.EvaluationDomain(ctx, j, k)
+            n = 1 << k
+            cols = O.random_field_mont(O.FP, 2 * n, 70 + k).reshape(2, n, 4)
+            coeff = dom.lagrange_to_coeff(cols)
+            assert np.array_equal(coeff, O.lagrange_to_coeff(O.FP, j, k, cols).reshape(2, n, 4))
+            assert np.array_equal(dom.coeff_to_extended(coeff), O.coeff_to_extended(O.FP, j, k, coeff))
+            h = O.random_field_mont(O.FP, 1 << dom.extended_k, 60 + k)
+            assert np.array_equal(dom.extended_to_coeff(h, divide_by_vanishing_poly=True), O.extended_to_coeff(O.FP, j, k, h, divide=True))
+        print("tma ok")
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, "TRP_NTT_TMA": "1"}, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "tma ok" in out.stdout, out.stderr[-3000:]

@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "trp_dev_permutation_product", "trp_permutation_product", "trp_dev_lookup_product", "trp_lookup_product",
     "trp_dev_permute_expression_pair", "trp_permute_expression_pair",
     "trp_dev_eval_polynomials", "trp_dev_eval_polynomials_at", "trp_dev_linear_combination", "trp_eval_polynomial", "trp_dev_inner_products", "trp_compute_inner_product", "trp_dev_powers",
-    "trp_dev_kate_division", "trp_kate_division", "trp_dev_fold", "trp_dev_ipa_round_scalars", "trp_dev_ipa_s_double", "trp_dev_generator_collapse", "trp_dev_msm_var",
+    "trp_dev_kate_division", "trp_kate_division", "trp_dev_random_field", "trp_dev_fold", "trp_dev_ipa_round_scalars", "trp_dev_ipa_s_double", "trp_dev_generator_collapse", "trp_dev_msm_var",
     "trp_dev_hash_to_curve", "trp_hash_to_curve", "trp_dev_group_fft", "trp_group_fft", "trp_params_new", "trp_dev_params_new",
 ]
 
@@ -134,6 +134,7 @@ def load_library():
     L.trp_dev_kate_division.argtypes = [vp, i, vp, sz, vp, vp]
     L.trp_kate_division.argtypes = [vp, i, vp, sz, vp, vp]
     L.trp_dev_fold.argtypes = [vp, i, vp, sz, vp]
+    L.trp_dev_random_field.argtypes = [vp, i, ctypes.c_char_p, ctypes.c_uint64, sz, vp]
     L.trp_dev_ipa_round_scalars.argtypes = [vp, i, vp, vp, sz, sz, sz, sz, vp]
     L.trp_dev_ipa_s_double.argtypes = [vp, i, vp, sz, vp, vp]
     L.trp_dev_generator_collapse.argtypes = [vp, vp, sz, vp]

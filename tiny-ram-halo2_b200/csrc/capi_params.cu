@@ -6,6 +6,7 @@ using namespace ff;
 
 size_t trp_group_fft_ws_bytes(unsigned log_n);
 int trp_group_fft_impl(trp_ctx* ctx, void* d_points, unsigned log_n, const uint64_t omega[4], const uint64_t* scale, void* ws);
+int trp_random_field_impl(trp_ctx* ctx, int field, const uint8_t key[32], uint64_t first, size_t n, void* d_out);
 int trp_hash_to_curve_impl(trp_ctx* ctx, const char* domain_prefix, const uint8_t* d_msgs, size_t msg_len, const uint8_t* msg_prefix,
                            size_t prefix_len, int append_index, uint64_t first_index, size_t n, void* d_out);
 
@@ -58,6 +59,14 @@ int params_new_device(trp_ctx* ctx, unsigned k, uint64_t* d_g, uint64_t* d_gl, u
 }  // namespace
 
 extern "C" {
+
+int trp_dev_random_field(trp_ctx* ctx, int which_field, const uint8_t key[32], uint64_t first_counter, size_t n, uint64_t* d_out) {
+  if (!ctx) return TRP_E_INVALID;
+  Locked l(ctx);
+  if (!key || (n && !d_out)) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
+  const int field = which_field == 0 ? scalar_field_of(ctx->curve) : base_field_of(ctx->curve);
+  return trp_random_field_impl(ctx, field, key, first_counter, n, d_out);
+}
 
 int trp_dev_hash_to_curve(trp_ctx* ctx, const char* domain_prefix, const uint8_t* msg_prefix, size_t prefix_len, int append_index,
                           uint64_t first_index, size_t n, uint64_t* d_out) {

@@ -15,6 +15,7 @@
 // HBM traffic per transform: (#passes) x (read + write) of the vector, #passes = ceil(log_n / 10).
 #include "common.cuh"
 
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 #include <cstdlib>
 #include <type_traits>
 
@@ -237,6 +238,141 @@ __global__ void __launch_bounds__(NTT_THREADS, R >= 3 ? 2 : 3) ntt_pass_reg_kern
   }
 }
 
+// ---- TMA-staged pass (sm_100a: cp.async.bulk.tensor + mbarrier) ------------------------------------------------------------------
+// Same pass geometry and the same register-blocked butterflies as ntt_pass_reg_kernel, but the tile reaches shared memory
+// through the TMA unit instead of through registers: the 2^(s+c) elements of a tile are 2^s runs of 2^c adjacent elements
+// (2^c * 32 B contiguous), i.e. ONE 2-D box of the vector viewed as rows of 2^lo elements (later passes) or rows of
+// 2^(L-s) elements (first pass: the bit reversal turns the tile's index i into the row index bitrev_s(i), so the bit-reversed
+// gather is just a box whose rows are read in a different order).  One elected thread arms an mbarrier with the tile's byte
+// count and issues the bulk tensor copies (<= 256 rows per box); the CTA waits on the barrier and then runs every stage group
+// in place on that buffer (element (t, i) lives where the box put it; a thread rewrites only the slots it read), so no
+// global load instruction, no address arithmetic per element and no bit-reversal arithmetic on the load path remain.
+// Out-of-range rows of a zero-padded input (n_src < 2^L) come back as zeros from the TMA unit itself.
+struct NttTma {
+  CUtensorMap map;        // rank 3: { 8 x u32 per element x row length, rows, batch columns }
+  unsigned rows_per_box;  // <= 256
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <class PR, int R>
+__global__ void __launch_bounds__(NTT_THREADS, R >= 3 ? 2 : 3) ntt_pass_tma_kernel(NttPass p, const __grid_constant__ NttTma tma) {
+  extern __shared__ __align__(128) uint4 smem[];
+  const unsigned s = p.s, c = p.c, L = p.L, lo = p.lo;
+  const unsigned nelem = 1u << (s + c);
+  uint4* tile = smem;                                      // AoS: element e at tile[2 e], tile[2 e + 1]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * nelem);
+  const unsigned g = blockIdx.x;
+  uint4* dst = p.dst + 2 * (size_t)blockIdx.y * p.dst_stride;
+  const unsigned cmask = (1u << c) - 1;
+  unsigned low_base = 0, hi = 0;
+  if (!p.first) { low_base = (g & ((1u << (lo - c)) - 1)) << c; hi = g >> (lo - c); }
+  auto pos_of = [&](unsigned t, unsigned i) -> unsigned {
+    if (p.first) return (t << (L - c)) | (g << s) | i;
+    return (hi << (lo + s)) | (i << lo) | low_base | t;
+  };
+  // where the box put element (t, i): row-major [row][run of 2^c]; the first pass reads rows (and the run) bit-reversed
+  auto slot = [&](unsigned t, unsigned i) -> unsigned {
+    if (p.first) return ((s ? (__brev(i) >> (32 - s)) : 0u) << c) | (c ? (__brev(t) >> (32 - c)) : 0u);
+    return (i << c) | t;
+  };
+
+  // ---- tile load: one thread, TMA ------------------------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(nelem * 32u) : "memory");
+    const unsigned rows = 1u << s;
+    // first pass: inner coordinate = bitrev_{L-s-c}(g) runs in, rows 0 .. 2^s; later passes: inner = low_base, rows from hi * 2^s
+    const unsigned x0 = (p.first ? ((L - s - c) ? (__brev(g) >> (32 - (L - s - c))) : 0u) << c : low_base) * 8u;
+    const unsigned r0 = p.first ? 0u : hi << s;
+    for (unsigned r = 0; r < rows; r += tma.rows_per_box) {
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"(smem_u32(tile + 2 * ((size_t)r << c))), "l"(&tma.map), "r"(x0), "r"(r0 + r), "r"((unsigned)blockIdx.y), "r"(smem_u32(bar))
+          : "memory");
+    }
+  }
+  {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0; selp.u32 %0, 1, 0, q; }"
+                   : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+    }
+  }
+
+  // ---- the stage groups, in place ---------------------------------------------------------------------------------------------
+  const unsigned ngroups = (s + R - 1) / R;
+  unsigned q0 = 0;
+  for (unsigned gi = 0; gi < ngroups; ++gi) {
+    const unsigned r = s / ngroups + (gi < s % ngroups ? 1u : 0u);
+    const bool gfirst = gi == 0, glast = gi + 1 == ngroups;
+    const unsigned units = nelem >> r, tile_units_log = s - r;
+    auto body = [&](auto rtag) {
+      constexpr int RR = decltype(rtag)::value;
+      constexpr int E = 1 << RR;
+      for (unsigned u = threadIdx.x; u < units; u += blockDim.x) {
+        unsigned t, j;
+        if (glast && p.first) { j = u & ((1u << tile_units_log) - 1); t = u >> tile_units_log; }   // contiguous stores along i
+        else { t = u & cmask; j = u >> c; }
+        const unsigned j_low = j & ((1u << q0) - 1), j_high = j >> q0;
+        const unsigned i_base = (j_high << (q0 + RR)) | j_low;
+        Fe<PR> x[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const unsigned i = i_base | ((unsigned)e << q0);
+          const unsigned sl = slot(t, i);
+          x[e] = lds_fe<PR>(tile, tile + 1, 2 * sl);
+          if (gfirst && p.pre) {
+            const unsigned sidx = p.first ? (L ? (__brev(pos_of(t, i)) >> (32 - L)) : 0u) : pos_of(t, i);
+            if (sidx < p.n_src) x[e] = fe_mul(x[e], fe_load_ro<PR>(p.pre + 2 * (sidx % p.pre_period)));
+          }
+        }
+        const unsigned low = p.first ? 0u : (low_base | t);
+#pragma unroll
+        for (int a = 0; a < RR; ++a) {
+          const unsigned tt = lo + q0 + a;
+#pragma unroll
+          for (int b = 0; b < E / 2; ++b) {
+            const int el = b & ((1 << a) - 1);
+            const int e0 = ((b >> a) << (a + 1)) | el, e1 = e0 | (1 << a);
+            Fe<PR> y = x[e1];
+            if (tt > 0 && !(el == 0 && gfirst && p.first)) {
+              const unsigned jl = j_low | ((unsigned)el << q0);
+              const unsigned expo = ((jl << lo) | low) << (L - tt - 1);
+              y = fe_mul(y, fe_load_ro<PR>(p.tw + 2 * (size_t)expo));
+            }
+            x[e1] = fe_sub(x[e0], y);
+            x[e0] = fe_add(x[e0], y);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const unsigned i = i_base | ((unsigned)e << q0);
+          if (glast) {
+            unsigned pos = pos_of(t, i);
+            if (p.last && pos >= p.n_dst) continue;
+            Fe<PR> v = x[e];
+            if (p.last && p.post) v = fe_mul(v, fe_load_ro<PR>(p.post + 2 * (pos % p.post_period)));
+            fe_store(dst + 2 * (size_t)pos, v);
+          } else {
+            const unsigned sl = slot(t, i);
+            sts_fe(tile, tile + 1, 2 * sl, x[e]);
+          }
+        }
+      }
+    };
+    if (r == 1) body(std::integral_constant<int, 1>());
+    else if (r == 2) body(std::integral_constant<int, 2>());
+    else if constexpr (R >= 3) body(std::integral_constant<int, 3>());
+    if (!glast) __syncthreads();
+    q0 += r;
+  }
+}
+
 // tab[i] = omega^i, i < count
 template <class PR>
 __global__ void gen_twiddles_kernel(uint4* tab, Fe<PR> omega, unsigned count, unsigned chunk) {
@@ -256,6 +392,33 @@ __global__ void copy_columns_kernel(const uint4* src, uint4* dst, size_t n, size
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * n) return;
   dst[2 * (size_t)blockIdx.y * dst_stride + i] = src[2 * (size_t)blockIdx.y * src_stride + i];
+}
+
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+// The pass's source as a rank-3 tensor of u32: { 8 * row_len, rows, batch }, box { 8 * 2^c, rows_per_box, 1 }
+bool encode_pass_map(NttTma& out, const void* src, size_t row_len, size_t rows, size_t batch, size_t batch_stride, unsigned c, unsigned rows_per_box) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {8 * (cuuint64_t)row_len, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)row_len * 32, (cuuint64_t)batch_stride * 32};       // bytes, dims 1 and 2
+  cuuint32_t box[3] = {8u << c, rows_per_box, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (batch == 1) strides[1] = strides[0] * rows;                                        // unused, but must be a multiple of 16
+  out.rows_per_box = rows_per_box;
+  return enc(&out.map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 struct PassPlan { unsigned lo, s, c; };
@@ -351,6 +514,23 @@ int ntt_run(trp_ctx* ctx, const void* d_src, void* d_dst, size_t batch, unsigned
     } else if (radix_log == 2) {
       unsigned th = nelem / 4 < NTT_THREADS ? nelem / 4 : NTT_THREADS;
       if (th < 32) th = 32;
+      // TMA-staged tile loads (TRP_NTT_TMA=1; profiles/ncu_ntt_r02.md has the A/B): needs whole rows, so a zero-padded first
+      // pass qualifies only when the padding starts on a row boundary
+      static const bool use_tma = [] { const char* e = getenv("TRP_NTT_TMA"); return e && atoi(e) == 1; }();
+      const size_t row_len = p.first ? (N >> p.s) : ((size_t)1 << p.lo);
+      const size_t rows = p.first ? (p.n_src / row_len) : (N >> p.lo);
+      if (use_tma && p.s >= 2 && (!p.first || (p.n_src % row_len == 0 && rows >= 1)) && ((uintptr_t)in % 16 == 0)) {
+        NttTma tma;
+        const unsigned rpb = (1u << p.s) < 256u ? (1u << p.s) : 256u;
+        if (encode_pass_map(tma, in, row_len, rows, batch, in_stride, p.c, rpb)) {
+          const size_t smem_tma = smem + 16;
+          if (smem_tma > 48 * 1024)
+            TRP_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_tma_kernel<PR, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((32u << TILE_LOG_MAX) + 16)));
+          ntt_pass_tma_kernel<PR, 2><<<grid, th, smem_tma, ctx->stream>>>(p, tma);
+          TRP_LAUNCHED(ctx);
+          continue;
+        }
+      }
       if (smem > 48 * 1024)
         TRP_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_reg_kernel<PR, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32u << TILE_LOG_MAX)));
       ntt_pass_reg_kernel<PR, 2><<<grid, th, smem, ctx->stream>>>(p);

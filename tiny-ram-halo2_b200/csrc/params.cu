@@ -30,6 +30,34 @@ __global__ void __launch_bounds__(64) h2c_kernel(h2c::H2cConsts K, const uint8_t
   fe_store(out + 4 * i + 2, y);
 }
 
+// ---- bulk random field elements: a CSPRNG seed expanded on the device ---------------------------------------------------------------
+// out[i] = Field::random over the 64 bytes BLAKE2b-512(key ++ u64_le(first + i)) -- pasta_curves' from_u512 (lo * R^2 + hi * R^3 in
+// Montgomery products) -- so a random polynomial (vanishing::Argument::commit's random poly, the IPA's S) costs the caller's RNG
+// 32 bytes instead of 64 n, on every GPU alike.
+struct Key32 { uint8_t b[32]; };
+template <class PR>
+__global__ void __launch_bounds__(128) random_field_kernel(Key32 key, uint64_t first, size_t n, uint4* out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  h2c::B2b s;
+  h2c::b2b_init(s);
+  h2c::b2b_update(s, key.b, 32);
+  uint8_t ctr[8], d[64];
+  const uint64_t c = first + i;
+  for (int k = 0; k < 8; ++k) ctr[k] = (uint8_t)(c >> (8 * k));
+  h2c::b2b_update(s, ctr, 8);
+  h2c::b2b_final(s, d);
+  Fe<PR> lo, hi, r2;
+  for (int k = 0; k < 8; ++k) {
+    lo.v[k] = (uint32_t)d[4 * k] | ((uint32_t)d[4 * k + 1] << 8) | ((uint32_t)d[4 * k + 2] << 16) | ((uint32_t)d[4 * k + 3] << 24);
+    hi.v[k] = (uint32_t)d[32 + 4 * k] | ((uint32_t)d[32 + 4 * k + 1] << 8) | ((uint32_t)d[32 + 4 * k + 2] << 16) | ((uint32_t)d[32 + 4 * k + 3] << 24);
+    r2.v[k] = PR::r2(k);
+  }
+  const Fe<PR> r3 = fe_mul(r2, r2);
+  for (int k = 0; k < 3; ++k) { fe_final_sub(lo); fe_final_sub(hi); }      // halves < 2^256 < 4p: fe_mul expects reduced operands
+  fe_store(out + 2 * i, fe_add(fe_mul(lo, r2), fe_mul(hi, r3)));
+}
+
 // ---- group FFT ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ size_t bitrev(size_t x, unsigned bits) { return bits ? (size_t)(__brevll((unsigned long long)x) >> (64 - bits)) : 0; }
 
@@ -175,6 +203,17 @@ size_t trp_group_fft_ws_bytes(unsigned log_n) {
 int trp_group_fft_impl(trp_ctx* ctx, void* d_points, unsigned log_n, const uint64_t omega[4], const uint64_t* scale, void* ws) {
   if (ctx->curve == TRP_CURVE_PALLAS) return group_fft_run<FqParams, FpParams>(ctx, d_points, log_n, omega, scale, ws);
   return group_fft_run<FpParams, FqParams>(ctx, d_points, log_n, omega, scale, ws);
+}
+
+int trp_random_field_impl(trp_ctx* ctx, int field, const uint8_t key[32], uint64_t first, size_t n, void* d_out) {
+  if (n == 0) return TRP_OK;
+  Key32 k;
+  memcpy(k.b, key, 32);
+  unsigned blocks = (unsigned)((n + 127) / 128);
+  if (field == 0) random_field_kernel<FpParams><<<blocks, 128, 0, ctx->stream>>>(k, first, n, (uint4*)d_out);
+  else random_field_kernel<FqParams><<<blocks, 128, 0, ctx->stream>>>(k, first, n, (uint4*)d_out);
+  TRP_LAUNCHED(ctx);
+  return TRP_OK;
 }
 
 int trp_hash_to_curve_impl(trp_ctx* ctx, const char* domain_prefix, const uint8_t* d_msgs, size_t msg_len, const uint8_t* msg_prefix,

@@ -85,8 +85,8 @@ def create_proof(params: IpaParams, rand, transcript, p_poly, p_blind, x_3, rand
     """poly::commitment::prover::create_proof(params, rng, transcript, p_poly, p_blind, x_3).
 
     p_poly: (n, 4) Montgomery host array or a cuda int64 tensor (coefficient form); p_blind, x_3: canonical ints.
-    rand() draws one canonical scalar; rand_vector(n), if given, draws n at once as an (n, 4) Montgomery array (the
-    coefficients of the blinding polynomial S).  transcript: write_point((8,) affine Montgomery limbs),
+    rand() draws one canonical scalar; rand_vector(n), if given, draws n at once as an (n, 4) Montgomery array or cuda tensor
+    (the coefficients of the blinding polynomial S).  transcript: write_point((8,) affine Montgomery limbs),
     write_scalar(int), squeeze_challenge_scalar() -> int.  Nothing is returned: like halo2, the proof is what was written
     to the transcript.
 
@@ -153,9 +153,13 @@ def create_proof(params: IpaParams, rand, transcript, p_poly, p_blind, x_3, rand
     # random polynomial S with a root at x_3
     s_host = rand_vector(n) if rand_vector else np.stack([mont(rand()) for _ in range(n)])
     mark("draw S")
-    d_s = dev(as_u64(s_host))
+    if hasattr(s_host, "data_ptr"):             # already on the device (a seed expanded there: trp_dev_random_field)
+        d_s = s_host.reshape(n, 4)
+        s0 = unmont(d_s[0].cpu().numpy().view(np.uint64))
+    else:
+        d_s = dev(as_u64(s_host))
+        s0 = unmont(as_u64(s_host)[0])
     mark("upload S")
-    s0 = unmont(as_u64(s_host)[0])
     s_at_x3 = evaluate(d_s, x_3)
     set_elem(d_s, 0, s0 - s_at_x3)
     s_poly_blind = rand()

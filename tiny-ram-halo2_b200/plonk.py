@@ -505,8 +505,6 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     if len(instances) != cs.num_instance or len(advice) != cs.num_advice:
         raise ValueError("InvalidInstances / wrong number of advice columns")
     transcript.common_scalar(vk.transcript_repr)
-    if hasattr(rand, "prefetch"):              # the two bulk draws of a proof (random polynomial, the opening's S) on a worker thread
-        rand.prefetch(n, 2)
     if hasattr(B, "begin_proof"):              # instance + advice + (A', S', Z) per lookup + one Z per permutation chunk
         chunks = -(-len(cs.permutation) // (vk.cs_degree - 2)) if cs.permutation else 0
         B.begin_proof(cs.num_instance + cs.num_advice + 3 * len(cs.lookups) + chunks)
@@ -926,6 +924,11 @@ class GpuBackend:
                 off += len(vals)
 
     def random_vec(self, rand):
+        key = getattr(rand, "bulk_key", None)          # optional: 32 bytes of the caller's RNG, expanded on the device
+        if key is not None:
+            out = self._new()
+            self.ctx.check(self.lib.trp_dev_random_field(self.ctx.handle, 0, key(), 0, self.n, out.data_ptr()))
+            return out
         bulk = getattr(rand, "vector", None)           # optional bulk draw: (n, 4) Montgomery limbs
         return self._dev(bulk(self.n)) if bulk else self._dev(self._limbs([rand() for _ in range(self.n)]))
 
@@ -1284,8 +1287,8 @@ class GpuBackend:
             def squeeze_challenge_scalar(self): return transcript.squeeze_challenge_scalar()
 
         self._sync()
-        self._ipa.create_proof(self.ipa_params, rand, _Adapter(), p_poly, p_blind, x_3, rand_vector=getattr(rand, "vector", None),
-                               dist=self._ipa_dist())
+        bulk = (lambda n_: self.random_vec(rand)) if hasattr(rand, "bulk_key") else getattr(rand, "vector", None)
+        self._ipa.create_proof(self.ipa_params, rand, _Adapter(), p_poly, p_blind, x_3, rand_vector=bulk, dist=self._ipa_dist())
 
     def _ipa_dist(self):
         return None                       # sharded_backend.ShardedGpuBackend divides the opening's rounds between its ranks

@@ -110,6 +110,16 @@ class ShardedRng:
         self._off += 64
         return v
 
+    def bulk_key(self) -> bytes:
+        """32 bytes of the scalar stream: the key a device-resident backend expands into a random polynomial
+        (plonk.GpuBackend.random_vec -> trp_dev_random_field), instead of 64 n bytes of keystream crossing PCIe"""
+        if self._off + 32 > len(self._buf):
+            self._buf, self._off = self._enc.update(bytes(1 << 16)), 0
+        k = self._buf[self._off:self._off + 32]
+        self._off += 32
+        self.draws += 1
+        return k
+
     def _make_vector(self, index: int, n: int):
         a = np.frombuffer(self._stream(index + 1).update(bytes(32 * n)), dtype=np.uint64).reshape(n, 4).copy()
         a[:, 3] &= np.uint64((1 << 62) - 1)
