@@ -186,3 +186,58 @@ def test_copy_blocks_nested_in_a_wide_block_take_the_general_path(PL):
                ((A, cols[0], 77), (A, cols[4], 3))]
     pairs2, blocks2 = PL._split_disjoint_blocks(cs, n, list(copies2))
     assert blocks2 == [(2, 5, 3, 5, 4)]
+
+
+def test_cached_quotient_program_equals_a_fresh_compile(PL):
+    """GpuBackend.quotient_program keeps the compiled quotient program of a proving key and patches the challenge-dependent
+    constants (theta, beta, gamma, y, beta * DELTA^i).  Run here over the oracle's PythonBackend: for two proofs of the same key
+    (the second one takes the cached path) the patched program must equal a fresh compile of that proof's Ast, for the small
+    test circuit and for the real TinyRamCircuit (lookups with theta, a 47-chunk permutation)."""
+    import random
+    import numpy as np
+    from util import pm
+    import plonk_model as VM
+    import plonk_circuits
+    import tinyram_programs as TP
+    import __graft_entry__ as ge
+    ge.load_package()
+    from tiny_ram_halo2_b200 import poly as P, tinyram as TR, trace as T
+    C = pm.Vesta
+
+    class Stop(Exception):
+        pass
+
+    class Probe(VM.PythonBackend):
+        checked = 0
+
+        def quotient_program(self, pk, build_h, challenges, n_perm):
+            got = PL.GpuBackend.quotient_program(self, pk, build_h, challenges, n_perm)
+            assert got is not None
+            prog, keys = got
+            ast, keys_fresh = build_h(*challenges)
+            fresh = P.compile_ast(ast, self.p)
+            assert keys == keys_fresh and (prog.code == fresh.code).all() and prog.consts == fresh.consts and prog.n_regs == fresh.n_regs
+            Probe.checked += 1
+            if self.stop_after_check:
+                raise Stop()
+            return None                                  # carry on with the Ast path: the proof must still verify
+
+    rnd = random.Random(5)
+    rand = lambda: rnd.randrange(C.scalar.p)
+    cs, fixed, copies, adv, inst = plonk_circuits.standard(PL, wide_lookup=True)
+    be = Probe(C, 4, cs.degree()); be.stop_after_check = False
+    pk = PL.keygen(be, cs, fixed, copies)
+    for _ in range(2):
+        proof = PL.create_proof(be, pk, inst, adv, rand, PL.Blake2bWrite(C.base.p, C.scalar.p))
+        assert VM.verify_proof(C, be.params, pk.vk, inst, proof)
+    assert Probe.checked == 2 and pk._quotient_program[id(be)]
+    circ, fixed, copies, adv, inst = TR.build(PL, TP.answer_only(T, 8), 6)
+    be = Probe(C, 6, circ.cs.degree()); be.stop_after_check = True
+    pk = PL.keygen(be, circ.cs, fixed, copies)
+    for _ in range(2):
+        with pytest.raises(Stop):
+            PL.create_proof(be, pk, inst, adv, rand, PL.Blake2bWrite(C.base.p, C.scalar.p))
+    assert Probe.checked == 4
+    slots = pk._quotient_program[id(be)][2]
+    names = {s[0] for s in slots if s is not None}
+    assert names == {"theta", "beta", "gamma", "y", "beta_delta"}

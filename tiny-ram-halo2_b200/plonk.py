@@ -610,59 +610,90 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
 
     # ---- quotient --------------------------------------------------------------------------------------------------------------------
     y = transcript.squeeze_challenge_scalar()
-    leaves, ext_polys = {}, []
-
-    def leaf(key, coset):
-        if key not in leaves:
-            leaves[key] = len(ext_polys)
-            ext_polys.append(coset)
-        return P.Poly(leaves[key], 0)
-
     cos_of = {ADVICE: adv_cosets, FIXED: pk.fixed_cosets, INSTANCE: inst_cosets}
+    n_lookups = len(lookups)
 
-    def to_ast(e):
-        if isinstance(e, Constant): return P.ConstantTerm(e.value % p)
-        if isinstance(e, Query): return leaf((e.kind, e.column), cos_of[e.kind][e.column]).with_rotation(e.rotation)
-        if isinstance(e, Negated): return -to_ast(e.a)
-        if isinstance(e, Sum): return to_ast(e.a) + to_ast(e.b)
-        if isinstance(e, Product): return to_ast(e.a) * to_ast(e.b)
-        return to_ast(e.a) * (e.scalar % p)
+    def build_h(theta_, beta_, gamma_, y_):
+        """the folded constraint polynomial as a poly::Ast over symbolic leaves: (h_ast, leaf keys in leaf-index order).  Its SHAPE
+        depends on the constraint system only; the challenges enter as constants."""
+        leaves, keys = {}, []
 
-    l0, l_blind, l_last = leaf("l0", pk.l0), leaf("l_blind", pk.l_blind), leaf("l_last", pk.l_last)
-    one = P.ConstantTerm(1)
-    active = one - (l_last + l_blind)
-    exprs = [to_ast(g) for g in cs.gates]
-    if perm_sets:
-        zs = [leaf(("perm_z", i), S["coset"]) for i, S in enumerate(perm_sets)]
-        exprs.append(l0 * (one - zs[0]))
-        exprs.append(l_last * (zs[-1] * zs[-1] - zs[-1]))
-        for i in range(1, len(zs)):
-            exprs.append(l0 * (zs[i] - zs[i - 1].with_rotation(-(bf + 1))))
-        for i, z in enumerate(zs):
-            cols = cs.permutation[i * chunk_len:(i + 1) * chunk_len]
-            left, right = z.with_rotation(1), z
-            cur_delta = beta * pow(B.delta, i * chunk_len, p) % p
-            for off, (kk, c) in enumerate(cols):
-                col = leaf((kk, c), cos_of[kk][c])
-                sig = leaf(("sigma", i * chunk_len + off), pk.sigma_cosets[i * chunk_len + off])
-                left = left * (col + sig * beta + gamma)
-                right = right * (col + P.LinearTerm(cur_delta) + gamma)
-                cur_delta = cur_delta * B.delta % p
-            exprs.append((left - right) * active)
-    for li, (L, (inputs, tables)) in enumerate(zip(lookups, cs.lookups)):
-        z = leaf(("lookup_z", li), B.coeff_to_extended(L["z_poly"]))
-        a = leaf(("lookup_a", li), B.coeff_to_extended(L["pi_poly"]))
-        s = leaf(("lookup_s", li), B.coeff_to_extended(L["pt_poly"]))
-        comp = lambda es: P.DistributePowers([to_ast(e) for e in es], P.ConstantTerm(theta)) if len(es) > 1 else to_ast(es[0])
-        exprs.append(l0 * (one - z))
-        exprs.append(l_last * (z * z - z))
-        exprs.append((z.with_rotation(1) * (a + beta) * (s + gamma) - z * (comp(inputs) + beta) * (comp(tables) + gamma)) * active)
-        exprs.append(l0 * (a - s))
-        exprs.append(((a - s) * (a - a.with_rotation(-1))) * active)
-    h_ast = P.ConstantTerm(0)
-    for e in exprs:
-        h_ast = h_ast * y + e
-    pieces = B.quotient(h_ast, ext_polys)                       # the j - 1 pieces (n coefficients each) of h(X)
+        def leaf(key):
+            if key not in leaves:
+                leaves[key] = len(keys)
+                keys.append(key)
+            return P.Poly(leaves[key], 0)
+
+        def to_ast(e):
+            if isinstance(e, Constant): return P.ConstantTerm(e.value % p)
+            if isinstance(e, Query): return leaf((e.kind, e.column)).with_rotation(e.rotation)
+            if isinstance(e, Negated): return -to_ast(e.a)
+            if isinstance(e, Sum): return to_ast(e.a) + to_ast(e.b)
+            if isinstance(e, Product): return to_ast(e.a) * to_ast(e.b)
+            return to_ast(e.a) * (e.scalar % p)
+
+        l0, l_blind, l_last = leaf("l0"), leaf("l_blind"), leaf("l_last")
+        one = P.ConstantTerm(1)
+        active = one - (l_last + l_blind)
+        exprs = [to_ast(g) for g in cs.gates]
+        if perm_sets:
+            zs = [leaf(("perm_z", i)) for i in range(len(perm_sets))]
+            exprs.append(l0 * (one - zs[0]))
+            exprs.append(l_last * (zs[-1] * zs[-1] - zs[-1]))
+            for i in range(1, len(zs)):
+                exprs.append(l0 * (zs[i] - zs[i - 1].with_rotation(-(bf + 1))))
+            for i, z in enumerate(zs):
+                cols = cs.permutation[i * chunk_len:(i + 1) * chunk_len]
+                left, right = z.with_rotation(1), z
+                cur_delta = beta_ * pow(B.delta, i * chunk_len, p) % p
+                for off, (kk, c) in enumerate(cols):
+                    col = leaf((kk, c))
+                    sig = leaf(("sigma", i * chunk_len + off))
+                    left = left * (col + sig * beta_ + gamma_)
+                    right = right * (col + P.LinearTerm(cur_delta) + gamma_)
+                    cur_delta = cur_delta * B.delta % p
+                exprs.append((left - right) * active)
+        for li, (inputs, tables) in enumerate(cs.lookups[:n_lookups]):
+            z, a, s = leaf(("lookup_z", li)), leaf(("lookup_a", li)), leaf(("lookup_s", li))
+            comp = lambda es: P.DistributePowers([to_ast(e) for e in es], P.ConstantTerm(theta_)) if len(es) > 1 else to_ast(es[0])
+            exprs.append(l0 * (one - z))
+            exprs.append(l_last * (z * z - z))
+            exprs.append((z.with_rotation(1) * (a + beta_) * (s + gamma_) - z * (comp(inputs) + beta_) * (comp(tables) + gamma_)) * active)
+            exprs.append(l0 * (a - s))
+            exprs.append(((a - s) * (a - a.with_rotation(-1))) * active)
+        h = P.ConstantTerm(0)
+        for e in exprs:
+            h = h * y_ + e
+        return h, keys
+
+    def resolve(key):                           # the polynomial of THIS proof behind a leaf key
+        if isinstance(key, str):
+            return getattr(pk, key)             # l0, l_blind, l_last
+        tag = key[0]
+        if tag == "perm_z": return perm_sets[key[1]]["coset"]
+        if tag == "sigma": return pk.sigma_cosets[key[1]]
+        if tag in ("lookup_z", "lookup_a", "lookup_s"):
+            L = lookups[key[1]]
+            name = {"lookup_z": "z_poly", "lookup_a": "pi_poly", "lookup_s": "pt_poly"}[tag]
+            if name + "_ext" not in L:
+                L[name + "_ext"] = B.coeff_to_extended(L[name])
+            return L[name + "_ext"]
+        return cos_of[tag][key[1]]
+
+    # A backend may keep the compiled program of a proving key (its code depends on the constraint system only) and patch the
+    # challenge-dependent constants: GpuBackend.quotient_program.  h_ast itself is then built only for debug.
+    h_ast = None
+    cached = getattr(B, "quotient_program", None)
+    prog_and_keys = cached(pk, build_h, (theta, beta, gamma, y), len(cs.permutation)) if cached is not None else None
+    if prog_and_keys is not None:
+        h_in, keys = prog_and_keys
+    else:
+        h_ast, keys = build_h(theta, beta, gamma, y)
+        h_in = h_ast
+    ext_polys = [resolve(k_) for k_ in keys]
+    if debug and h_ast is None:
+        h_ast, _ = build_h(theta, beta, gamma, y)
+    pieces = B.quotient(h_in, ext_polys)                        # the j - 1 pieces (n coefficients each) of h(X)
     if debug:        # h(X) (X^n - 1) must equal the folded constraint polynomial: checked at a point outside the domain
         if not getattr(B, "leaves_are_coefficients", False):
             raise ValueError("debug=True needs a backend whose quotient leaves stay in coefficient form (GpuBackend)")
@@ -1146,10 +1177,61 @@ class GpuBackend:
         prog = P.compile_ast(ast, self.p)
         self.ev.evaluate_device(prog, self.dom, [c.data_ptr() for c in columns], out.data_ptr(), coset=coset | Q_CONTIGUOUS)
 
+    def quotient_program(self, pk, build_h, challenges, n_perm_columns):
+        """The compiled quotient program of `pk` with this proof's challenges patched in, or None (then create_proof builds and
+        compiles the Ast as usual).  The program's CODE depends on the constraint system only; its constants are literals of the
+        gates or one of theta, beta, gamma, y, beta * DELTA^i.  The first proof of a key compiles the Ast twice -- with the real
+        challenges and with a probe set -- and explains every constant slot by exactly one of those formulas; later proofs
+        evaluate the formulas (microseconds) instead of rebuilding and recompiling the Ast (~60 ms of Python at 8 000
+        instructions, during which the GPU would idle: the challenge y is the last thing the transcript yields before the
+        quotient).  Any slot that cannot be explained disables the cache for that key."""
+        p = self.p
+        cache = pk.__dict__.setdefault("_quotient_program", {})
+        entry = cache.get(id(self))
+        if entry is None:
+            real = tuple(c % p for c in challenges)
+            probe = tuple((c * 0x9e3779b97f4a7c15 + 0x632be59bd9b4e019 + i) % p for i, c in enumerate(real))
+            ast_r, keys_r = build_h(*real)
+            ast_p, keys_p = build_h(*probe)
+            prog_r, prog_p = P.compile_ast(ast_r, p), P.compile_ast(ast_p, p)
+            entry = False
+            if keys_r == keys_p and prog_r.code.shape == prog_p.code.shape and (prog_r.code == prog_p.code).all() and len(prog_r.consts) == len(prog_p.consts):
+                def formulas(ch):
+                    theta, beta, gamma, y = ch
+                    f = {("theta",): theta, ("beta",): beta, ("gamma",): gamma, ("y",): y}
+                    d = beta
+                    for i in range(n_perm_columns):
+                        f[("beta_delta", i)] = d
+                        d = d * self.delta % p
+                    return f
+                fr, fp = formulas(real), formulas(probe)
+                slots = []
+                for vr, vp in zip(prog_r.consts, prog_p.consts):
+                    if vr == vp:
+                        slots.append(None)                      # a literal of the constraint system
+                        continue
+                    match = [name for name in fr if fr[name] == vr and fp[name] == vp]
+                    if len(match) < 1:
+                        slots = None
+                        break
+                    slots.append(match[0])
+                if slots is not None:
+                    entry = (prog_r, keys_r, slots, formulas)
+            cache[id(self)] = entry
+            if entry:
+                return entry[0], entry[1]
+            return None
+        if entry is False:
+            return None
+        prog, keys, slots, formulas = entry
+        f = formulas(tuple(c % p for c in challenges))
+        consts = [v if name is None else f[name] for v, name in zip(prog.consts, slots)]
+        return P.Program(prog.code, consts, prog.n_regs, prog.n_cols), keys
+
     def quotient(self, ast, ext_polys):
         from ._lib import Q_CONTIGUOUS
         t, n, ncos = self.torch, self.n, self.j - 1
-        prog = P.compile_ast(ast, self.p)
+        prog = ast if isinstance(ast, P.Program) else P.compile_ast(ast, self.p)
         dyn = [i for i, c in enumerate(ext_polys) if id(c) not in self._static]
         in_arena = [self._arena_slot.get(id(ext_polys[i])) for i in dyn]
         if dyn and all(a is not None and a[1] is ext_polys[i] for a, i in zip(in_arena, dyn)):

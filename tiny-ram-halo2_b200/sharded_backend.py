@@ -197,6 +197,18 @@ class ShardedGpuBackend(ShardedCommits, GpuBackend):
         parallel.all_gather_blocks_inplace(self._arena[first:first + per * self.world], per, self.dist)
         return out
 
+    # -- openings: every rank evaluates a block of the polynomials, the values are all_gathered --------------------------------------------
+    def eval_polynomials_at(self, vs, x):
+        if self.world == 1 or len(vs) < 4 * self.world:
+            return super().eval_polynomials_at(vs, x)
+        per, lo, hi = parallel.block_range(len(vs), self.world, self.rank)
+        vals = self.torch.zeros((per * self.world, 4), dtype=self.torch.int64, device="cuda")
+        if hi > lo:
+            tab = (self.ct.c_void_p * (hi - lo))(*[v.data_ptr() for v in vs[lo:hi]])
+            self.ctx.check(self.lib.trp_dev_eval_polynomials_at(self.ctx.handle, 0, tab, self.n, hi - lo, self._m(x), vals[lo].data_ptr()))
+        parallel.all_gather_blocks_inplace(vals, per, self.dist)
+        return self._ints(vals[:len(vs)].cpu().numpy().view(self.np.uint64))
+
     # -- lookups: owned in blocks -------------------------------------------------------------------------------------------------------
     def lookups_commit_permuted(self, lookups, theta, values_of, usable, bf, rand):
         L = len(lookups)
@@ -347,7 +359,7 @@ class ShardedGpuBackend(ShardedCommits, GpuBackend):
                 parallel.pack_row_slices(own, hi - lo, n, G, H, H, send[cs & 1])
             handle = self.dist.all_to_all_single(recv[cs & 1], send[cs & 1], async_op=True) if ncols else None
             if prog is None:
-                prog = P.compile_ast(ast, self.p)
+                prog = ast if isinstance(ast, P.Program) else P.compile_ast(ast, self.p)
             if pending is not None:
                 run_program(*pending)
             pending = (cs, handle)
