@@ -282,7 +282,7 @@ int trp_dev_field_op(trp_ctx* ctx, int which_field, int op, const uint64_t* d_a,
 /* ---- microbenchmarks used by bench.py to measure the integer-pipe roofline denominator -------------------
  * kind 0: independent 32x32+64 wide MACs with carry-out (IMAD.WIDE.U32 + carry count), 1: 32-bit IMAD,
  * 2: IADD3.X carry chains, 3: carry-chained wide MACs as in the field multiplier (IMAD.WIDE.U32.X; the wide-MAC peak),
- * 4: field mul, 5: field add/sub, 6-8: reduced-radix experiments, 10: IMAD.WIDE + IADD3 mix, 11: DFMA.
+ * 4: field mul, 5: field add/sub, 10: IMAD.WIDE + IADD3 mix, 11: DFMA.
  * Returns achieved G-ops/s in *out_gops (ops = wide MACs / thread-level instructions / field muls). */
 int trp_microbench(trp_ctx* ctx, int kind, int iters, double* out_gops);
 

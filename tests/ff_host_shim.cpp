@@ -2,7 +2,6 @@
 // limb logic is unit-tested on the CPU box.  Built by tests/test_ff_host.py; not part of the product.
 #include "../tiny-ram-halo2_b200/csrc/ff.cuh"
 #include "../tiny-ram-halo2_b200/csrc/ec.cuh"
-#include "../tiny-ram-halo2_b200/csrc/affine_add.cuh"
 #include "../tiny-ram-halo2_b200/csrc/bucket_reduce.cuh"
 #include <vector>
 #include <cstring>
@@ -41,26 +40,6 @@ template <class PR> static void ecop(const uint32_t* pts, const int* neg, size_t
   ec::Affine<PR> a = ec::xyzz_to_affine(acc);
   memcpy(out_aff, a.x.v, 32); memcpy(out_aff + 8, a.y.v, 32);
 }
-// one level of the batched-affine pairwise tree (affine_add.cuh) the way the MSM stage runs it: out[o] = in[2o] + in[2o+1], all
-// denominators of the level inverted through ONE field inversion (prefix products, then the back substitution in reverse)
-template <class PR> static void affine_level(const uint32_t* in, size_t n_out, uint32_t* out) {
-  std::vector<Fe<PR>> prefix(n_out);
-  Fe<PR> run = fe_one<PR>();
-  auto load = [&](size_t i) { ec::Affine<PR> p; memcpy(p.x.v, in + 16 * i, 32); memcpy(p.y.v, in + 16 * i + 8, 32); return p; };
-  for (size_t o = 0; o < n_out; ++o) {
-    Fe<PR> den;
-    if (ec::pair_classify(load(2 * o), load(2 * o + 1), den) >= ec::PAIR_ADD) { prefix[o] = run; run = fe_mul(run, den); }
-  }
-  Fe<PR> inv = fe_inv(run);
-  for (size_t o = n_out; o-- > 0;) {
-    ec::Affine<PR> p1 = load(2 * o), p2 = load(2 * o + 1), r;
-    Fe<PR> den, dinv = fe_zero<PR>();
-    int cs = ec::pair_classify(p1, p2, den);
-    if (cs >= ec::PAIR_ADD) { dinv = fe_mul(inv, prefix[o]); inv = fe_mul(inv, den); }
-    r = ec::pair_finish(cs, p1, p2, dinv);
-    memcpy(out + 16 * o, r.x.v, 32); memcpy(out + 16 * o + 8, r.y.v, 32);
-  }
-}
 
 // the two-level weighted bucket sum of bucket_reduce.cuh the way msm_reduce_chunks2 / msm_reduce_sets2 run it: chunks of
 // 2^log_chunk buckets, `threads` leaves of 2^log_m chunks each, a binary tree over the leaves
@@ -90,9 +69,6 @@ extern "C" {
 void ffh_bucket_reduce2(int base_field, const uint32_t* buckets_aff, unsigned threads, unsigned log_m, unsigned log_chunk, uint32_t* out_aff) {
   if (base_field == 0) bucket_reduce2<FpParams>(buckets_aff, threads, log_m, log_chunk, out_aff);
   else bucket_reduce2<FqParams>(buckets_aff, threads, log_m, log_chunk, out_aff);
-}
-void ffh_affine_level(int base_field, const uint32_t* in, size_t n_out, uint32_t* out) {
-  if (base_field == 0) affine_level<FpParams>(in, n_out, out); else affine_level<FqParams>(in, n_out, out);
 }
 void ffh_op(int field, int o, const uint32_t* a, const uint32_t* b, uint32_t* r, size_t n) {
   if (field == 0) op<FpParams>(o, a, b, r, n); else op<FqParams>(o, a, b, r, n);

@@ -9,7 +9,7 @@ resident (bench.py's step), 5 timed steps with CUDA events; the normalised resul
   SHAPE=sparse16 python tests/gpu_msm_variants.py   # what a real advice column looks like: tinyram-shaped values on the first 2^16
                                                     # rows (the execution table), zero elsewhere, 6 uniform blinding rows at the end
 
-Switches: TRP_MSM_SEG=0 (per-bucket level-1 tasks instead of aligned windows of the sorted entry list), TRP_MSM_C=c (window
+Switches: TRP_MSM_C=c (window
 width), TRP_MSM_REDUCE=1/2 (one doubling chain per chunk / the two-level weighted bucket sum of csrc/bucket_reduce.cuh)."""
 import hashlib
 import json
@@ -18,7 +18,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-VARIANTS = ([("default", {}), ("per-bucket level-1 tasks", {"TRP_MSM_SEG": "0"})]
+VARIANTS = ([("default", {})]
             + [(f"c = {c}", {"TRP_MSM_C": str(c)}) for c in (13, 14, 15, 16, 17, 18, 19, 20, 21)]
             + [(f"c = {c}, chunk-chain reduction", {"TRP_MSM_C": str(c), "TRP_MSM_REDUCE": "1"}) for c in (18,)]
             + [(f"c = {c}, two-level reduction", {"TRP_MSM_C": str(c), "TRP_MSM_REDUCE": "2"}) for c in (16, 17)])

@@ -100,45 +100,6 @@ def test_xyzz_ops_match_bigint(shim, cid, C):
 
 
 @pytest.mark.parametrize("cid,C", [(0, pm.Pallas), (1, pm.Vesta)])
-def test_affine_tree_level_matches_bigint(shim, cid, C):
-    """csrc/affine_add.cuh: one level of the batched-affine pairwise tree (all denominators through one inversion), every
-    special case in the batch: identity operands, P + P, P + (-P), both identity"""
-    rnd = random.Random(23 + cid)
-    F = C.base
-    bf = O.BASE_FIELD[cid]
-    P = [C.mul(rnd.randrange(C.scalar.p), C.G) for _ in range(40)]
-    pairs = [(P[2 * i], P[2 * i + 1]) for i in range(16)]
-    pairs += [(P[0], P[0]), (P[1], C.neg(P[1])), (None, P[2]), (P[3], None), (None, None), (P[4], P[4]), (C.neg(P[5]), C.neg(P[5]))]
-    pairs += [(P[32 + i], P[33 + i]) for i in range(6)]
-    rnd.shuffle(pairs)
-    aff = lambda Q: [0, 0] if Q is None else [F.to_mont(Q[0]), F.to_mont(Q[1])]
-    arr = O.ints_to_limbs([c for a, b in pairs for Q in (a, b) for c in aff(Q)])
-    out = np.zeros((2 * len(pairs), 4), dtype=np.uint64)
-    shim.ffh_affine_level(bf, arr.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(pairs)), out.ctypes.data_as(ctypes.c_void_p))
-    vals = [F.from_mont(v) for v in O.limbs_to_ints(out)]
-    got = [None if (vals[2 * i] == 0 and vals[2 * i + 1] == 0) else (vals[2 * i], vals[2 * i + 1]) for i in range(len(pairs))]
-    assert got == [C.add(a, b) for a, b in pairs]
-    # three levels = the sum of every aligned group of eight
-    pts = [P[i] for i in range(32)] + [None] * 5 + [P[7], P[7], C.neg(P[7])]
-    arr = O.ints_to_limbs([c for Q in pts for c in aff(Q)])
-    cur, n = arr, len(pts)
-    for _ in range(3):
-        n //= 2
-        nxt = np.zeros((2 * n, 4), dtype=np.uint64)
-        shim.ffh_affine_level(bf, cur.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), nxt.ctypes.data_as(ctypes.c_void_p))
-        cur = nxt
-    vals = [F.from_mont(v) for v in O.limbs_to_ints(cur)]
-    got = [None if (vals[2 * i] == 0 and vals[2 * i + 1] == 0) else (vals[2 * i], vals[2 * i + 1]) for i in range(n)]
-    want = []
-    for g in range(n):
-        acc = None
-        for Q in pts[8 * g:8 * g + 8]:
-            acc = C.add(acc, Q)
-        want.append(acc)
-    assert got == want
-
-
-@pytest.mark.parametrize("cid,C", [(0, pm.Pallas), (1, pm.Vesta)])
 @pytest.mark.parametrize("threads,log_m,log_chunk", [(8, 2, 2), (4, 0, 3), (1, 3, 1), (16, 1, 0)])
 def test_two_level_bucket_sum_matches_bigint(shim, cid, C, threads, log_m, log_chunk):
     """csrc/bucket_reduce.cuh: sum_b (b + 1) B_b through chunk sums, per-thread running sums over the chunk totals and the

@@ -97,23 +97,3 @@ def test_lookup_failure_and_argument_errors(pkg, ctxs):
         PL.keygen(PL.GpuBackend(ctxs[O.VESTA], 2, cs.degree()), cs, fixed, copies)      # NotEnoughRowsAvailable (n = 4 < 8)
 
 
-@pytest.mark.parametrize("k,scale", [(8, 0.1), (10, 0.25)])
-def test_tinyram_shaped_circuit_proves_and_verifies(pkg, ctxs, k, scale):
-    """a satisfiable circuit with the TinyRamCircuit's shape (tinyram_circuit.py; device-generated witness): gates of degree 6,
-    one-column / multi-column / dynamic lookups, a many-chunk permutation with instance columns.  The full-size run (k = 20,
-    scale 1: 263 advice columns) is tests/gpu_tinyram_proof.py / profiles/tinyram_proof_r01.md."""
-    from tiny_ram_halo2_b200 import tinyram_circuit
-    PL = pkg.plonk
-    C = pm.Vesta
-    be = PL.GpuBackend(ctxs[O.VESTA], k, 6)
-    cs, fixed, copies, adv, inst = tinyram_circuit.build(PL, be, seed=40 + k, scale=scale)
-    assert cs.degree() == 6 and cs.blinding_factors() == 5
-    rows = min(1 << 12, (be.n - 6) // 2)
-    inst_lists = [be._ints(c[:rows].cpu().numpy().view(np.uint64)) for c in inst]
-    pk = PL.keygen(be, cs, fixed, copies)
-    rnd = random.Random(k)
-    proof = PL.create_proof(be, pk, inst, adv, lambda: rnd.randrange(C.scalar.p), PL.Blake2bWrite(C.base.p, C.scalar.p), debug=True)
-    params = _params_as_oracle(be)
-    assert VM.verify_proof(C, params, pk.vk, inst_lists, proof), VM.verify_proof.last_error
-    inst_lists[0][1] = (inst_lists[0][1] + 1) % C.scalar.p
-    assert not VM.verify_proof(C, params, pk.vk, inst_lists, proof)

@@ -1,5 +1,5 @@
-"""The task / slot algebra of the segmented level-1 accumulation (csrc/msm.cu: msm_accum_l1_seg_kernel, scan_input mode 2;
-TRP_MSM_SEG=1) restated in Python and checked exhaustively on small cases: thread t walks the aligned window [L t, L t + L) of
+"""The task / slot algebra of the segmented level-1 accumulation (csrc/msm.cu: msm_accum_l1_seg_kernel, scan_input mode 2)
+restated in Python and checked exhaustively on small cases: thread t walks the aligned window [L t, L t + L) of
 the sorted entry list, emits one partial per bucket the window meets into slot pbase[b] + (t - off[b] // L), and
 
   * every bucket's slots are exactly [pbase[b], pbase[b + 1]) and together hold the bucket's entries once each, in order;

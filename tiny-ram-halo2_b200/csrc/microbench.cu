@@ -5,7 +5,6 @@
 // of the fmaheavy pipe whichever way it is written (IMAD.WIDE.U32[.X] runs at 32 lanes/clk/SM, IMAD lo / IMAD.HI at
 // 64 each), so the wide-MAC peak is half the 32-bit IMAD rate: 148 x 32 x 1.965 GHz = 9.3 T MAC/s.
 #include "common.cuh"
-#include "ff29_experiment.cuh"
 
 using namespace ff;
 
@@ -119,30 +118,6 @@ __global__ void mb_fe_addsub(uint64_t* out, uint32_t a, uint32_t b, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-// kind 6: reduced-radix (9 x 29) field multiplications, two independent chains per thread
-template <class PR, int V>
-__device__ __forceinline__ ff29::F29<PR> mul29_variant(const ff29::F29<PR>& x, const ff29::F29<PR>& w) {
-  if (V == 0) return ff29::mul(x, w);
-  if (V == 1) return ff29::mul_cios(x, w);
-  return ff29::mul_v3(x, w);
-}
-template <class PR, int V>
-__global__ void mb_mul29(uint64_t* out, uint32_t a, uint32_t b, int iters) {
-  ff29::F29<PR> x, y, w;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) { x.l[k] = (threadIdx.x * 77 + a + k) & ff29::MASK29; y.l[k] = (threadIdx.x * 3 + blockIdx.x + b + k) & ff29::MASK29; w.l[k] = ((a ^ b) + threadIdx.x * 5 + k) & ff29::MASK29; }
-  for (int it = 0; it < iters; ++it) {
-#pragma unroll 1
-    for (int u = 0; u < MB_UNROLL / 2; ++u) {
-      x = mul29_variant<PR, V>(x, w);
-      y = mul29_variant<PR, V>(y, w);
-    }
-  }
-  uint32_t s = 0;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) s ^= x.l[k] ^ y.l[k];
-  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
 
 // kind 9: wide MAC with carry-OUT only (no carry-in), the carry counted into a separate register
 // (carry-save accumulation): expect IMAD.WIDE.U32 R, P + IADD3.X cnt.  Counts one op per wide MAC.
@@ -230,9 +205,6 @@ int trp_microbench_impl(trp_ctx* ctx, int kind, int iters, double* out_gops) {
       case 3: mb_madc_chain<<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = 4.0 * MB_UNROLL; break;
       case 4: mb_fe_mul<FqParams><<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = MB_UNROLL; break;
       case 5: mb_fe_addsub<FqParams><<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = MB_UNROLL; break;
-      case 6: mb_mul29<ff29::FqP, 0><<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = MB_UNROLL; break;
-      case 7: mb_mul29<ff29::FqP, 1><<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = MB_UNROLL; break;
-      case 8: mb_mul29<ff29::FqP, 2><<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = MB_UNROLL; break;
       case 9: mb_wide_carryout<<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = 4.0 * MB_UNROLL; break;
       case 10: mb_wide_plus_iadd3<<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = 8.0 * MB_UNROLL; break;
       case 11: mb_dfma<<<blocks, MB_THREADS, 0, ctx->stream>>>(out, 12345u, 67891u, iters); ops_per_thread_iter = 8.0 * MB_UNROLL; break;

@@ -9,10 +9,12 @@
 //   1. hist      scalar -> canonical -> signed c-bit digits; warp-aggregated histogram of bucket sizes
 //   2. scan      exclusive prefix sum -> bucket offsets
 //   3. scatter   counting sort of (point index | sign) entries into bucket order
-//   4. accumulate  multi-level segmented reduction: every task adds <= L consecutive entries of one bucket
-//                (mixed XYZZ adds for level 1, full adds above), so run time is independent of how skewed
-//                the bucket sizes are (TinyRAM columns are mostly 0/1: one bucket gets ~n entries)
-//   5. reduce    sum_b (b+1) * B_b per bucket set by chunked running sums, block tree-sum
+//   4. accumulate  multi-level segmented reduction: level 1 cuts the sorted entry list into aligned windows of 64 entries
+//                (mixed XYZZ adds; one partial per bucket a window meets), the levels above add <= 16 partials of one bucket
+//                (full adds), so run time is independent of how skewed the bucket sizes are (TinyRAM columns are mostly
+//                0/1: one bucket gets ~n entries)
+//   5. reduce    sum_b (b+1) * B_b per bucket set: chunked running sums, then the chunks' totals either scaled by their first
+//                bucket index (c < 18) or folded by the two-level weighted sum of bucket_reduce.cuh (c >= 18)
 //   6. final     Horner over bucket sets (none when bases are precomputed) -> Jacobian point
 //
 // Bases are static (Params.g_lagrange ++ [w]); with 180 GB of HBM the loader precomputes 2^(c*w) * P_i for
@@ -154,31 +156,10 @@ __device__ __forceinline__ void store_xyzz(uint4* p, const XYZZ<BPR>& a) {
   fe_store(p, a.x); fe_store(p + 2, a.y); fe_store(p + 4, a.zz); fe_store(p + 6, a.zzz);
 }
 
-// level 1: entries (index | sign) -> affine bases, mixed adds
-template <class BPR>
-__global__ void __launch_bounds__(ACC_THREADS) msm_accum_l1_kernel(const uint32_t* entries, const uint32_t* in_off,
-                                                                 const uint32_t* task_off, unsigned nb,
-                                                                 const uint4* bases, uint4* partials) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= __ldg(task_off + nb)) return;
-  unsigned b = find_segment(task_off, nb, t);
-  uint32_t j = t - __ldg(task_off + b);
-  uint32_t start = __ldg(in_off + b) + j * L1;
-  uint32_t end = min(start + L1, __ldg(in_off + b + 1));
-  XYZZ<BPR> acc = xyzz_identity<BPR>();
-  for (uint32_t e = start; e < end; ++e) {
-    uint32_t ent = __ldg(entries + e);
-    Affine<BPR> p = load_affine<BPR>(bases, ent & 0x7fffffffu);
-    if (ent >> 31) p.y = fe_neg(p.y);
-    xyzz_add_mixed(acc, p);
-  }
-  store_xyzz(partials + 8 * (size_t)t, acc);
-}
-
-// DEFAULT level 1 since round 2 (TRP_MSM_SEG=0 selects msm_accum_l1_kernel above): tasks cut the SORTED ENTRY LIST into aligned
-// windows of L1 entries instead of cutting every bucket into tasks of its own, so every thread of a warp performs exactly L1
-// additions whatever the bucket sizes are (per-bucket tasks leave the last task of a bucket partial: ~6 % idle lanes at 512
-// entries per bucket, ~30 % at the 26 entries per bucket of c = 20).  A thread emits one partial per bucket its window meets:
+// Level 1: entries (point index | sign) -> affine bases, mixed adds.  Tasks cut the SORTED ENTRY LIST into aligned windows of L1
+// entries (not every bucket into tasks of its own, round 1's layout, whose last task per bucket was partial: ~6 % idle lanes at
+// 512 entries per bucket, ~30 % at the 26 entries per bucket of c = 20), so every thread of a warp performs exactly L1
+// additions whatever the bucket sizes are.  A thread emits one partial per bucket its window meets:
 // bucket b's partials are the slots pbase[b] + (t - off[b] / L1), pbase = the scan of scan_input mode 2, which is exactly the
 // per-bucket layout the upper levels read.  Measured on B200 (profiles/msm_variants_r02.md): 8 x 2^20 uniform, c = 16:
 // accumulate 22.2 -> 21.3 ms; it is what makes wider windows pay (c = 20: 25.0 -> 18.0 ms).
@@ -485,18 +466,13 @@ unsigned choose_c(size_t n, unsigned requested = 0) {
   return (unsigned)c;
 }
 
-bool seg_mode() {      // the segmented level-1 tasks (msm_accum_l1_seg_kernel) unless TRP_MSM_SEG=0
-  static const bool on = [] { const char* e = getenv("TRP_MSM_SEG"); return !(e && atoi(e) == 0); }();
-  return on;
-}
-
 // Worst-case task counts per level for mc columns processed together (entries may all fall into one bucket, or
 // spread over all of them).
 std::vector<size_t> plan_levels(const MsmGeom& g, size_t n, size_t mc) {
   const size_t M = n * g.W * mc, NB = (size_t)g.nb * mc;
   std::vector<size_t> level_tasks;
   size_t single = (n * g.W + L1 - 1) / L1;      // tasks if ONE bucket of a column held all its entries
-  if (seg_mode()) ++single;                     // an unaligned run of entries meets one window more
+  ++single;                                     // an unaligned run of entries meets one window more
   size_t bound = (M + L1 - 1) / L1 + NB;        // sum_b ceil(cnt_b / L1) <= M / L1 + NB
   level_tasks.push_back(bound);
   while (single > 1) {
@@ -544,7 +520,6 @@ int msm_chunk(trp_ctx* ctx, const trp_bases_impl* bs, const uint4* d_scalars, si
   std::vector<size_t> level_tasks = plan_levels(g, n, mc);
   MsmWs w = carve(g, n, mc, ws);
   if (w.bytes > ws_cap) TRP_FAIL(ctx, TRP_E_INVALID, "internal: MSM workspace underestimated (%zu > %zu)", w.bytes, ws_cap);
-  const bool segmented = seg_mode();
   {
     ProfScope ps(ctx, PROF_MSM_SORT);
     TRP_CUDA(ctx, cudaMemsetAsync(w.counts, 0, (NB + 1) * sizeof(uint32_t), ctx->stream));
@@ -554,17 +529,12 @@ int msm_chunk(trp_ctx* ctx, const trp_bases_impl* bs, const uint4* d_scalars, si
     TRP_TRY(run_scan(ctx, w.counts, w.offsets, w.cursor, w.block_sums, w.total, NB, 0, 1));
     msm_scatter_kernel<SPR><<<sgrid, 128, 0, ctx->stream>>>(d_scalars, n, g, w.cursor, w.entries);
     TRP_LAUNCHED(ctx);
-    TRP_TRY(run_scan(ctx, w.offsets, w.task_off[0], nullptr, w.block_sums, w.total, NB, segmented ? 2 : 1, L1));
+    TRP_TRY(run_scan(ctx, w.offsets, w.task_off[0], nullptr, w.block_sums, w.total, NB, 2, L1));
   }
   {
     ProfScope ps(ctx, PROF_MSM_ACCUM_L1, (double)M);      // work = entries if no digit were zero (n * windows * columns): an upper bound
-    unsigned gridl1 = (unsigned)((level_tasks[0] + ACC_THREADS - 1) / ACC_THREADS);
-    if (segmented)
-      msm_accum_l1_seg_kernel<BPR><<<(unsigned)(((M + L1 - 1) / L1 + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(
-          w.entries, w.offsets, w.task_off[0], (unsigned)NB, (const uint4*)bs->pub.d_xy, w.part[0]);
-    else
-      msm_accum_l1_kernel<BPR><<<gridl1, ACC_THREADS, 0, ctx->stream>>>(w.entries, w.offsets, w.task_off[0], (unsigned)NB,
-                                                                       (const uint4*)bs->pub.d_xy, w.part[0]);
+    msm_accum_l1_seg_kernel<BPR><<<(unsigned)(((M + L1 - 1) / L1 + ACC_THREADS - 1) / ACC_THREADS), ACC_THREADS, 0, ctx->stream>>>(
+        w.entries, w.offsets, w.task_off[0], (unsigned)NB, (const uint4*)bs->pub.d_xy, w.part[0]);
     TRP_LAUNCHED(ctx);
   }
   int curp = 0;
