@@ -373,3 +373,32 @@ def test_device_columns_host_logic_on_a_fake_backend(mods, monkeypatch):
             want[:len(prefix)] = np.array(list(prefix), dtype=np.uint64)
             assert np.array_equal(x[:, 0].numpy().view(np.uint64), want) and not x[:, 1:].any()
     assert calls and set(calls) == {be.n}
+
+
+def test_parity_vector_of_the_reproducible_rng(mods):
+    """tests/golden/parity_vectors.json (what rust/parity/parity.rs is compared with): the first vector -- `Answer 1`, keys from the
+    empty circuit, blinding scalars from rng.ScalarStreamRng (AES-256-CTR, 64 bytes per scalar) -- is reproduced byte for byte, and
+    the RNG itself is pinned by a known answer"""
+    import hashlib, json, os
+    import pasta_model as pm
+    import plonk_model as VM
+    PL, TR, T = mods
+    from tiny_ram_halo2_b200 import rng as RNG
+    C = pm.Vesta
+    r = RNG.ScalarStreamRng(C.scalar.p, bytes(range(32)))
+    from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+    ks = Cipher(algorithms.AES(bytes(range(32))), modes.CTR(bytes(16))).encryptor().update(bytes(192))
+    assert [r(), r(), r()] == [int.from_bytes(ks[i:i + 64], "little") % C.scalar.p for i in (0, 64, 128)] and r.draws == 3
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "parity_vectors.json")) as f:
+        want = json.load(f)[0]
+    circ, fixed, copies, adv, inst = TR.build(PL, TP.answer_only(T, 8), 6, keygen_from_empty_circuit=True)
+    be = VM.PythonBackend(C, 6, circ.cs.degree())
+    pk = PL.keygen(be, circ.cs, fixed, copies)
+    rng = RNG.ScalarStreamRng(C.scalar.p, bytes.fromhex(want["seed_hex"]))
+    proof = PL.create_proof(be, pk, inst, adv, rng, PL.Blake2bWrite(C.base.p, C.scalar.p))
+    assert (len(proof), hashlib.sha256(proof).hexdigest(), rng.draws, hex(pk.vk.transcript_repr), proof[:32].hex()) == \
+        (want["proof_bytes"], want["proof_sha256"], want["scalars_drawn"], want["transcript_repr_of_this_repo"], want["first_proof_point_le_hex"])
+    cs = circ.cs
+    assert want["shape"] == {"advice": cs.num_advice, "instance": cs.num_instance, "fixed": cs.num_fixed, "lookups": len(cs.lookups),
+                             "gates": len(cs.gates), "equality_columns": len(cs.permutation), "degree": cs.degree(),
+                             "blinding_factors": cs.blinding_factors()}
