@@ -1,0 +1,85 @@
+// Host build of csrc/qlower.h (the lowering of the public quotient program into the kernel's internal form) with two
+// interpreters over the real field arithmetic of csrc/ff.cuh: one of the PUBLIC program (include/tr_prover.h semantics), one
+// of the LOWERED program that follows quotient_vm_kernel statement for statement (forwarding register, operand modes,
+// write-back elision).  Built by tests/test_qlower_cpu.py; not part of the product.
+#include "../tiny-ram-halo2_b200/csrc/ff.cuh"
+#include "../tiny-ram-halo2_b200/csrc/qlower.h"
+#include <cstring>
+#include <vector>
+using namespace ff;
+typedef Fe<FpParams> F;
+
+static F ld(const uint32_t* p) { F r; memcpy(r.v, p, 32); return r; }
+
+extern "C" int qls_run(const uint32_t* prog, size_t n_instr, unsigned n_regs, const uint32_t* consts, const uint32_t* cols, size_t n_cols,
+                       size_t rows, const uint32_t* xraw, const uint32_t* zeta_limbs, uint32_t* out_pub, uint32_t* out_low, uint64_t* stats) {
+  const F zeta = ld(zeta_limbs);
+  auto col_at = [&](uint32_t c, size_t row, int rot) { return ld(cols + 8 * ((size_t)c * rows + (size_t)(((long long)row + rot) % (long long)rows + rows) % rows)); };
+  // public program
+  {
+    std::vector<F> r(n_regs);
+    for (size_t row = 0; row < rows; ++row)
+      for (size_t pc = 0; pc < n_instr; ++pc) {
+        const uint32_t op = prog[4 * pc], d = prog[4 * pc + 1], a = prog[4 * pc + 2], b = prog[4 * pc + 3];
+        switch (op) {
+          case 0: r[d] = col_at(a, row, (int)b); break;
+          case 1: r[d] = ld(consts + 8 * a); break;
+          case 2: r[d] = fe_add(r[a], r[b]); break;
+          case 3: r[d] = fe_sub(r[a], r[b]); break;
+          case 4: r[d] = fe_mul(r[a], r[b]); break;
+          case 5: r[d] = fe_neg(r[a]); break;
+          case 6: r[d] = fe_sqr(r[a]); break;
+          case 7: r[d] = fe_dbl(r[a]); break;
+          case 8: r[d] = fe_mul(ld(xraw + 8 * row), zeta); break;
+          case 9: memcpy(out_pub + 8 * row, r[a].v, 32); break;
+          case 10: r[d] = fe_mul(r[a], ld(consts + 8 * b)); break;
+          case 11: r[d] = fe_add(r[a], ld(consts + 8 * b)); break;
+          default: r[d] = fe_sub(r[a], ld(consts + 8 * b)); break;
+        }
+      }
+  }
+  std::vector<uint32_t> low;
+  unsigned regs2 = 0;
+  qlower::Stats st;
+  if (!qlower::lower(prog, n_instr, n_regs, low, &regs2, &st)) return 1;
+  stats[0] = st.in; stats[1] = st.out; stats[2] = st.fused; stats[3] = st.fwd; stats[4] = st.nowb; stats[5] = st.hoisted_x; stats[6] = regs2; stats[7] = st.negs;
+  const size_t n_low = low.size() / 4 - qlower::PAD;
+  if (n_low != st.out) return 2;
+  {
+    using namespace qlower;
+    std::vector<F> r(regs2);
+    for (size_t row = 0; row < rows; ++row) {
+      // poison the register file between rows: a lowered program must not depend on what an earlier row left behind
+      for (auto& x : r) for (int i = 0; i < 8; ++i) x.v[i] = 0xdeadbeefu;
+      F last = fe_zero<FpParams>();
+      for (size_t pc = 0; pc < n_low; ++pc) {
+        const uint32_t x = low[4 * pc], dst = low[4 * pc + 1], ra = low[4 * pc + 2], w = low[4 * pc + 3];
+        const uint32_t op = x & 15u, bm = (x >> 4) & 7u, fl = (x >> 7) & 15u, col = x >> 11;
+        F a = (fl & F_FWD_A) ? last : (fl & F_NO_A) ? zeta : r[ra];
+        F b;
+        switch (bm) {
+          case B_REG: b = (fl & F_FWD_B) ? last : r[w]; break;
+          case B_CONST: b = ld(consts + 8 * w); break;
+          case B_COL: b = col_at(col, row, (int)w); break;
+          case B_X: b = ld(xraw + 8 * row); break;
+          default: b = a; break;
+        }
+        F res;
+        switch (op) {
+          case L_MOV: res = b; break;
+          case L_ADD: res = fe_add(a, b); break;
+          case L_SUB: res = fe_sub(a, b); break;
+          case L_RSUB: res = fe_sub(b, a); break;
+          case L_MUL: res = fe_mul(a, b); break;
+          case L_NEG: res = fe_neg(a); break;
+          case L_DBL: res = fe_dbl(a); break;
+          case L_STORE: memcpy(out_low + 8 * row, a.v, 32); res = last; break;
+          default: res = last; break;
+        }
+        if (!(fl & F_NOWB)) r[dst] = res;
+        last = res;
+      }
+    }
+  }
+  return 0;
+}

@@ -45,6 +45,9 @@ struct trp_ctx {
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   std::vector<TwiddleTable> twiddles;
+  // quotient.cu: the caller's last quotient program and its lowered form (qlower.h); a prover runs one program on j - 1 cosets
+  std::vector<uint32_t> q_src, q_low;
+  unsigned q_src_regs = 0, q_low_regs = 0;
 };
 
 struct trp_bases {

@@ -15,7 +15,9 @@
 //     written interleaved (row * 2^(ext_k-k) + coset) so that 2^(ext_k-k) calls assemble h_ext without ever
 //     materialising the extended columns (700 columns x 256 MiB at k = 20 would not fit).
 #include "common.cuh"
+#include "qlower.h"
 
+#include <cstdlib>
 #include <cstring>
 
 using namespace ff;
@@ -34,8 +36,8 @@ enum QOp : uint32_t {
 };
 
 struct QParams {
-  const uint4* prog;
-  unsigned n_instr, n_regs;
+  const uint4* prog;     // LOWERED program (qlower.h), qlower::PAD NOPs appended
+  unsigned n_instr, n_regs, bd_log;
   const uint4* consts;
   const uint4* const* cols;
   unsigned rows_log, step, out_stride, out_off, x_stride, x_off, ext_log;
@@ -46,61 +48,86 @@ struct QParams {
   uint4* out;
 };
 
-template <class PR>
+// One thread = one row; the lowered program (qlower.h) is interpreted with ONE instance of every field operation: operand a
+// comes from the virtual register file (shared memory, two 16-byte planes [reg][thread]), from the previous instruction's
+// result (kept in hardware registers) or is zeta; operand b from the register file, the previous result, the constant table, a
+// column at (row + rotation) or the coset-X table.  The fetch is software-pipelined so that no load waits for another load:
+// instruction pc + 2 (PF = 0) is fetched while pc executes, the column POINTER of pc + 1 with it, so a column operand costs one
+// memory latency, not three in a row; with PF = 1 the pipeline is one deeper and the column VALUE of pc + 1 is requested before
+// pc executes.  The program is padded with NOPs so the look-ahead never leaves it.
+template <class PR, int PF>
 __global__ void __launch_bounds__(128) quotient_vm_kernel(QParams p, Fe<PR> zeta) {
+  using namespace qlower;
   extern __shared__ uint4 smem[];
-  uint4* plane0 = smem;
-  uint4* plane1 = smem + (size_t)p.n_regs * blockDim.x;
+  const unsigned tid = threadIdx.x;
+  uint4* plane0 = smem + tid;
+  uint4* plane1 = plane0 + ((size_t)p.n_regs << p.bd_log);
   const bool slice = p.nrows != 0;
   const unsigned rows = slice ? p.nrows : 1u << p.rows_log;
-  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned gid = blockIdx.x * blockDim.x + tid;
   // surplus threads of the last block recompute a valid row and never store
   const unsigned row = slice ? (gid < rows ? gid : rows - 1) : (gid & (rows - 1));
   const bool live = gid < rows;
-  const unsigned tid = threadIdx.x, bd = blockDim.x;
+  const unsigned idx0 = slice ? row + p.halo_before : row, idx_mask = slice ? 0xffffffffu : rows - 1, idx_step = slice ? 1u : p.step;
   auto rd = [&](unsigned reg) -> Fe<PR> {
-    uint4 lo = plane0[reg * bd + tid], hi = plane1[reg * bd + tid];
+    const uint4 lo = plane0[reg << p.bd_log], hi = plane1[reg << p.bd_log];
     Fe<PR> r;
     r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w; r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
     return r;
   };
-  auto wr = [&](unsigned reg, const Fe<PR>& a) {
-    plane0[reg * bd + tid] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
-    plane1[reg * bd + tid] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+  auto col_ptr = [&](const uint4& i) -> const uint4* {
+    return reinterpret_cast<const uint4*>(__ldg(reinterpret_cast<const unsigned long long*>(p.cols) + (i.x >> 11)));
   };
+  auto col_val = [&](const uint4* col, const uint4& i) -> Fe<PR> {
+    const unsigned idx = (idx0 + (unsigned)((int)i.w * (int)idx_step)) & idx_mask;
+    return fe_load<PR>(col + 2 * (size_t)idx);
+  };
+  Fe<PR> last = zeta, bcol = zeta;
+  uint4 ins = __ldg(p.prog), nxt = __ldg(p.prog + 1), nn = nxt;
+  const uint4* ptr = col_ptr(ins);                 // column pointer of `ins` (PF = 0) / of `nxt` (PF = 1)
+  if (PF) {
+    nn = __ldg(p.prog + 2);
+    if (((ins.x >> 4) & 7u) == B_COL) bcol = col_val(ptr, ins);
+    ptr = col_ptr(nxt);
+  }
   for (unsigned pc = 0; pc < p.n_instr; ++pc) {
-    const uint4 ins = __ldg(p.prog + pc);
-    switch (ins.x) {
-      case Q_LOAD: {
-        unsigned idx = slice ? (unsigned)((int)(row + p.halo_before) + (int)ins.w)
-                             : ((row + (unsigned)((int)ins.w * (int)p.step)) & (rows - 1));
-        const uint4* col = p.cols[ins.z];
-        wr(ins.y, fe_load<PR>(col + 2 * (size_t)idx));
+    const uint4 ahead = __ldg(p.prog + pc + 2 + PF);
+    const uint4* ptr_ahead = col_ptr(PF ? nn : nxt);
+    const unsigned op = ins.x & 15u, bm = (ins.x >> 4) & 7u, fl = ins.x >> 7;
+    Fe<PR> bnext = bcol;
+    if (PF && ((nxt.x >> 4) & 7u) == B_COL) bnext = col_val(ptr, nxt);
+    Fe<PR> a = last, b;
+    if (!(fl & F_FWD_A)) a = (fl & F_NO_A) ? zeta : rd(ins.z);
+    b = a;                                                              // B_A, B_NONE
+    if (bm == B_REG) { if (fl & F_FWD_B) b = last; else b = rd(ins.w); }
+    else if (bm == B_CONST) b = fe_load_ro<PR>(p.consts + 2 * (size_t)ins.w);
+    else if (bm == B_COL) b = PF ? bcol : col_val(ptr, ins);
+    else if (bm == B_X) {
+      const unsigned g = (row + p.row0) * p.x_stride + p.x_off, half = 1u << (p.ext_log - 1);
+      b = fe_load_ro<PR>(p.tw_ext + 2 * (size_t)(g & (half - 1)));
+      if (g & half) b = fe_neg(b);
+    }
+    Fe<PR> r = last;
+    switch (op) {
+      case L_MOV: r = b; break;
+      case L_ADD: r = fe_add(a, b); break;
+      case L_SUB: r = fe_sub(a, b); break;
+      case L_RSUB: r = fe_sub(b, a); break;
+      case L_MUL: r = fe_mul(a, b); break;
+      case L_NEG: r = fe_neg(a); break;
+      case L_DBL: r = fe_dbl(a); break;
+      case L_STORE:
+        if (live) fe_store(p.out + 2 * ((size_t)row * p.out_stride + p.out_off), a);
         break;
-      }
-      case Q_CONST: wr(ins.y, fe_load_ro<PR>(p.consts + 2 * (size_t)ins.z)); break;
-      case Q_ADD: wr(ins.y, fe_add(rd(ins.z), rd(ins.w))); break;
-      case Q_SUB: wr(ins.y, fe_sub(rd(ins.z), rd(ins.w))); break;
-      case Q_MUL: wr(ins.y, fe_mul(rd(ins.z), rd(ins.w))); break;
-      case Q_NEG: wr(ins.y, fe_neg(rd(ins.z))); break;
-      case Q_SQR: wr(ins.y, fe_sqr(rd(ins.z))); break;
-      case Q_DBL: wr(ins.y, fe_dbl(rd(ins.z))); break;
-      case Q_COSETX: {
-        unsigned g = (row + p.row0) * p.x_stride + p.x_off;
-        unsigned half = 1u << (p.ext_log - 1);
-        Fe<PR> w = fe_load_ro<PR>(p.tw_ext + 2 * (size_t)(g & (half - 1)));
-        if (g & half) w = fe_neg(w);
-        wr(ins.y, fe_mul(w, zeta));
-        break;
-      }
-      case Q_STORE:
-        if (live) fe_store(p.out + 2 * ((size_t)row * p.out_stride + p.out_off), rd(ins.z));
-        break;
-      case Q_MULC: wr(ins.y, fe_mul(rd(ins.z), fe_load_ro<PR>(p.consts + 2 * (size_t)ins.w))); break;
-      case Q_ADDC: wr(ins.y, fe_add(rd(ins.z), fe_load_ro<PR>(p.consts + 2 * (size_t)ins.w))); break;
-      case Q_SUBC: wr(ins.y, fe_sub(rd(ins.z), fe_load_ro<PR>(p.consts + 2 * (size_t)ins.w))); break;
       default: break;
     }
+    if (!(fl & F_NOWB)) {
+      plane0[ins.y << p.bd_log] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+      plane1[ins.y << p.bd_log] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+    }
+    last = r;
+    ins = nxt; ptr = ptr_ahead; bcol = bnext;
+    if (PF) { nxt = nn; nn = ahead; } else nxt = ahead;
   }
 }
 
@@ -124,12 +151,18 @@ int validate_program(trp_ctx* ctx, const uint32_t* prog, size_t n_instr, unsigne
   return TRP_OK;
 }
 
-// d_cols_dev: device array of column pointers; everything else already validated
-int launch_vm(trp_domain* d, const uint4* d_prog, size_t n_instr, unsigned n_regs, const uint4* d_consts,
-              const uint4* const* d_cols_dev, int coset, uint4* d_out, unsigned row0 = 0, unsigned nrows = 0, unsigned halo_before = 0) {
+// what stage_tables leaves at the front of the arena
+struct Staged {
+  const uint4* prog; size_t n_instr; unsigned n_regs;     // lowered program
+  const uint4* consts;
+  const uint4* const* cols;                                // device array of column pointers
+  char* after;
+};
+
+int launch_vm(trp_domain* d, const Staged& st, int coset, uint4* d_out, unsigned row0 = 0, unsigned nrows = 0, unsigned halo_before = 0) {
   trp_ctx* ctx = d->ctx;
   QParams p;
-  p.prog = d_prog; p.n_instr = (unsigned)n_instr; p.n_regs = n_regs; p.consts = d_consts; p.cols = d_cols_dev;
+  p.prog = st.prog; p.n_instr = (unsigned)st.n_instr; p.n_regs = st.n_regs; p.consts = st.consts; p.cols = st.cols;
   p.ext_log = d->ext_k;
   const unsigned period = 1u << (d->ext_k - d->k);
   const bool contiguous = coset >= 0 && (coset & TRP_Q_CONTIGUOUS);
@@ -145,20 +178,22 @@ int launch_vm(trp_domain* d, const uint4* d_prog, size_t n_instr, unsigned n_reg
   TRP_TRY(trp_get_powers(ctx, d->field, d->ext_k, d->ext_omega, &tw));
   p.tw_ext = (const uint4*)tw;
   p.out = d_out;
-  unsigned threads = 128;
-  while (threads > 32 && (size_t)n_regs * threads * 32 > 200 * 1024) threads >>= 1;
-  size_t smem = (size_t)n_regs * threads * 32;
-  if (smem > 200 * 1024) TRP_FAIL(ctx, TRP_E_INVALID, "quotient program needs %u registers (max %u)", n_regs, 200 * 1024 / (32 * 32));
+  unsigned threads = 128, bd_log = 7;
+  while (threads > 32 && (size_t)st.n_regs * threads * 32 > 200 * 1024) { threads >>= 1; --bd_log; }
+  p.bd_log = bd_log;
+  size_t smem = (size_t)st.n_regs * threads * 32;
+  if (smem > 200 * 1024) TRP_FAIL(ctx, TRP_E_INVALID, "quotient program needs %u registers (max %u)", st.n_regs, 200 * 1024 / (32 * 32));
   const size_t rows = nrows ? (size_t)nrows : (size_t)1 << p.rows_log;
   unsigned blocks = (unsigned)((rows + threads - 1) / threads);
   auto go = [&](auto tag) -> int {
     typedef decltype(tag) PR;
     Fe<PR> zeta;
     for (int i = 0; i < 4; ++i) { zeta.v[2 * i] = (uint32_t)d->g_coset[i]; zeta.v[2 * i + 1] = (uint32_t)(d->g_coset[i] >> 32); }
-    if (smem > 48 * 1024)
-      TRP_CUDA(ctx, cudaFuncSetAttribute(quotient_vm_kernel<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    static const int pf = [] { const char* e = getenv("TRP_VM_PF"); return e ? atoi(e) : 0; }();
+    auto kern = pf ? quotient_vm_kernel<PR, 1> : quotient_vm_kernel<PR, 0>;
+    if (smem > 48 * 1024) TRP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     ProfScope ps(ctx, PROF_QUOTIENT, (double)rows);      // work = rows evaluated (x the program's multiplications, known to the caller)
-    quotient_vm_kernel<PR><<<blocks, threads, smem, ctx->stream>>>(p, zeta);
+    kern<<<blocks, threads, smem, ctx->stream>>>(p, zeta);
     TRP_LAUNCHED(ctx);
     return TRP_OK;
   };
@@ -253,18 +288,29 @@ struct Locked {
   explicit Locked(trp_ctx* c) : g(c->mu) { cudaSetDevice(c->device); }
 };
 
-// stage program / constants / column-pointer table at the front of the arena; returns the bytes used
-int stage_tables(trp_ctx* ctx, const uint32_t* program, size_t n_instr, const uint64_t* consts, size_t n_consts,
-                 const uint64_t* const* col_ptrs, size_t n_cols, size_t extra, char** after) {
-  size_t b_prog = ws_align(n_instr * 16), b_c = ws_align((n_consts ? n_consts : 1) * 32), b_p = ws_align((n_cols ? n_cols : 1) * 8);
+// lower the caller's program (cached: a prover evaluates one program on j - 1 cosets, proof after proof) and stage the lowered
+// program / constants / column-pointer table at the front of the arena
+int stage_tables(trp_ctx* ctx, const uint32_t* program, size_t n_instr, unsigned n_regs, const uint64_t* consts, size_t n_consts,
+                 const uint64_t* const* col_ptrs, size_t n_cols, size_t extra, Staged* st) {
+  if (ctx->q_src.size() != n_instr * 4 || ctx->q_src_regs != n_regs || memcmp(ctx->q_src.data(), program, n_instr * 16) != 0) {
+    ctx->q_src.clear();
+    if (!qlower::lower(program, n_instr, n_regs, ctx->q_low, &ctx->q_low_regs))
+      TRP_FAIL(ctx, TRP_E_INVALID, "quotient program: column index above %u", qlower::MAX_COLS - 1);
+    ctx->q_src.assign(program, program + n_instr * 4);
+    ctx->q_src_regs = n_regs;
+  }
+  const size_t low_bytes = ctx->q_low.size() * 4;                     // includes the trailing NOP
+  size_t b_prog = ws_align(low_bytes), b_c = ws_align((n_consts ? n_consts : 1) * 32), b_p = ws_align((n_cols ? n_cols : 1) * 8);
   TRP_TRY(trp_ws_reserve(ctx, b_prog + b_c + b_p + extra));
   char* w = (char*)ctx->ws;
-  TRP_CUDA(ctx, cudaMemcpyAsync(w, program, n_instr * 16, cudaMemcpyHostToDevice, ctx->stream));
+  TRP_CUDA(ctx, cudaMemcpyAsync(w, ctx->q_low.data(), low_bytes, cudaMemcpyHostToDevice, ctx->stream));
   if (n_consts) TRP_CUDA(ctx, cudaMemcpyAsync(w + b_prog, consts, n_consts * 32, cudaMemcpyHostToDevice, ctx->stream));
   if (n_cols && col_ptrs) TRP_CUDA(ctx, cudaMemcpyAsync(w + b_prog + b_c, col_ptrs, n_cols * 8, cudaMemcpyHostToDevice, ctx->stream));
   // the host arrays may be reused by the caller as soon as we return
   TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  *after = w + b_prog + b_c + b_p;
+  st->prog = (const uint4*)w; st->n_instr = ctx->q_low.size() / 4 - qlower::PAD; st->n_regs = ctx->q_low_regs;
+  st->consts = (const uint4*)(w + b_prog); st->cols = (const uint4* const*)(w + b_prog + b_c);
+  st->after = w + b_prog + b_c + b_p;
   return TRP_OK;
 }
 
@@ -282,12 +328,9 @@ int trp_dev_quotient_eval(trp_domain* d, const uint32_t* program, size_t n_instr
     TRP_FAIL(ctx, TRP_E_INVALID, "bad register count or coset index");
   TRP_TRY(validate_program(ctx, program, n_instr, n_regs, n_consts, n_cols));
   for (size_t c = 0; c < n_cols; ++c) if (!d_cols[c]) TRP_FAIL(ctx, TRP_E_INVALID, "column %zu is NULL", c);
-  char* after = nullptr;
-  TRP_TRY(stage_tables(ctx, program, n_instr, consts, n_consts, d_cols, n_cols, 0, &after));
-  char* w = (char*)ctx->ws;
-  size_t b_prog = ws_align(n_instr * 16), b_c = ws_align((n_consts ? n_consts : 1) * 32);
-  return launch_vm(d, (const uint4*)w, n_instr, n_regs, (const uint4*)(w + b_prog), (const uint4* const*)(w + b_prog + b_c), coset,
-                   (uint4*)d_out);
+  Staged st;
+  TRP_TRY(stage_tables(ctx, program, n_instr, n_regs, consts, n_consts, d_cols, n_cols, 0, &st));
+  return launch_vm(d, st, coset, (uint4*)d_out);
 }
 
 // Row-slice form of the coset evaluation (the multi-GPU quotient: a coset's rows are split between the devices): the columns
@@ -311,12 +354,9 @@ int trp_dev_quotient_eval_rows(trp_domain* d, const uint32_t* program, size_t n_
         TRP_FAIL(ctx, TRP_E_INVALID, "quotient program rotates by %d rows, the slice carries -%u .. +%u", rot, halo_before, halo_after);
     }
   for (size_t c = 0; c < n_cols; ++c) if (!d_cols[c]) TRP_FAIL(ctx, TRP_E_INVALID, "column %zu is NULL", c);
-  char* after = nullptr;
-  TRP_TRY(stage_tables(ctx, program, n_instr, consts, n_consts, d_cols, n_cols, 0, &after));
-  char* w = (char*)ctx->ws;
-  size_t b_prog = ws_align(n_instr * 16), b_c = ws_align((n_consts ? n_consts : 1) * 32);
-  return launch_vm(d, (const uint4*)w, n_instr, n_regs, (const uint4*)(w + b_prog), (const uint4* const*)(w + b_prog + b_c), (int)coset,
-                   (uint4*)d_out, (unsigned)row0, (unsigned)nrows, halo_before);
+  Staged st;
+  TRP_TRY(stage_tables(ctx, program, n_instr, n_regs, consts, n_consts, d_cols, n_cols, 0, &st));
+  return launch_vm(d, st, (int)coset, (uint4*)d_out, (unsigned)row0, (unsigned)nrows, halo_before);
 }
 
 // host-pointer form over the whole extended domain (what poly::Evaluator::evaluate returns): columns are uploaded,
@@ -331,20 +371,18 @@ int trp_quotient_eval(trp_domain* d, const uint32_t* program, size_t n_instr, un
   TRP_TRY(validate_program(ctx, program, n_instr, n_regs, n_consts, n_cols));
   for (size_t c = 0; c < n_cols; ++c) if (!cols[c]) TRP_FAIL(ctx, TRP_E_INVALID, "column %zu is NULL", c);
   const size_t EN = (size_t)1 << d->ext_k;
-  char* after = nullptr;
-  TRP_TRY(stage_tables(ctx, program, n_instr, consts, n_consts, nullptr, n_cols, (n_cols + 1) * EN * 32, &after));
-  char* w = (char*)ctx->ws;
-  size_t b_prog = ws_align(n_instr * 16), b_c = ws_align((n_consts ? n_consts : 1) * 32);
+  Staged st;
+  TRP_TRY(stage_tables(ctx, program, n_instr, n_regs, consts, n_consts, nullptr, n_cols, (n_cols + 1) * EN * 32, &st));
+  char* after = st.after;
   std::vector<const uint64_t*> dptr(n_cols);
   for (size_t c = 0; c < n_cols; ++c) {
     dptr[c] = (const uint64_t*)(after + c * EN * 32);
     TRP_CUDA(ctx, cudaMemcpyAsync((void*)dptr[c], cols[c], EN * 32, cudaMemcpyHostToDevice, ctx->stream));
   }
-  if (n_cols) TRP_CUDA(ctx, cudaMemcpyAsync(w + b_prog + b_c, dptr.data(), n_cols * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_cols) TRP_CUDA(ctx, cudaMemcpyAsync((void*)st.cols, dptr.data(), n_cols * 8, cudaMemcpyHostToDevice, ctx->stream));
   TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // dptr goes out of scope below
   char* d_out = after + n_cols * EN * 32;
-  TRP_TRY(launch_vm(d, (const uint4*)w, n_instr, n_regs, (const uint4*)(w + b_prog), (const uint4* const*)(w + b_prog + b_c), -1,
-                    (uint4*)d_out));
+  TRP_TRY(launch_vm(d, st, -1, (uint4*)d_out));
   TRP_CUDA(ctx, cudaMemcpyAsync(out_ext, d_out, EN * 32, cudaMemcpyDeviceToHost, ctx->stream));
   TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return TRP_OK;
