@@ -1,7 +1,7 @@
 // Host build of csrc/qlower.h (the lowering of the public quotient program into the kernel's internal form) with two
 // interpreters over the real field arithmetic of csrc/ff.cuh: one of the PUBLIC program (include/tr_prover.h semantics), one
-// of the LOWERED program that follows quotient_vm_kernel statement for statement (forwarding register, operand modes,
-// write-back elision).  Built by tests/test_qlower_cpu.py; not part of the product.
+// of the LOWERED program that follows quotient_vm_kernel statement for statement (accumulator, one case per operation and
+// operand source, write-back elision, zeta as the constant after the caller's).  Built by tests/test_qlower_cpu.py; not part of the product.
 #include "../tiny-ram-halo2_b200/csrc/ff.cuh"
 #include "../tiny-ram-halo2_b200/csrc/qlower.h"
 #include <cstring>
@@ -11,7 +11,7 @@ typedef Fe<FpParams> F;
 
 static F ld(const uint32_t* p) { F r; memcpy(r.v, p, 32); return r; }
 
-extern "C" int qls_run(const uint32_t* prog, size_t n_instr, unsigned n_regs, const uint32_t* consts, const uint32_t* cols, size_t n_cols,
+extern "C" int qls_run(const uint32_t* prog, size_t n_instr, unsigned n_regs, const uint32_t* consts, size_t n_consts, const uint32_t* cols, size_t n_cols,
                        size_t rows, const uint32_t* xraw, const uint32_t* zeta_limbs, uint32_t* out_pub, uint32_t* out_low, uint64_t* stats) {
   const F zeta = ld(zeta_limbs);
   auto col_at = [&](uint32_t c, size_t row, int rot) { return ld(cols + 8 * ((size_t)c * rows + (size_t)(((long long)row + rot) % (long long)rows + rows) % rows)); };
@@ -41,43 +41,47 @@ extern "C" int qls_run(const uint32_t* prog, size_t n_instr, unsigned n_regs, co
   std::vector<uint32_t> low;
   unsigned regs2 = 0;
   qlower::Stats st;
-  if (!qlower::lower(prog, n_instr, n_regs, low, &regs2, &st)) return 1;
+  const size_t n_consts_ = n_consts;
+  if (!qlower::lower(prog, n_instr, n_regs, n_consts_, low, &regs2, &st)) return 1;
   stats[0] = st.in; stats[1] = st.out; stats[2] = st.fused; stats[3] = st.fwd; stats[4] = st.nowb; stats[5] = st.hoisted_x; stats[6] = regs2; stats[7] = st.negs;
   const size_t n_low = low.size() / 4 - qlower::PAD;
   if (n_low != st.out) return 2;
   {
     using namespace qlower;
     std::vector<F> r(regs2);
+    auto cst = [&](uint32_t i) { return i == n_consts_ ? zeta : ld(consts + 8 * i); };      // the library appends zeta
     for (size_t row = 0; row < rows; ++row) {
       // poison the register file between rows: a lowered program must not depend on what an earlier row left behind
       for (auto& x : r) for (int i = 0; i < 8; ++i) x.v[i] = 0xdeadbeefu;
-      F last = fe_zero<FpParams>();
+      F acc = fe_zero<FpParams>();
       for (size_t pc = 0; pc < n_low; ++pc) {
         const uint32_t x = low[4 * pc], dst = low[4 * pc + 1], ra = low[4 * pc + 2], w = low[4 * pc + 3];
-        const uint32_t op = x & 15u, bm = (x >> 4) & 7u, fl = (x >> 7) & 15u, col = x >> 11;
-        F a = (fl & F_FWD_A) ? last : (fl & F_NO_A) ? zeta : r[ra];
-        F b;
-        switch (bm) {
-          case B_REG: b = (fl & F_FWD_B) ? last : r[w]; break;
-          case B_CONST: b = ld(consts + 8 * w); break;
-          case B_COL: b = col_at(col, row, (int)w); break;
-          case B_X: b = ld(xraw + 8 * row); break;
-          default: b = a; break;
+        const uint32_t fl = x >> 5, col = x >> 11;
+        if (!(fl & (F_FWD_A | F_NO_A))) acc = r[ra];
+        switch (x & 31u) {
+          case K_MOV_CONST: acc = cst(w); break;
+          case K_MOV_COL: acc = col_at(col, row, (int)w); break;
+          case K_MOV_REG: acc = r[w]; break;
+          case K_MOV_X: acc = ld(xraw + 8 * row); break;
+          case K_ADD_REG: acc = fe_add(acc, r[w]); break;
+          case K_ADD_CONST: acc = fe_add(acc, cst(w)); break;
+          case K_ADD_COL: acc = fe_add(acc, col_at(col, row, (int)w)); break;
+          case K_SUB_REG: acc = fe_sub(acc, r[w]); break;
+          case K_SUB_CONST: acc = fe_sub(acc, cst(w)); break;
+          case K_SUB_COL: acc = fe_sub(acc, col_at(col, row, (int)w)); break;
+          case K_RSUB_REG: acc = fe_sub(r[w], acc); break;
+          case K_RSUB_CONST: acc = fe_sub(cst(w), acc); break;
+          case K_RSUB_COL: acc = fe_sub(col_at(col, row, (int)w), acc); break;
+          case K_MUL_REG: acc = fe_mul(acc, r[w]); break;
+          case K_MUL_CONST: acc = fe_mul(acc, cst(w)); break;
+          case K_MUL_COL: acc = fe_mul(acc, col_at(col, row, (int)w)); break;
+          case K_MUL_A: acc = fe_mul(acc, acc); break;
+          case K_NEG: acc = fe_neg(acc); break;
+          case K_DBL: acc = fe_dbl(acc); break;
+          case K_STORE: memcpy(out_low + 8 * row, acc.v, 32); break;
+          default: break;
         }
-        F res;
-        switch (op) {
-          case L_MOV: res = b; break;
-          case L_ADD: res = fe_add(a, b); break;
-          case L_SUB: res = fe_sub(a, b); break;
-          case L_RSUB: res = fe_sub(b, a); break;
-          case L_MUL: res = fe_mul(a, b); break;
-          case L_NEG: res = fe_neg(a); break;
-          case L_DBL: res = fe_dbl(a); break;
-          case L_STORE: memcpy(out_low + 8 * row, a.v, 32); res = last; break;
-          default: res = last; break;
-        }
-        if (!(fl & F_NOWB)) r[dst] = res;
-        last = res;
+        if (!(fl & F_NOWB)) r[dst] = acc;
       }
     }
   }

@@ -48,6 +48,7 @@ struct trp_ctx {
   // quotient.cu: the caller's last quotient program and its lowered form (qlower.h); a prover runs one program on j - 1 cosets
   std::vector<uint32_t> q_src, q_low;
   unsigned q_src_regs = 0, q_low_regs = 0;
+  size_t q_src_consts = 0;
 };
 
 struct trp_bases {

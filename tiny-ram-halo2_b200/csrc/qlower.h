@@ -8,13 +8,16 @@
 //   1. folds a LOAD / CONST into its single consumer (the operand is then read straight from the column or the constant
 //      table): `b` operand modes B_COL, B_CONST; the value of X on the coset (COSETX, one multiplication by zeta each time the
 //      tree walk meets a LinearTerm: 188 times in the TinyRAM program) is computed once into an extra register;
-//   2. marks operands that are the result of the PREVIOUS instruction (F_FWD_A, F_FWD_B: the kernel keeps it in hardware
-//      registers) and results nobody reads from the register file afterwards (F_NOWB: no store to shared memory).
-// The arithmetic performed per row is unchanged, instruction for instruction (same operations on the same values in the same
-// order), so results are bit-identical.
+//   2. turns the program into ACCUMULATOR form: the kernel keeps the result of the previous instruction in hardware registers
+//      (ACC), operand a of every instruction IS the accumulator -- either left as it is (F_FWD_A: a was the previous result;
+//      operands are swapped, SUB <-> RSUB, to bring a forwarded value to the a side) or first loaded from the register file --
+//      and the result replaces it, so forwarding costs no register moves (on sm_100a a move is an IMAD.MOV on the same pipe as the
+//      multiplier).  Results nobody reads from the register file afterwards are not stored (F_NOWB).
+// The field operations performed per row are the same operations on the same values (additions and multiplications commute
+// exactly, x + (-y) and x - y give the same canonical representative), so results are bit-identical.
 //
-// Lowered instruction = 4 x uint32:  x = op | bmode << 4 | flags << 7 | col << 11,  y = dst,  z = a,  w = b (register index,
-// constant index, or the rotation of a column operand).
+// Lowered instruction = 4 x uint32:  x = kernel opcode (K_*) | flags << 5 | col << 11,  y = dst,  z = a,  w = b (register index,
+// constant index, or the rotation of a column operand).  Constant index n_consts is zeta (appended by the library).
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -24,7 +27,10 @@ namespace qlower {
 
 enum Op : uint32_t { L_MOV = 0, L_ADD = 1, L_SUB = 2, L_MUL = 3, L_NEG = 4, L_DBL = 5, L_STORE = 6, L_RSUB = 7, L_NOP = 8 };   // RSUB: dst = b - a
 enum BMode : uint32_t { B_REG = 0, B_CONST = 1, B_COL = 2, B_X = 3, B_A = 4, B_NONE = 5 };
-enum Flag : uint32_t { F_FWD_A = 1, F_FWD_B = 2, F_NOWB = 4, F_NO_A = 8 };
+enum Flag : uint32_t { F_FWD_A = 1, F_NOWB = 2, F_NO_A = 4 };
+// what the kernel switches on: operation x source of operand b
+enum KOp : uint32_t { K_NOP = 0, K_MOV_CONST, K_MOV_COL, K_MOV_X, K_MOV_REG, K_ADD_REG, K_ADD_CONST, K_ADD_COL, K_SUB_REG, K_SUB_CONST, K_SUB_COL,
+                      K_RSUB_REG, K_RSUB_CONST, K_RSUB_COL, K_MUL_REG, K_MUL_CONST, K_MUL_COL, K_MUL_A, K_NEG, K_DBL, K_STORE, K_COUNT };
 constexpr uint32_t MAX_COLS = 1u << 21;
 constexpr int PAD = 4;                     // NOPs appended to a lowered program
 
@@ -33,7 +39,20 @@ struct Ins {
   bool dead;
 };
 
-inline uint32_t pack_x(const Ins& i) { return i.op | (i.bm << 4) | (i.fl << 7) | (i.col << 11); }
+inline uint32_t kop_of(const Ins& i) {
+  switch (i.op) {
+    case L_MOV: return i.bm == B_CONST ? K_MOV_CONST : i.bm == B_COL ? K_MOV_COL : i.bm == B_X ? K_MOV_X : K_MOV_REG;
+    case L_ADD: return i.bm == B_CONST ? K_ADD_CONST : i.bm == B_COL ? K_ADD_COL : K_ADD_REG;
+    case L_SUB: return i.bm == B_CONST ? K_SUB_CONST : i.bm == B_COL ? K_SUB_COL : K_SUB_REG;
+    case L_RSUB: return i.bm == B_CONST ? K_RSUB_CONST : i.bm == B_COL ? K_RSUB_COL : K_RSUB_REG;
+    case L_MUL: return i.bm == B_CONST ? K_MUL_CONST : i.bm == B_COL ? K_MUL_COL : i.bm == B_A ? K_MUL_A : K_MUL_REG;
+    case L_NEG: return K_NEG;
+    case L_DBL: return K_DBL;
+    case L_STORE: return K_STORE;
+    default: return K_NOP;
+  }
+}
+inline uint32_t pack_x(const Ins& i) { return kop_of(i) | (i.fl << 5) | (i.col << 11); }
 
 struct Stats { size_t in = 0, out = 0, fused = 0, fwd = 0, nowb = 0, hoisted_x = 0, negs = 0; };
 
@@ -58,20 +77,26 @@ inline bool dead_after(const std::vector<Ins>& v, size_t j, uint32_t r) {
 // `prog` must already have passed validate_program (opcodes and operand ranges).  Returns false if a column index does not fit.
 // *n_regs_out = n_regs, or n_regs + 1 when the value of X (COSETX: one multiplication each) is used more than once: it is then
 // computed once into an extra register that is never overwritten, and every COSETX becomes a read of it.
-inline bool lower(const uint32_t* prog, size_t n_instr_in, unsigned n_regs, std::vector<uint32_t>& out, unsigned* n_regs_out,
-                  Stats* st = nullptr) {
+// COSETX (dst = zeta * (+-ext_omega^g)) becomes MOV dst <- X table; MUL dst <- dst * consts[n_consts] (= zeta).
+inline bool lower(const uint32_t* prog, size_t n_instr_in, unsigned n_regs, size_t n_consts, std::vector<uint32_t>& out,
+                  unsigned* n_regs_out, Stats* st = nullptr) {
   size_t n_x = 0;
   for (size_t i = 0; i < n_instr_in; ++i) n_x += prog[4 * i] == 8;
   const bool hoist = n_x >= 2;
-  const uint32_t RX = n_regs;
+  const uint32_t RX = n_regs, ZETA = (uint32_t)n_consts;
   *n_regs_out = n_regs + (hoist ? 1 : 0);
-  const size_t n_instr = n_instr_in + (hoist ? 1 : 0);
-  std::vector<Ins> v(n_instr);
-  if (hoist) v[0] = Ins{L_MUL, B_X, F_NO_A, 0, RX, 0, 0, false};                        // RX = zeta * (+-ext_omega^g)
-  for (size_t i = hoist ? 1 : 0; i < n_instr; ++i) {
-    const uint32_t* q = prog + 4 * (i - (hoist ? 1 : 0));
+  std::vector<Ins> v;
+  v.reserve(n_instr_in + n_x + 2);
+  auto push_x = [&](uint32_t d) {
+    v.push_back(Ins{L_MOV, B_X, F_NO_A, 0, d, 0, 0, false});
+    v.push_back(Ins{L_MUL, B_CONST, 0, 0, d, d, ZETA, false});
+  };
+  if (hoist) push_x(RX);
+  for (size_t i = 0; i < n_instr_in; ++i) {
+    const uint32_t* q = prog + 4 * i;
     const uint32_t op = q[0], d = q[1], a = q[2], b = q[3];
     Ins x{L_NOP, B_NONE, F_NO_A, 0, d, a, b, false};
+    if (op == 8 && !hoist) { push_x(d); continue; }
     switch (op) {
       case 0: if (a >= MAX_COLS) return false;
               x.op = L_MOV; x.bm = B_COL; x.col = a; x.a = 0; break;                    // LOAD: b = rotation
@@ -82,16 +107,15 @@ inline bool lower(const uint32_t* prog, size_t n_instr_in, unsigned n_regs, std:
       case 5: x.op = L_NEG; x.fl = 0; x.b = 0; break;
       case 6: x.op = L_MUL; x.bm = B_A; x.fl = 0; x.b = 0; break;                       // SQR
       case 7: x.op = L_DBL; x.fl = 0; x.b = 0; break;
-      case 8: x.a = 0; x.b = 0;                                                        // COSETX
-              if (hoist) { x.op = L_MOV; x.bm = B_REG; x.b = RX; } else { x.op = L_MUL; x.bm = B_X; }
-              break;
+      case 8: x.a = 0; x.op = L_MOV; x.bm = B_REG; x.b = RX; break;                     // COSETX, hoisted: a copy of RX
       case 9: x.op = L_STORE; x.fl = F_NOWB; x.dst = 0; x.b = 0; break;                    // STORE a
       case 10: x.op = L_MUL; x.bm = B_CONST; x.fl = 0; break;
       case 11: x.op = L_ADD; x.bm = B_CONST; x.fl = 0; break;
       default: x.op = L_SUB; x.bm = B_CONST; x.fl = 0; break;
     }
-    v[i] = x;
+    v.push_back(x);
   }
+  const size_t n_instr = v.size();
   Stats s;
   s.in = n_instr_in;
   s.hoisted_x = hoist ? n_x : 0;
@@ -143,18 +167,22 @@ inline bool lower(const uint32_t* prog, size_t n_instr_in, unsigned n_regs, std:
     m.dead = true;
     ++s.fused;
   }
-  // 2. forwarding of the previous result, and results that never need to reach the register file
+  // 2. accumulator form: an operand that is the previous result is brought to the a side and taken from the accumulator
   size_t prev = n_instr;
   for (size_t j = 0; j < n_instr; ++j) {
     if (v[j].dead) continue;
     if (prev != n_instr && writes(v[prev])) {
       const uint32_t d = v[prev].dst;
-      bool fwd = false;
-      if (reads_a(v[j]) && v[j].a == d) { v[j].fl |= F_FWD_A; fwd = true; }
-      if (reads_reg_b(v[j]) && v[j].b == d) { v[j].fl |= F_FWD_B; fwd = true; }
-      if (fwd) {
+      Ins& c = v[j];
+      const bool as_a = reads_a(c) && c.a == d, as_b = reads_reg_b(c) && c.b == d;
+      if (as_b && !as_a && reads_a(c) && (c.op == L_ADD || c.op == L_MUL || c.op == L_SUB || c.op == L_RSUB)) {
+        if (c.op == L_SUB) c.op = L_RSUB; else if (c.op == L_RSUB) c.op = L_SUB;
+        const uint32_t t = c.a; c.a = c.b; c.b = t;                 // a (op) d  ->  d (op') a
+      }
+      if (reads_a(c) && c.a == d && !(reads_reg_b(c) && c.b == d)) {      // (both operands = d: read both from the register file)
+        c.fl |= F_FWD_A;
         ++s.fwd;
-        if ((writes(v[j]) && v[j].dst == d) || dead_after(v, j, d)) { v[prev].fl |= F_NOWB; ++s.nowb; }
+        if ((writes(c) && c.dst == d) || dead_after(v, j, d)) { v[prev].fl |= F_NOWB; ++s.nowb; }
       }
     }
     prev = j;
@@ -166,7 +194,7 @@ inline bool lower(const uint32_t* prog, size_t n_instr_in, unsigned n_regs, std:
   }
   s.out = out.size() / 4;
   for (int pad = 0; pad < PAD; ++pad)                                                 // the kernel fetches up to PAD instructions ahead
-    for (int k = 0; k < 4; ++k) out.push_back(k == 0 ? (uint32_t)L_NOP | (B_NONE << 4) | ((F_NO_A | F_NOWB) << 7) : 0u);
+    for (int k = 0; k < 4; ++k) out.push_back(k == 0 ? (uint32_t)K_NOP | ((F_NO_A | F_NOWB) << 5) : 0u);
   if (st) *st = s;
   return true;
 }

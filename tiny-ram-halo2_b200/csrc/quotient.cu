@@ -48,15 +48,15 @@ struct QParams {
   uint4* out;
 };
 
-// One thread = one row; the lowered program (qlower.h) is interpreted with ONE instance of every field operation: operand a
-// comes from the virtual register file (shared memory, two 16-byte planes [reg][thread]), from the previous instruction's
-// result (kept in hardware registers) or is zeta; operand b from the register file, the previous result, the constant table, a
-// column at (row + rotation) or the coset-X table.  The fetch is software-pipelined so that no load waits for another load:
-// instruction pc + 2 (PF = 0) is fetched while pc executes, the column POINTER of pc + 1 with it, so a column operand costs one
-// memory latency, not three in a row; with PF = 1 the pipeline is one deeper and the column VALUE of pc + 1 is requested before
-// pc executes.  The program is padded with NOPs so the look-ahead never leaves it.
-template <class PR, int PF>
-__global__ void __launch_bounds__(128) quotient_vm_kernel(QParams p, Fe<PR> zeta) {
+// One thread = one row.  The lowered program (qlower.h) is in accumulator form: the previous result stays in hardware registers
+// (acc); an instruction first reloads acc from the virtual register file (shared memory, two 16-byte planes [reg][thread]) unless
+// its operand a IS the previous result, combines it with operand b -- register file, constant table, a column at (row +
+// rotation), the coset-X table -- and stores acc back unless nobody will read it from the register file.  One case per
+// (operation, source of b), so that no operand is ever moved between registers.  The fetch is software-pipelined so that no load
+// waits for another load: instruction pc + 2 and the column POINTER of pc + 1 are requested while pc executes, a column operand
+// costs one memory latency instead of three in a row.  The program is padded with NOPs so the look-ahead never leaves it.
+template <class PR>
+__global__ void __launch_bounds__(128) quotient_vm_kernel(QParams p) {
   using namespace qlower;
   extern __shared__ uint4 smem[];
   const unsigned tid = threadIdx.x;
@@ -78,56 +78,54 @@ __global__ void __launch_bounds__(128) quotient_vm_kernel(QParams p, Fe<PR> zeta
   auto col_ptr = [&](const uint4& i) -> const uint4* {
     return reinterpret_cast<const uint4*>(__ldg(reinterpret_cast<const unsigned long long*>(p.cols) + (i.x >> 11)));
   };
-  auto col_val = [&](const uint4* col, const uint4& i) -> Fe<PR> {
-    const unsigned idx = (idx0 + (unsigned)((int)i.w * (int)idx_step)) & idx_mask;
-    return fe_load<PR>(col + 2 * (size_t)idx);
-  };
-  Fe<PR> last = zeta, bcol = zeta;
-  uint4 ins = __ldg(p.prog), nxt = __ldg(p.prog + 1), nn = nxt;
-  const uint4* ptr = col_ptr(ins);                 // column pointer of `ins` (PF = 0) / of `nxt` (PF = 1)
-  if (PF) {
-    nn = __ldg(p.prog + 2);
-    if (((ins.x >> 4) & 7u) == B_COL) bcol = col_val(ptr, ins);
-    ptr = col_ptr(nxt);
-  }
+  auto cst = [&](unsigned i) -> Fe<PR> { return fe_load_ro<PR>(p.consts + 2 * (size_t)i); };
+  Fe<PR> acc = fe_zero<PR>();
+  uint4 ins = __ldg(p.prog), nxt = __ldg(p.prog + 1);
+  const uint4* ptr = col_ptr(ins);
   for (unsigned pc = 0; pc < p.n_instr; ++pc) {
-    const uint4 ahead = __ldg(p.prog + pc + 2 + PF);
-    const uint4* ptr_ahead = col_ptr(PF ? nn : nxt);
-    const unsigned op = ins.x & 15u, bm = (ins.x >> 4) & 7u, fl = ins.x >> 7;
-    Fe<PR> bnext = bcol;
-    if (PF && ((nxt.x >> 4) & 7u) == B_COL) bnext = col_val(ptr, nxt);
-    Fe<PR> a = last, b;
-    if (!(fl & F_FWD_A)) a = (fl & F_NO_A) ? zeta : rd(ins.z);
-    b = a;                                                              // B_A, B_NONE
-    if (bm == B_REG) { if (fl & F_FWD_B) b = last; else b = rd(ins.w); }
-    else if (bm == B_CONST) b = fe_load_ro<PR>(p.consts + 2 * (size_t)ins.w);
-    else if (bm == B_COL) b = PF ? bcol : col_val(ptr, ins);
-    else if (bm == B_X) {
-      const unsigned g = (row + p.row0) * p.x_stride + p.x_off, half = 1u << (p.ext_log - 1);
-      b = fe_load_ro<PR>(p.tw_ext + 2 * (size_t)(g & (half - 1)));
-      if (g & half) b = fe_neg(b);
-    }
-    Fe<PR> r = last;
-    switch (op) {
-      case L_MOV: r = b; break;
-      case L_ADD: r = fe_add(a, b); break;
-      case L_SUB: r = fe_sub(a, b); break;
-      case L_RSUB: r = fe_sub(b, a); break;
-      case L_MUL: r = fe_mul(a, b); break;
-      case L_NEG: r = fe_neg(a); break;
-      case L_DBL: r = fe_dbl(a); break;
-      case L_STORE:
-        if (live) fe_store(p.out + 2 * ((size_t)row * p.out_stride + p.out_off), a);
+    const uint4 ahead = __ldg(p.prog + pc + 2);
+    const uint4* ptr_ahead = col_ptr(nxt);
+    const unsigned fl = ins.x >> 5;
+    if (!(fl & (F_FWD_A | F_NO_A))) acc = rd(ins.z);
+    auto col = [&]() -> Fe<PR> {
+      const unsigned idx = (idx0 + (unsigned)((int)ins.w * (int)idx_step)) & idx_mask;
+      return fe_load_ro<PR>(ptr + 2 * (size_t)idx);
+    };
+    switch (ins.x & 31u) {
+      case K_MOV_CONST: acc = cst(ins.w); break;
+      case K_MOV_COL: acc = col(); break;
+      case K_MOV_REG: acc = rd(ins.w); break;
+      case K_MOV_X: {
+        const unsigned g = (row + p.row0) * p.x_stride + p.x_off, half = 1u << (p.ext_log - 1);
+        acc = fe_load_ro<PR>(p.tw_ext + 2 * (size_t)(g & (half - 1)));
+        if (g & half) acc = fe_neg(acc);
+        break;
+      }
+      case K_ADD_REG: acc = fe_add(acc, rd(ins.w)); break;
+      case K_ADD_CONST: acc = fe_add(acc, cst(ins.w)); break;
+      case K_ADD_COL: acc = fe_add(acc, col()); break;
+      case K_SUB_REG: acc = fe_sub(acc, rd(ins.w)); break;
+      case K_SUB_CONST: acc = fe_sub(acc, cst(ins.w)); break;
+      case K_SUB_COL: acc = fe_sub(acc, col()); break;
+      case K_RSUB_REG: acc = fe_sub(rd(ins.w), acc); break;
+      case K_RSUB_CONST: acc = fe_sub(cst(ins.w), acc); break;
+      case K_RSUB_COL: acc = fe_sub(col(), acc); break;
+      case K_MUL_REG: acc = fe_mul(acc, rd(ins.w)); break;
+      case K_MUL_CONST: acc = fe_mul(acc, cst(ins.w)); break;
+      case K_MUL_COL: acc = fe_mul(acc, col()); break;
+      case K_MUL_A: acc = fe_mul(acc, acc); break;
+      case K_NEG: acc = fe_neg(acc); break;
+      case K_DBL: acc = fe_dbl(acc); break;
+      case K_STORE:
+        if (live) fe_store(p.out + 2 * ((size_t)row * p.out_stride + p.out_off), acc);
         break;
       default: break;
     }
     if (!(fl & F_NOWB)) {
-      plane0[ins.y << p.bd_log] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
-      plane1[ins.y << p.bd_log] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+      plane0[ins.y << p.bd_log] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+      plane1[ins.y << p.bd_log] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
     }
-    last = r;
-    ins = nxt; ptr = ptr_ahead; bcol = bnext;
-    if (PF) { nxt = nn; nn = ahead; } else nxt = ahead;
+    ins = nxt; nxt = ahead; ptr = ptr_ahead;
   }
 }
 
@@ -187,13 +185,10 @@ int launch_vm(trp_domain* d, const Staged& st, int coset, uint4* d_out, unsigned
   unsigned blocks = (unsigned)((rows + threads - 1) / threads);
   auto go = [&](auto tag) -> int {
     typedef decltype(tag) PR;
-    Fe<PR> zeta;
-    for (int i = 0; i < 4; ++i) { zeta.v[2 * i] = (uint32_t)d->g_coset[i]; zeta.v[2 * i + 1] = (uint32_t)(d->g_coset[i] >> 32); }
-    static const int pf = [] { const char* e = getenv("TRP_VM_PF"); return e ? atoi(e) : 0; }();
-    auto kern = pf ? quotient_vm_kernel<PR, 1> : quotient_vm_kernel<PR, 0>;
-    if (smem > 48 * 1024) TRP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (smem > 48 * 1024)
+      TRP_CUDA(ctx, cudaFuncSetAttribute(quotient_vm_kernel<PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     ProfScope ps(ctx, PROF_QUOTIENT, (double)rows);      // work = rows evaluated (x the program's multiplications, known to the caller)
-    kern<<<blocks, threads, smem, ctx->stream>>>(p, zeta);
+    quotient_vm_kernel<PR><<<blocks, threads, smem, ctx->stream>>>(p);
     TRP_LAUNCHED(ctx);
     return TRP_OK;
   };
@@ -290,21 +285,24 @@ struct Locked {
 
 // lower the caller's program (cached: a prover evaluates one program on j - 1 cosets, proof after proof) and stage the lowered
 // program / constants / column-pointer table at the front of the arena
-int stage_tables(trp_ctx* ctx, const uint32_t* program, size_t n_instr, unsigned n_regs, const uint64_t* consts, size_t n_consts,
+int stage_tables(trp_domain* d, const uint32_t* program, size_t n_instr, unsigned n_regs, const uint64_t* consts, size_t n_consts,
                  const uint64_t* const* col_ptrs, size_t n_cols, size_t extra, Staged* st) {
-  if (ctx->q_src.size() != n_instr * 4 || ctx->q_src_regs != n_regs || memcmp(ctx->q_src.data(), program, n_instr * 16) != 0) {
+  trp_ctx* ctx = d->ctx;
+  if (ctx->q_src.size() != n_instr * 4 || ctx->q_src_regs != n_regs || ctx->q_src_consts != n_consts ||
+      memcmp(ctx->q_src.data(), program, n_instr * 16) != 0) {
     ctx->q_src.clear();
-    if (!qlower::lower(program, n_instr, n_regs, ctx->q_low, &ctx->q_low_regs))
+    if (!qlower::lower(program, n_instr, n_regs, n_consts, ctx->q_low, &ctx->q_low_regs))
       TRP_FAIL(ctx, TRP_E_INVALID, "quotient program: column index above %u", qlower::MAX_COLS - 1);
     ctx->q_src.assign(program, program + n_instr * 4);
-    ctx->q_src_regs = n_regs;
+    ctx->q_src_regs = n_regs; ctx->q_src_consts = n_consts;
   }
   const size_t low_bytes = ctx->q_low.size() * 4;                     // includes the trailing NOP
-  size_t b_prog = ws_align(low_bytes), b_c = ws_align((n_consts ? n_consts : 1) * 32), b_p = ws_align((n_cols ? n_cols : 1) * 8);
+  size_t b_prog = ws_align(low_bytes), b_c = ws_align((n_consts + 1) * 32), b_p = ws_align((n_cols ? n_cols : 1) * 8);   // + zeta
   TRP_TRY(trp_ws_reserve(ctx, b_prog + b_c + b_p + extra));
   char* w = (char*)ctx->ws;
   TRP_CUDA(ctx, cudaMemcpyAsync(w, ctx->q_low.data(), low_bytes, cudaMemcpyHostToDevice, ctx->stream));
   if (n_consts) TRP_CUDA(ctx, cudaMemcpyAsync(w + b_prog, consts, n_consts * 32, cudaMemcpyHostToDevice, ctx->stream));
+  TRP_CUDA(ctx, cudaMemcpyAsync(w + b_prog + n_consts * 32, d->g_coset, 32, cudaMemcpyHostToDevice, ctx->stream));   // consts[n_consts] = zeta
   if (n_cols && col_ptrs) TRP_CUDA(ctx, cudaMemcpyAsync(w + b_prog + b_c, col_ptrs, n_cols * 8, cudaMemcpyHostToDevice, ctx->stream));
   // the host arrays may be reused by the caller as soon as we return
   TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -329,7 +327,7 @@ int trp_dev_quotient_eval(trp_domain* d, const uint32_t* program, size_t n_instr
   TRP_TRY(validate_program(ctx, program, n_instr, n_regs, n_consts, n_cols));
   for (size_t c = 0; c < n_cols; ++c) if (!d_cols[c]) TRP_FAIL(ctx, TRP_E_INVALID, "column %zu is NULL", c);
   Staged st;
-  TRP_TRY(stage_tables(ctx, program, n_instr, n_regs, consts, n_consts, d_cols, n_cols, 0, &st));
+  TRP_TRY(stage_tables(d, program, n_instr, n_regs, consts, n_consts, d_cols, n_cols, 0, &st));
   return launch_vm(d, st, coset, (uint4*)d_out);
 }
 
@@ -355,7 +353,7 @@ int trp_dev_quotient_eval_rows(trp_domain* d, const uint32_t* program, size_t n_
     }
   for (size_t c = 0; c < n_cols; ++c) if (!d_cols[c]) TRP_FAIL(ctx, TRP_E_INVALID, "column %zu is NULL", c);
   Staged st;
-  TRP_TRY(stage_tables(ctx, program, n_instr, n_regs, consts, n_consts, d_cols, n_cols, 0, &st));
+  TRP_TRY(stage_tables(d, program, n_instr, n_regs, consts, n_consts, d_cols, n_cols, 0, &st));
   return launch_vm(d, st, (int)coset, (uint4*)d_out, (unsigned)row0, (unsigned)nrows, halo_before);
 }
 
@@ -372,7 +370,7 @@ int trp_quotient_eval(trp_domain* d, const uint32_t* program, size_t n_instr, un
   for (size_t c = 0; c < n_cols; ++c) if (!cols[c]) TRP_FAIL(ctx, TRP_E_INVALID, "column %zu is NULL", c);
   const size_t EN = (size_t)1 << d->ext_k;
   Staged st;
-  TRP_TRY(stage_tables(ctx, program, n_instr, n_regs, consts, n_consts, nullptr, n_cols, (n_cols + 1) * EN * 32, &st));
+  TRP_TRY(stage_tables(d, program, n_instr, n_regs, consts, n_consts, nullptr, n_cols, (n_cols + 1) * EN * 32, &st));
   char* after = st.after;
   std::vector<const uint64_t*> dptr(n_cols);
   for (size_t c = 0; c < n_cols; ++c) {
