@@ -21,7 +21,7 @@ fn main() {
     assert!(!units.is_empty());
     for entry in fs::read_dir(&csrc).unwrap() {
         let p = entry.unwrap().path();
-        if p.extension().map_or(false, |e| e == "cuh") { println!("cargo:rerun-if-changed={}", p.display()); }
+        if p.extension().map_or(false, |e| e == "cuh" || e == "h") { println!("cargo:rerun-if-changed={}", p.display()); }
     }
     println!("cargo:rerun-if-changed={}", root.join("include").join("tr_prover.h").display());
     let mut objs = Vec::new();
