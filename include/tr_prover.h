@@ -102,6 +102,14 @@ int trp_dev_points_sum(trp_ctx* ctx, const uint64_t* d_jacobian, size_t g, uint6
  * memory (an arithmetic progression of random multiples of the generator). */
 int trp_dev_points_progression(trp_ctx* ctx, const uint64_t p0[8], const uint64_t d[8], size_t n, uint64_t* d_out);
 
+/* Inclusive prefix sums of n affine points in DEVICE memory: d_out[j] = d_in[0] + ... + d_in[j] (affine; may alias d_in).
+ * Summation by parts turns a commitment into one over these sums: sum_i z_i G_i = sum_j (z_j - z_{j+1}) Q_j (z_n = 0), and the
+ * difference column is SPARSE whenever z rarely changes from row to row -- halo2's grand-product columns (permutation::Argument::
+ * commit, lookup::Permuted::commit_product) stay constant over the rows a circuit does not use.  Same group element, so
+ * Params::commit_lagrange's result is unchanged; the prover builds Q once per parameter set and commits such columns through
+ * its sparse path. */
+int trp_dev_points_prefix_sum(trp_ctx* ctx, const uint64_t* d_in, size_t n, uint64_t* d_out);
+
 /* ---- NTT: halo2_proofs::arithmetic::best_fft(a, omega, log_n) (field instance) -------------------------
  * In place, natural order in and out: a[k] <- sum_j a[j] * omega^(j k); batch contiguous vectors of 2^log_n. */
 int trp_ntt(trp_ctx* ctx, uint64_t* a, size_t batch, unsigned log_n, const uint64_t omega[4]);

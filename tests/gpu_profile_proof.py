@@ -34,8 +34,9 @@ def prove(timings=None):
     return PL.create_proof(be, pk, d_inst, cols, rng, PL.Blake2bWrite(be.q, be.p), timings=timings)
 
 
-for _ in range(2):
-    prove()
+import hashlib
+first_sha = hashlib.sha256(prove()).hexdigest()          # fixed seed: comparable between runs (e.g. TRP_COMMIT_BY_PARTS=0 / 1)
+prove()
 be._wait()
 t0 = time.perf_counter(); prove(); be._wait(); wall = time.perf_counter() - t0
 ph = {}
@@ -48,7 +49,7 @@ pr = cProfile.Profile()
 pr.enable(); prove(); be._wait(); pr.disable()
 s = io.StringIO()
 pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(45)
-print(json.dumps({"k": k, "create_proof_s": round(wall, 3), "with_phase_waits_s": round(wall_sync, 3), "phases_s": {a: round(b, 3) for a, b in ph.items()},
+print(json.dumps({"k": k, "first_proof_sha256": first_sha, "create_proof_s": round(wall, 3), "with_phase_waits_s": round(wall_sync, 3), "phases_s": {a: round(b, 3) for a, b in ph.items()},
                   "device_ms_by_library_phase": {a: round(b[0], 1) for a, b in prof.items() if b[1]}, "spans": {a: b[1] for a, b in prof.items() if b[1]},
                   "ntt_butterflies": work["ntt_pass"]}))
 print(s.getvalue()[:9000])

@@ -216,6 +216,73 @@ def test_point_range_split_and_points_sum(pkg, ctxs):
     assert not out.any()
 
 
+@pytest.mark.parametrize("curve", [O.VESTA, O.PALLAS])
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 4097, 70001])
+def test_points_prefix_sum(pkg, ctxs, curve, n):
+    """trp_dev_points_prefix_sum against a sequential sum with the oracle's point addition: identity inputs, P + P (the doubling
+    case), P + (-P) (a prefix that IS the identity), chunk / segment boundaries (16 points per thread, 256 chunks per segment)"""
+    import torch
+    if curve == O.PALLAS and n > 4097:
+        pytest.skip("one curve is enough at this size")
+    ctx = ctxs[curve]
+    pts = make_points(curve, n).copy()
+    base = O.BASE_FIELD[curve]
+    neg = lambda P: np.concatenate([P[:4], O.field_op(base, "sub", np.zeros((1, 4), dtype=np.uint64), P[4:].reshape(1, 4))[0]])
+    if n >= 15:
+        pts[1] = neg(pts[0])                  # prefix[1] = identity
+        pts[3] = pts[2]                       # the accumulator equals the next input: the exact P + P case
+        pts[4] = 0                            # an identity input
+        pts[7] = neg(pts[6])
+    if n >= 4097:
+        pts[16 * 256 - 1] = 0
+        pts[16 * 256] = pts[16 * 256 + 1]
+    want = np.zeros((n, 8), dtype=np.uint64)
+    acc = np.zeros(8, dtype=np.uint64)
+    for i in range(n):
+        acc = O.point_add(curve, acc, pts[i])
+        want[i] = acc
+    d = torch.from_numpy(pts.view(np.int64)).cuda()
+    out = torch.empty_like(d)
+    torch.cuda.synchronize()
+    ctx.check(ctx.lib.trp_dev_points_prefix_sum(ctx.handle, d.data_ptr(), n, out.data_ptr()))
+    ctx.sync()
+    assert np.array_equal(out.cpu().numpy().view(np.uint64).reshape(n, 8), want)
+    ctx.check(ctx.lib.trp_dev_points_prefix_sum(ctx.handle, d.data_ptr(), n, d.data_ptr()))          # in place
+    ctx.sync()
+    assert np.array_equal(d.cpu().numpy().view(np.uint64).reshape(n, 8), want)
+
+
+def test_commitment_by_parts(pkg, ctxs):
+    """sum_i z_i G_i = sum_j (z_j - z_{j+1}) Q_j with Q = prefix sums of G (z_n = 0): the identity behind GpuBackend's commitment
+    of grand-product columns through their sparse differences; both sides on the device, and against the oracle's MSM"""
+    import torch
+    curve = O.VESTA
+    ctx = ctxs[curve]
+    n = 6000
+    G = make_points(curve, n)
+    rng = np.random.default_rng(3)
+    vals = scalars_uniform(curve, 40, 9)
+    z = np.zeros((n, 4), dtype=np.uint64)
+    i = 0
+    while i < n:                               # runs of equal values, some of them zero, a dense stretch in the middle
+        ln = int(rng.integers(1, 400)) if not (2000 <= i < 2300) else 1
+        z[i:i + ln] = 0 if rng.random() < 0.2 else vals[int(rng.integers(0, 40))]
+        i += ln
+    d = torch.from_numpy(G.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    ctx.check(ctx.lib.trp_dev_points_prefix_sum(ctx.handle, d.data_ptr(), n, d.data_ptr()))
+    ctx.sync()
+    Q = d.cpu().numpy().view(np.uint64).reshape(n, 8)
+    field = O.SCALAR_FIELD[curve]
+    e = z.copy()
+    e[:n - 1] = O.field_op(field, "sub", z[:n - 1], z[1:])
+    direct = pkg.best_multiexp(ctx, z, pkg.Bases(ctx, G))
+    by_parts = pkg.best_multiexp(ctx, e, pkg.Bases(ctx, Q))
+    assert np.array_equal(affine_of(curve, by_parts), affine_of(curve, direct))
+    assert np.array_equal(affine_of(curve, direct), O.msm(curve, z, G))
+    assert int((e != 0).any(axis=1).sum()) < int((z != 0).any(axis=1).sum()) // 3
+
+
 # ---- the upper half of BASELINE.json configs[1] / configs[2]: 2^22 and 2^24, compared with the oracle byte for byte ---------
 _LARGE = {}
 

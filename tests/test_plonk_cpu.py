@@ -241,3 +241,46 @@ def test_cached_quotient_program_equals_a_fresh_compile(PL):
     slots = pk._quotient_program[id(be)][2]
     names = {s[0] for s in slots if s is not None}
     assert names == {"theta", "beta", "gamma", "y", "beta_delta"}
+
+
+def test_summation_by_parts_commitment_identity():
+    """sum_i z_i G_i = sum_j (z_j - z_{j+1}) Q_j, Q_j = G_0 + ... + G_j, z_n = 0 -- what plonk.GpuBackend._commit_many(runs=True) relies
+    on to commit halo2's grand-product columns (constant over the rows a circuit leaves unused) through their sparse differences;
+    checked here with the oracle's affine group law on a column with runs, zeros and a change in the last row"""
+    import random
+    import pasta_model as pm
+    C = pm.Vesta
+    r = C.scalar.p
+    rng = random.Random(17)
+    n = 24
+    G, P = [], C.G
+    for _ in range(n):
+        P = C.add(C.double(P), C.G)
+        G.append(P)
+    z, v = [], 0
+    for i in range(n):
+        if rng.random() < 0.3:
+            v = rng.choice([0, rng.randrange(r)])
+        z.append(v)
+    z[-1] = rng.randrange(r)
+    def smul(k, P):
+        acc, k = None, k % r
+        while k:
+            if k & 1:
+                acc = C.add(acc, P)
+            P = C.double(P)
+            k >>= 1
+        return acc
+    direct = None
+    for zi, Gi in zip(z, G):
+        direct = C.add(direct, smul(zi, Gi))
+    Q, acc = [], None
+    for Gi in G:
+        acc = C.add(acc, Gi)
+        Q.append(acc)
+    e = [(z[j] - (z[j + 1] if j + 1 < n else 0)) % r for j in range(n)]
+    by_parts = None
+    for ej, Qj in zip(e, Q):
+        by_parts = C.add(by_parts, smul(ej, Qj))
+    assert by_parts == direct and direct is not None
+    assert sum(1 for x in e if x) < n

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "trp_ctx_create", "trp_ctx_destroy", "trp_last_error", "trp_ctx_set_stream", "trp_ctx_sync",
     "trp_ctx_launch_count", "trp_version", "trp_prof_enable", "trp_prof_reset", "trp_prof_get", "trp_prof_get_work",
     "trp_bases_load", "trp_dev_bases_load", "trp_bases_load_ex", "trp_dev_bases_load_ex", "trp_bases_len", "trp_bases_describe", "trp_bases_free",
-    "trp_msm", "trp_msm_batch", "trp_dev_msm_batch", "trp_dev_points_progression", "trp_points_sum", "trp_dev_points_sum",
+    "trp_msm", "trp_msm_batch", "trp_dev_msm_batch", "trp_dev_points_progression", "trp_dev_points_prefix_sum", "trp_points_sum", "trp_dev_points_sum",
     "trp_ntt", "trp_dev_ntt",
     "trp_domain_create", "trp_domain_free", "trp_domain_extended_k", "trp_domain_constants",
     "trp_lagrange_to_coeff", "trp_dev_lagrange_to_coeff", "trp_coeff_to_lagrange",
@@ -91,6 +91,7 @@ def load_library():
     L.trp_msm_batch.argtypes = [vp, vp, vp, sz, sz, vp]
     L.trp_dev_msm_batch.argtypes = [vp, vp, vp, sz, sz, vp]
     L.trp_dev_points_progression.argtypes = [vp, vp, vp, sz, vp]
+    L.trp_dev_points_prefix_sum.argtypes = [vp, vp, sz, vp]
     L.trp_points_sum.argtypes = [vp, vp, sz, vp]
     L.trp_dev_points_sum.argtypes = [vp, vp, sz, vp]
     L.trp_ntt.argtypes = [vp, vp, sz, u, vp]

@@ -333,6 +333,16 @@ int trp_dev_points_progression(trp_ctx* ctx, const uint64_t p0[8], const uint64_
   return trp_points_progression_impl(ctx, p0, d, n, d_out);
 }
 
+// inclusive prefix sums of n affine points on the device: d_out[j] = d_in[0] + ... + d_in[j] (affine, identity = all zero).
+// The base set of the summation-by-parts commitment: sum_i z_i G_i = sum_j (z_j - z_{j+1}) Q_j with Q = prefix sums of G.
+int trp_dev_points_prefix_sum(trp_ctx* ctx, const uint64_t* d_in, size_t n, uint64_t* d_out) {
+  if (!ctx) return TRP_E_INVALID;
+  Locked l(ctx);
+  if (n && (!d_in || !d_out)) TRP_FAIL(ctx, TRP_E_INVALID, "NULL buffer");
+  TRP_TRY(trp_ws_reserve(ctx, trp_points_prefix_ws_bytes(n)));
+  return trp_points_prefix_sum_impl(ctx, d_in, n, d_out, ctx->ws);
+}
+
 // ---- NTT ---------------------------------------------------------------------------------------------------
 int trp_dev_ntt(trp_ctx* ctx, uint64_t* d_a, size_t batch, unsigned log_n, const uint64_t omega[4]) {
   if (!ctx) return TRP_E_INVALID;

@@ -169,6 +169,8 @@ int trp_msm_impl(trp_ctx* ctx, const trp_bases* bases, const void* d_scalars, si
 size_t trp_msm_ws_bytes(const trp_bases* bases, size_t n, size_t m);
 int trp_points_sum_impl(trp_ctx* ctx, const void* d_jac, size_t g, void* d_out);
 int trp_points_progression_impl(trp_ctx* ctx, const uint64_t* p0, const uint64_t* d, size_t n, void* d_out);
+size_t trp_points_prefix_ws_bytes(size_t n);
+int trp_points_prefix_sum_impl(trp_ctx* ctx, const void* d_in, size_t n, void* d_out, void* ws);
 int trp_bases_create(trp_ctx* ctx, const void* src, bool src_on_device, size_t n, int flags, trp_bases** out);
 void trp_bases_destroy(trp_bases* b);
 int trp_bases_info(const trp_bases* b, unsigned* c, unsigned* W, unsigned* precomp);

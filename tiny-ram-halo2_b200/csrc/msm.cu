@@ -659,6 +659,98 @@ int trp_bases_info(const trp_bases* b, unsigned* c, unsigned* W, unsigned* preco
   return TRP_OK;
 }
 
+// ---- inclusive prefix sums of affine points: out[j] = P_0 + ... + P_j (affine) -------------------------------------------
+// The base set of the "summation by parts" commitment (capi.cu, trp_dev_points_prefix_sum): a column z whose value rarely
+// CHANGES from row to row (halo2's grand-product columns are constant over the unused rows of a circuit) commits as
+//   sum_i z_i G_i = sum_j (z_j - z_{j+1}) Q_j,   Q_j = G_0 + ... + G_j,  z_n = 0,
+// an MSM over Q with a SPARSE scalar column.  Q is built once per parameter set: per-thread chunk totals (PS_CH points), a
+// two-level serial scan of the totals (segments of PS_SEG), then every thread replays its chunk from its offset and
+// normalises its PS_CH results with one inversion.
+constexpr unsigned PS_CH = 16, PS_SEG = 256;
+template <class BPR>
+__global__ void __launch_bounds__(128) points_chunk_totals_kernel(const uint4* in, size_t n, uint4* tot) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t start = t * PS_CH;
+  if (start >= n) return;
+  unsigned cnt = (unsigned)(n - start < PS_CH ? n - start : PS_CH);
+  XYZZ<BPR> acc = xyzz_identity<BPR>();
+  for (unsigned k = 0; k < cnt; ++k) xyzz_add_mixed(acc, load_affine<BPR>(in, start + k));
+  store_xyzz(tot + 8 * t, acc);
+}
+// v[g * seg .. (g + 1) * seg) -> exclusive prefix sums within the segment, seg_tot[g] = the segment's total
+template <class BPR>
+__global__ void __launch_bounds__(64) points_scan_segments_kernel(uint4* v, size_t count, size_t seg, uint4* seg_tot) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t start = g * seg;
+  if (start >= count) return;
+  size_t end = start + seg < count ? start + seg : count;
+  XYZZ<BPR> acc = xyzz_identity<BPR>();
+  for (size_t i = start; i < end; ++i) {
+    XYZZ<BPR> x = load_xyzz<BPR>(v + 8 * i);
+    store_xyzz(v + 8 * i, acc);
+    xyzz_add(acc, x);
+  }
+  store_xyzz(seg_tot + 8 * g, acc);
+}
+template <class BPR>
+__global__ void __launch_bounds__(128) points_prefix_finish_kernel(const uint4* in, size_t n, const uint4* tot_excl, const uint4* seg_excl,
+                                                                    const uint4* seg2_excl, uint4* out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t start = t * PS_CH;
+  if (start >= n) return;
+  unsigned cnt = (unsigned)(n - start < PS_CH ? n - start : PS_CH);
+  XYZZ<BPR> cur = load_xyzz<BPR>(seg2_excl + 8 * (t / PS_SEG / PS_SEG));
+  xyzz_add(cur, load_xyzz<BPR>(seg_excl + 8 * (t / PS_SEG)));
+  xyzz_add(cur, load_xyzz<BPR>(tot_excl + 8 * t));
+  XYZZ<BPR> chain[PS_CH];
+  Fe<BPR> pre[PS_CH];
+  Fe<BPR> prod = fe_one<BPR>();
+  for (unsigned k = 0; k < cnt; ++k) {
+    xyzz_add_mixed(cur, load_affine<BPR>(in, start + k));
+    chain[k] = cur;
+    pre[k] = prod;
+    if (!xyzz_is_identity(cur)) prod = fe_mul(prod, fe_mul(cur.zz, cur.zzz));
+  }
+  Fe<BPR> inv = fe_inv(prod);
+  for (int k = (int)cnt - 1; k >= 0; --k) {
+    uint4* slot = out + 4 * (start + k);
+    const XYZZ<BPR> e = chain[k];
+    if (xyzz_is_identity(e)) { for (int q = 0; q < 4; ++q) slot[q] = make_uint4(0, 0, 0, 0); continue; }
+    Fe<BPR> einv = fe_mul(inv, pre[k]);
+    inv = fe_mul(inv, fe_mul(e.zz, e.zzz));
+    fe_store(slot, fe_mul(e.x, fe_mul(einv, e.zzz)));
+    fe_store(slot + 2, fe_mul(e.y, fe_mul(einv, e.zz)));
+  }
+}
+
+// d_in / d_out: n affine points (may alias: a thread reads its chunk before it writes it, and only its own chunk).
+// ws: (ceil(n / PS_CH) + ceil(.. / PS_SEG) + ceil(.. / PS_SEG^2) + 1) XYZZ slots
+size_t trp_points_prefix_ws_bytes(size_t n) {
+  size_t t0 = (n + PS_CH - 1) / PS_CH, t1 = (t0 + PS_SEG - 1) / PS_SEG, t2 = (t1 + PS_SEG - 1) / PS_SEG;
+  return (t0 + t1 + t2 + 1) * 128 + 1024;
+}
+int trp_points_prefix_sum_impl(trp_ctx* ctx, const void* d_in, size_t n, void* d_out, void* ws) {
+  if (n == 0) return TRP_OK;
+  const size_t t0 = (n + PS_CH - 1) / PS_CH, t1 = (t0 + PS_SEG - 1) / PS_SEG, t2 = (t1 + PS_SEG - 1) / PS_SEG;
+  if (t2 > PS_SEG) TRP_FAIL(ctx, TRP_E_INVALID, "prefix sums of more than %zu points are not supported", (size_t)PS_CH * PS_SEG * PS_SEG * PS_SEG);
+  uint4* tot = (uint4*)ws; uint4* seg = tot + 8 * t0; uint4* seg2 = seg + 8 * t1; uint4* top = seg2 + 8 * t2;
+  auto launch = [&](auto tag) -> int {
+    typedef decltype(tag) BPR;
+    points_chunk_totals_kernel<BPR><<<(unsigned)((t0 + 127) / 128), 128, 0, ctx->stream>>>((const uint4*)d_in, n, tot);
+    TRP_LAUNCHED(ctx);
+    points_scan_segments_kernel<BPR><<<(unsigned)((t1 + 63) / 64), 64, 0, ctx->stream>>>(tot, t0, PS_SEG, seg);
+    TRP_LAUNCHED(ctx);
+    points_scan_segments_kernel<BPR><<<(unsigned)((t2 + 63) / 64), 64, 0, ctx->stream>>>(seg, t1, PS_SEG, seg2);
+    TRP_LAUNCHED(ctx);
+    points_scan_segments_kernel<BPR><<<1, 64, 0, ctx->stream>>>(seg2, t2, PS_SEG, top);     // t2 <= PS_SEG: one segment
+    TRP_LAUNCHED(ctx);
+    points_prefix_finish_kernel<BPR><<<(unsigned)((t0 + 127) / 128), 128, 0, ctx->stream>>>((const uint4*)d_in, n, tot, seg, seg2, (uint4*)d_out);
+    TRP_LAUNCHED(ctx);
+    return TRP_OK;
+  };
+  return base_field_of(ctx->curve) == 0 ? launch(FpParams()) : launch(FqParams());
+}
+
 int trp_points_progression_impl(trp_ctx* ctx, const uint64_t* p0, const uint64_t* d, size_t n, void* d_out) {
   if (n == 0) return TRP_OK;
   unsigned threads = (unsigned)((n + GEN_CH - 1) / GEN_CH);

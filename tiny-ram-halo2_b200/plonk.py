@@ -527,6 +527,9 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     # instance / advice / permuted lookup columns are often mostly zero (a circuit that uses a fraction of its rows): backends that
     # keep a narrow MSM table for such columns take the hint (they check the density themselves)
     sparse_kw = {"sparse": True} if getattr(B, "accepts_sparse_hint", False) else {}
+    # grand-product columns (and permuted lookup columns with a non-zero default) are constant over the rows a circuit leaves
+    # unused: backends that can commit a column through its row-to-row differences take this hint (GpuBackend._commit_many)
+    runs_kw = {"runs": True} if getattr(B, "accepts_runs_hint", False) else {}
 
     # ---- instance columns: commit (not written, only absorbed) -------------------------------------------------------------
     inst_values = [column(c, "InstanceTooLarge: instance") for c in instances]
@@ -571,7 +574,7 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
     for L, pi_poly, pt_poly in zip(lookups, *[to_coeff_many([L[nm] for L in lookups]) for nm in ("pi", "pt")]):
         L["pi_poly"], L["pt_poly"] = pi_poly, pt_poly
     # the commitments do not feed the RNG, so they are computed as one batch and written in halo2's order
-    for cm in B.commit_lagrange_many([L[nm] for L in lookups for nm in ("pi", "pt")], [L[nm + "_blind"] for L in lookups for nm in ("pi", "pt")], **sparse_kw):
+    for cm in B.commit_lagrange_many([L[nm] for L in lookups for nm in ("pi", "pt")], [L[nm + "_blind"] for L in lookups for nm in ("pi", "pt")], **sparse_kw, **runs_kw):
         transcript.write_point(cm)
     tick("lookups_permuted")
 
@@ -586,7 +589,7 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
 
     if cs.permutation:
         B.permutation_commit([values_of[kk][c] for kk, c in cs.permutation], pk.sigma_values, beta, gamma, chunk_len, bf, rand, after_chunk)
-    for cm in B.commit_lagrange_many([S["z"] for S in perm_sets], [S["blind"] for S in perm_sets]):
+    for cm in B.commit_lagrange_many([S["z"] for S in perm_sets], [S["blind"] for S in perm_sets], **runs_kw):
         transcript.write_point(cm)
     for S, poly in zip(perm_sets, to_coeff_many([S["z"] for S in perm_sets])):
         S["poly"] = poly
@@ -597,7 +600,7 @@ def create_proof(backend, pk: ProvingKey, instances, advice, rand: Callable[[], 
         for L in lookups:
             L["z"] = B.lookup_product(L["ci"], L["ct"], L["pi"], L["pt"], beta, gamma, bf, rand)
             L["z_blind"] = rand()
-    for cm in B.commit_lagrange_many([L["z"] for L in lookups], [L["z_blind"] for L in lookups]):
+    for cm in B.commit_lagrange_many([L["z"] for L in lookups], [L["z_blind"] for L in lookups], **runs_kw):
         transcript.write_point(cm)
     for L, poly in zip(lookups, to_coeff_many([L["z"] for L in lookups])):
         L["z_poly"] = poly
@@ -837,6 +840,7 @@ class GpuBackend:
 
     def __init__(self, ctx, k: int, cs_degree: int, params=None):
         import ctypes
+        import os
         import numpy as np
         import torch
         from . import ipa as _ipa, permutation as _perm
@@ -867,12 +871,28 @@ class GpuBackend:
         if k >= 18:
             from .arithmetic import Bases
             self._gl_sparse = Bases(ctx, np.concatenate([self.params.g_lagrange_points, self.params.w.reshape(1, 8)]), 13 << 8)
+        # a third table over Q ++ [w], Q_j = g_lagrange_0 + ... + g_lagrange_j (trp_dev_points_prefix_sum): summation by parts,
+        #     sum_i z_i G_i = sum_j (z_j - z_{j+1}) Q_j   (z_n = 0),
+        # commits a column through its DIFFERENCES, which are sparse whenever the column rarely changes from row to row.  halo2's
+        # grand-product columns do exactly that: on the rows a circuit leaves unused every factor of the permutation / lookup
+        # product is 1, so Z is dense in value but constant over 15/16 of TinyRAM's rows (and some permuted lookup columns hold a
+        # non-zero default there).  Same group element, same proof bytes; 78 of the 86 dense MSMs of a proof become sparse ones.
+        self._gl_prefix = None
+        if os.environ.get("TRP_COMMIT_BY_PARTS", "1") != "0":
+            from .arithmetic import Bases
+            d_q = self.torch.from_numpy(np.ascontiguousarray(self.params.g_lagrange_points).view(np.int64)).cuda()
+            self._sync()
+            self.ctx.check(self.lib.trp_dev_points_prefix_sum(self.ctx.handle, d_q.data_ptr(), self.n, d_q.data_ptr()))
+            q_host = d_q.cpu().numpy().view(np.uint64).reshape(self.n, 8)
+            self._gl_prefix = Bases(ctx, np.concatenate([q_host, self.params.w.reshape(1, 8)]), (13 << 8) if k >= 18 else 0)
+            del d_q
         self.ev = P.new_evaluator(ctx)
         self._static, self._static_keep = {}, []
         self.static_budget_bytes = 48 << 30
         self._arena, self._arena_used, self._arena_slot, self._arena_on, self._coset_buf = None, 0, {}, False, None
         self.leaves_are_coefficients = True       # coeff_to_extended keeps coefficient form (cosets are expanded in quotient())
         self.accepts_sparse_hint = True
+        self.accepts_runs_hint = self._gl_prefix is not None
 
     def close(self):
         """release the library-side handles (MSM tables of the opening, the domain); torch tensors follow Python's lifetime"""
@@ -1041,9 +1061,11 @@ class GpuBackend:
     def commit_lagrange(self, v, blind): return self._commit(self.params.g_lagrange, v, blind)
     def commit(self, v, blind): return self._commit(self.params.g, v, blind)
 
-    def _commit_many(self, bases, vecs, blinds, batch=32, sparse=False):
+    def _commit_many(self, bases, vecs, blinds, batch=32, sparse=False, runs=False):
         """several commitments over the same bases as batched MSMs (trp_dev_msm_batch processes the columns concurrently).
-        sparse: the caller expects mostly-zero columns; batches whose non-zero rows are below 10 % go to the narrow table."""
+        sparse: the caller expects mostly-zero columns; batches whose non-zero rows are below 10 % go to the narrow table.
+        runs: the caller expects columns that rarely change from row to row (grand products over a partly used circuit): the
+        batch is committed by parts -- its row-to-row differences over the prefix sums of the bases -- if those are below 10 %."""
         t, n, results = self.torch, self.n, []
         if len(vecs) > batch:                        # equal batches (33 columns: 17 + 16, not 32 + 1)
             nb = -(-len(vecs) // batch)
@@ -1058,6 +1080,15 @@ class GpuBackend:
             if sparse and self._gl_sparse is not None and bases is self.params.g_lagrange:
                 if int((stage != 0).any(dim=-1).sum()) * 10 <= len(vs) * n:
                     use = self._gl_sparse
+            if runs and use is bases and self._gl_prefix is not None and bases is self.params.g_lagrange:
+                # e_j = z_j - z_{j+1} (j < n - 1), e_{n-1} = z_{n-1}; the blind keeps its own base w
+                diff = t.empty_like(stage)
+                flat_in, flat_out = stage.view(-1, 4), diff.view(-1, 4)
+                self.ctx.check(self.lib.trp_dev_field_op(self.ctx.handle, 0, 1, flat_in.data_ptr(), flat_in[1:].data_ptr(), flat_out.data_ptr(),
+                                                         flat_in.shape[0] - 1))
+                diff[:, n - 1:] = stage[:, n - 1:]
+                if int((diff != 0).any(dim=-1).sum()) * 10 <= len(vs) * n:
+                    use, stage = self._gl_prefix, diff
             res = t.zeros((len(vs), 12), dtype=t.int64, device="cuda")
             self.ctx.check(self.lib.trp_dev_msm_batch(self.ctx.handle, use.handle, stage.data_ptr(), n + 1, len(vs), res.data_ptr()))
             results.append(res)
@@ -1068,7 +1099,8 @@ class GpuBackend:
                 out.append(None if not j[2].any() else tuple(self._ints(j[:2], self.q, self.Rqinv)))
         return out
 
-    def commit_lagrange_many(self, vecs, blinds, sparse=False): return self._commit_many(self.params.g_lagrange, vecs, blinds, sparse=sparse)
+    def commit_lagrange_many(self, vecs, blinds, sparse=False, runs=False):
+        return self._commit_many(self.params.g_lagrange, vecs, blinds, sparse=sparse, runs=runs)
     def commit_many(self, vecs, blinds): return self._commit_many(self.params.g, vecs, blinds)
 
     # -- the verifier's three extras (verifier.py): the fixed points, the challenges' s vector, a variable-base MSM
