@@ -235,7 +235,7 @@ def test_points_prefix_sum(pkg, ctxs, curve, n):
         pts[7] = neg(pts[6])
     if n >= 4097:
         pts[16 * 256 - 1] = 0
-        pts[16 * 256] = pts[16 * 256 + 1]
+        pts[16 * 256] = pts[16 * 256 - 2]
     want = np.zeros((n, 8), dtype=np.uint64)
     acc = np.zeros(8, dtype=np.uint64)
     for i in range(n):
