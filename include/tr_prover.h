@@ -140,7 +140,7 @@ int trp_dev_extended_to_coeff(trp_domain* d, uint64_t* d_ext, uint64_t* d_out_co
  * plonk::vanishing::Argument::construct in create_proof: h_ext[r] = sum_j y^j expr_j(row r) over the extended domain.
  * The caller lowers its poly::Ast into a straight-line program over n_regs virtual registers (field elements);
  * an instruction is 4 x uint32 { op, dst, a, b }:
- *    0 LOAD   dst = cols[a][(row + (int32)b * step) mod rows]      (Ast::Poly(leaf).with_rotation(b))
+ *    0 LOAD   dst = cols[a][(row + (int32)b * step) mod rows]      (Ast::Poly(leaf).with_rotation(b), |b| <= 32767)
  *    1 CONST  dst = consts[a]                                       (Ast::ConstantTerm)
  *    2 ADD  3 SUB  4 MUL   dst = r[a] op r[b]                       (Ast::Add / Ast::Mul)
  *    5 NEG  6 SQR  7 DBL   dst = op r[a]

@@ -46,7 +46,7 @@ struct trp_ctx {
   size_t pinned_bytes = 0;
   std::vector<TwiddleTable> twiddles;
   // quotient.cu: the caller's last quotient program and its lowered form (qlower.h); a prover runs one program on j - 1 cosets
-  std::vector<uint32_t> q_src, q_low;
+  std::vector<uint32_t> q_src, q_low, q_staged;
   unsigned q_src_regs = 0, q_low_regs = 0;
   size_t q_src_consts = 0;
 };

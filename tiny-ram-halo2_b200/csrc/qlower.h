@@ -32,7 +32,7 @@ enum Flag : uint32_t { F_FWD_A = 1, F_NOWB = 2, F_NO_A = 4 };
 enum KOp : uint32_t { K_NOP = 0, K_MOV_CONST, K_MOV_COL, K_MOV_X, K_MOV_REG, K_ADD_REG, K_ADD_CONST, K_ADD_COL, K_SUB_REG, K_SUB_CONST, K_SUB_COL,
                       K_RSUB_REG, K_RSUB_CONST, K_RSUB_COL, K_MUL_REG, K_MUL_CONST, K_MUL_COL, K_MUL_A, K_NEG, K_DBL, K_STORE, K_COUNT };
 constexpr uint32_t MAX_COLS = 1u << 21;
-constexpr int PAD = 4;                     // NOPs appended to a lowered program
+constexpr int PAD = 2;                     // NOPs appended to a lowered program (the kernel fetches one instruction ahead)
 
 struct Ins {
   uint32_t op, bm, fl, col, dst, a, b;
@@ -196,6 +196,37 @@ inline bool lower(const uint32_t* prog, size_t n_instr_in, unsigned n_regs, size
   for (int pad = 0; pad < PAD; ++pad)                                                 // the kernel fetches up to PAD instructions ahead
     for (int k = 0; k < 4; ++k) out.push_back(k == 0 ? (uint32_t)K_NOP | ((F_NO_A | F_NOWB) << 5) : 0u);
   if (st) *st = s;
+  return true;
+}
+
+// Device encoding of a lowered program for ONE launch: everything the kernel would otherwise compute per instruction is folded in
+// here, on the host, once per call (the program is staged per call anyway) -- register indices become shared-memory slot offsets
+// (reg << bd_log, 2^bd_log threads per CTA) and a column operand carries the column's device ADDRESS, so the kernel needs no
+// pointer-table lookup (one dependent load and one level of prefetch less) and no index arithmetic for its register file:
+//     x = kernel opcode | flags << 5 | (dst << bd_log) << 8      y = (a << bd_log) | rotation << 16 (int16)
+//     z, w = b: register slot (z) / constant index (z) / column address (z = low, w = high 32 bits)
+// Returns false if a rotation does not fit 16 bits or a register slot does not fit its field.
+inline bool is_col(uint32_t k) { return k == K_MOV_COL || k == K_ADD_COL || k == K_SUB_COL || k == K_RSUB_COL || k == K_MUL_COL; }
+inline bool is_regb(uint32_t k) { return k == K_MOV_REG || k == K_ADD_REG || k == K_SUB_REG || k == K_RSUB_REG || k == K_MUL_REG; }
+inline bool stage(const std::vector<uint32_t>& low, unsigned n_regs, unsigned bd_log, const uint64_t* col_ptrs, size_t n_cols,
+                  std::vector<uint32_t>& out) {
+  if (((uint64_t)n_regs << bd_log) > 65536) return false;
+  out.resize(low.size());
+  for (size_t i = 0; i + 3 < low.size(); i += 4) {
+    const uint32_t x = low[i], k = x & 31u, fl = (x >> 5) & 7u, col = x >> 11, dst = low[i + 1], a = low[i + 2], b = low[i + 3];
+    uint32_t y = (fl & F_NO_A) ? 0u : (a << bd_log), z = 0, w = 0;
+    if (is_col(k)) {
+      const int32_t rot = (int32_t)b;
+      if (rot < -32768 || rot > 32767 || col >= n_cols) return false;
+      y |= ((uint32_t)rot & 0xffffu) << 16;
+      z = (uint32_t)col_ptrs[col]; w = (uint32_t)(col_ptrs[col] >> 32);
+    } else if (is_regb(k)) {
+      z = b << bd_log;
+    } else {
+      z = b;                                                       // constant index (or unused)
+    }
+    out[i] = k | (fl << 5) | ((dst << bd_log) << 8); out[i + 1] = y; out[i + 2] = z; out[i + 3] = w;
+  }
   return true;
 }
 

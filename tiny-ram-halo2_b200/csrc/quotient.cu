@@ -36,10 +36,9 @@ enum QOp : uint32_t {
 };
 
 struct QParams {
-  const uint4* prog;     // LOWERED program (qlower.h), qlower::PAD NOPs appended
+  const uint4* prog;     // lowered program in the staged encoding (qlower::stage), qlower::PAD NOPs appended
   unsigned n_instr, n_regs, bd_log;
   const uint4* consts;
-  const uint4* const* cols;
   unsigned rows_log, step, out_stride, out_off, x_stride, x_off, ext_log;
   // row-slice mode (nrows > 0): the columns hold rows [row0 - halo_before, row0 + nrows + halo_after) of the coset (cyclic
   // neighbours copied in by the caller), thread t evaluates coset row row0 + t and stores out[t]
@@ -52,9 +51,9 @@ struct QParams {
 // (acc); an instruction first reloads acc from the virtual register file (shared memory, two 16-byte planes [reg][thread]) unless
 // its operand a IS the previous result, combines it with operand b -- register file, constant table, a column at (row +
 // rotation), the coset-X table -- and stores acc back unless nobody will read it from the register file.  One case per
-// (operation, source of b), so that no operand is ever moved between registers.  The fetch is software-pipelined so that no load
-// waits for another load: instruction pc + 2 and the column POINTER of pc + 1 are requested while pc executes, a column operand
-// costs one memory latency instead of three in a row.  The program is padded with NOPs so the look-ahead never leaves it.
+// (operation, source of b), so that no operand is ever moved between registers.  The instructions arrive in the staged encoding
+// of qlower::stage: register operands are slot offsets, a column operand is the column's address, so the only arithmetic left per
+// instruction is the row index of a column read; the next instruction is fetched while the current one executes.
 template <class PR>
 __global__ void __launch_bounds__(128) quotient_vm_kernel(QParams p) {
   using namespace qlower;
@@ -69,49 +68,45 @@ __global__ void __launch_bounds__(128) quotient_vm_kernel(QParams p) {
   const unsigned row = slice ? (gid < rows ? gid : rows - 1) : (gid & (rows - 1));
   const bool live = gid < rows;
   const unsigned idx0 = slice ? row + p.halo_before : row, idx_mask = slice ? 0xffffffffu : rows - 1, idx_step = slice ? 1u : p.step;
-  auto rd = [&](unsigned reg) -> Fe<PR> {
-    const uint4 lo = plane0[reg << p.bd_log], hi = plane1[reg << p.bd_log];
+  auto rd = [&](unsigned slot) -> Fe<PR> {
+    const uint4 lo = plane0[slot], hi = plane1[slot];
     Fe<PR> r;
     r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w; r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
     return r;
   };
-  auto col_ptr = [&](const uint4& i) -> const uint4* {
-    return reinterpret_cast<const uint4*>(__ldg(reinterpret_cast<const unsigned long long*>(p.cols) + (i.x >> 11)));
-  };
   auto cst = [&](unsigned i) -> Fe<PR> { return fe_load_ro<PR>(p.consts + 2 * (size_t)i); };
   Fe<PR> acc = fe_zero<PR>();
-  uint4 ins = __ldg(p.prog), nxt = __ldg(p.prog + 1);
-  const uint4* ptr = col_ptr(ins);
+  uint4 ins = __ldg(p.prog);
   for (unsigned pc = 0; pc < p.n_instr; ++pc) {
-    const uint4 ahead = __ldg(p.prog + pc + 2);
-    const uint4* ptr_ahead = col_ptr(nxt);
+    const uint4 nxt = __ldg(p.prog + pc + 1);
     const unsigned fl = ins.x >> 5;
-    if (!(fl & (F_FWD_A | F_NO_A))) acc = rd(ins.z);
+    if (!(fl & (F_FWD_A | F_NO_A))) acc = rd(ins.y & 0xffffu);
     auto col = [&]() -> Fe<PR> {
-      const unsigned idx = (idx0 + (unsigned)((int)ins.w * (int)idx_step)) & idx_mask;
-      return fe_load_ro<PR>(ptr + 2 * (size_t)idx);
+      const unsigned idx = (idx0 + (unsigned)(((int)ins.y >> 16) * (int)idx_step)) & idx_mask;
+      const uint4* base = reinterpret_cast<const uint4*>(((unsigned long long)ins.w << 32) | ins.z);
+      return fe_load_ro<PR>(base + 2 * (size_t)idx);
     };
     switch (ins.x & 31u) {
-      case K_MOV_CONST: acc = cst(ins.w); break;
+      case K_MOV_CONST: acc = cst(ins.z); break;
       case K_MOV_COL: acc = col(); break;
-      case K_MOV_REG: acc = rd(ins.w); break;
+      case K_MOV_REG: acc = rd(ins.z); break;
       case K_MOV_X: {
         const unsigned g = (row + p.row0) * p.x_stride + p.x_off, half = 1u << (p.ext_log - 1);
         acc = fe_load_ro<PR>(p.tw_ext + 2 * (size_t)(g & (half - 1)));
         if (g & half) acc = fe_neg(acc);
         break;
       }
-      case K_ADD_REG: acc = fe_add(acc, rd(ins.w)); break;
-      case K_ADD_CONST: acc = fe_add(acc, cst(ins.w)); break;
+      case K_ADD_REG: acc = fe_add(acc, rd(ins.z)); break;
+      case K_ADD_CONST: acc = fe_add(acc, cst(ins.z)); break;
       case K_ADD_COL: acc = fe_add(acc, col()); break;
-      case K_SUB_REG: acc = fe_sub(acc, rd(ins.w)); break;
-      case K_SUB_CONST: acc = fe_sub(acc, cst(ins.w)); break;
+      case K_SUB_REG: acc = fe_sub(acc, rd(ins.z)); break;
+      case K_SUB_CONST: acc = fe_sub(acc, cst(ins.z)); break;
       case K_SUB_COL: acc = fe_sub(acc, col()); break;
-      case K_RSUB_REG: acc = fe_sub(rd(ins.w), acc); break;
-      case K_RSUB_CONST: acc = fe_sub(cst(ins.w), acc); break;
+      case K_RSUB_REG: acc = fe_sub(rd(ins.z), acc); break;
+      case K_RSUB_CONST: acc = fe_sub(cst(ins.z), acc); break;
       case K_RSUB_COL: acc = fe_sub(col(), acc); break;
-      case K_MUL_REG: acc = fe_mul(acc, rd(ins.w)); break;
-      case K_MUL_CONST: acc = fe_mul(acc, cst(ins.w)); break;
+      case K_MUL_REG: acc = fe_mul(acc, rd(ins.z)); break;
+      case K_MUL_CONST: acc = fe_mul(acc, cst(ins.z)); break;
       case K_MUL_COL: acc = fe_mul(acc, col()); break;
       case K_MUL_A: acc = fe_mul(acc, acc); break;
       case K_NEG: acc = fe_neg(acc); break;
@@ -122,10 +117,11 @@ __global__ void __launch_bounds__(128) quotient_vm_kernel(QParams p) {
       default: break;
     }
     if (!(fl & F_NOWB)) {
-      plane0[ins.y << p.bd_log] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
-      plane1[ins.y << p.bd_log] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+      const unsigned slot = ins.x >> 8;
+      plane0[slot] = make_uint4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+      plane1[slot] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
     }
-    ins = nxt; nxt = ahead; ptr = ptr_ahead;
+    ins = nxt;
   }
 }
 
@@ -135,7 +131,7 @@ int validate_program(trp_ctx* ctx, const uint32_t* prog, size_t n_instr, unsigne
     const uint32_t op = prog[4 * i], dst = prog[4 * i + 1], a = prog[4 * i + 2], b = prog[4 * i + 3];
     bool ok = op < Q_NOPS;
     if (ok) switch (op) {
-      case Q_LOAD: ok = dst < n_regs && a < n_cols && ((int)b > -(1 << 20) && (int)b < (1 << 20)); break;
+      case Q_LOAD: ok = dst < n_regs && a < n_cols && ((int)b >= -32768 && (int)b <= 32767); break;
       case Q_CONST: ok = dst < n_regs && a < n_consts; break;
       case Q_ADD: case Q_SUB: case Q_MUL: ok = dst < n_regs && a < n_regs && b < n_regs; break;
       case Q_NEG: case Q_SQR: case Q_DBL: ok = dst < n_regs && a < n_regs; break;
@@ -149,18 +145,24 @@ int validate_program(trp_ctx* ctx, const uint32_t* prog, size_t n_instr, unsigne
   return TRP_OK;
 }
 
+// threads per CTA for a program of n_regs virtual registers (the register file is n_regs x threads x 32 B of shared memory)
+bool vm_geometry(unsigned n_regs, unsigned* threads, unsigned* bd_log) {
+  *threads = 128; *bd_log = 7;
+  while (*threads > 32 && (size_t)n_regs * *threads * 32 > 200 * 1024) { *threads >>= 1; --*bd_log; }
+  return (size_t)n_regs * *threads * 32 <= 200 * 1024;
+}
+
 // what stage_tables leaves at the front of the arena
 struct Staged {
-  const uint4* prog; size_t n_instr; unsigned n_regs;     // lowered program
+  const uint4* prog; size_t n_instr; unsigned n_regs;     // lowered program, staged encoding
   const uint4* consts;
-  const uint4* const* cols;                                // device array of column pointers
   char* after;
 };
 
 int launch_vm(trp_domain* d, const Staged& st, int coset, uint4* d_out, unsigned row0 = 0, unsigned nrows = 0, unsigned halo_before = 0) {
   trp_ctx* ctx = d->ctx;
   QParams p;
-  p.prog = st.prog; p.n_instr = (unsigned)st.n_instr; p.n_regs = st.n_regs; p.consts = st.consts; p.cols = st.cols;
+  p.prog = st.prog; p.n_instr = (unsigned)st.n_instr; p.n_regs = st.n_regs; p.consts = st.consts;
   p.ext_log = d->ext_k;
   const unsigned period = 1u << (d->ext_k - d->k);
   const bool contiguous = coset >= 0 && (coset & TRP_Q_CONTIGUOUS);
@@ -176,11 +178,11 @@ int launch_vm(trp_domain* d, const Staged& st, int coset, uint4* d_out, unsigned
   TRP_TRY(trp_get_powers(ctx, d->field, d->ext_k, d->ext_omega, &tw));
   p.tw_ext = (const uint4*)tw;
   p.out = d_out;
-  unsigned threads = 128, bd_log = 7;
-  while (threads > 32 && (size_t)st.n_regs * threads * 32 > 200 * 1024) { threads >>= 1; --bd_log; }
+  unsigned threads, bd_log;
+  if (!vm_geometry(st.n_regs, &threads, &bd_log))
+    TRP_FAIL(ctx, TRP_E_INVALID, "quotient program needs %u registers (max %u)", st.n_regs, 200 * 1024 / (32 * 32));
   p.bd_log = bd_log;
   size_t smem = (size_t)st.n_regs * threads * 32;
-  if (smem > 200 * 1024) TRP_FAIL(ctx, TRP_E_INVALID, "quotient program needs %u registers (max %u)", st.n_regs, 200 * 1024 / (32 * 32));
   const size_t rows = nrows ? (size_t)nrows : (size_t)1 << p.rows_log;
   unsigned blocks = (unsigned)((rows + threads - 1) / threads);
   auto go = [&](auto tag) -> int {
@@ -283,10 +285,11 @@ struct Locked {
   explicit Locked(trp_ctx* c) : g(c->mu) { cudaSetDevice(c->device); }
 };
 
-// lower the caller's program (cached: a prover evaluates one program on j - 1 cosets, proof after proof) and stage the lowered
-// program / constants / column-pointer table at the front of the arena
+// lower the caller's program (cached: a prover evaluates one program on j - 1 cosets, proof after proof), encode it for this launch
+// (qlower::stage: slot offsets, column addresses) and put program / constants at the front of the arena.  col_ptrs = the columns'
+// device addresses, or NULL if the caller will upload the columns itself right behind the tables, own_col_bytes apart.
 int stage_tables(trp_domain* d, const uint32_t* program, size_t n_instr, unsigned n_regs, const uint64_t* consts, size_t n_consts,
-                 const uint64_t* const* col_ptrs, size_t n_cols, size_t extra, Staged* st) {
+                 const uint64_t* const* col_ptrs, size_t n_cols, size_t own_col_bytes, size_t extra, Staged* st) {
   trp_ctx* ctx = d->ctx;
   if (ctx->q_src.size() != n_instr * 4 || ctx->q_src_regs != n_regs || ctx->q_src_consts != n_consts ||
       memcmp(ctx->q_src.data(), program, n_instr * 16) != 0) {
@@ -296,19 +299,25 @@ int stage_tables(trp_domain* d, const uint32_t* program, size_t n_instr, unsigne
     ctx->q_src.assign(program, program + n_instr * 4);
     ctx->q_src_regs = n_regs; ctx->q_src_consts = n_consts;
   }
-  const size_t low_bytes = ctx->q_low.size() * 4;                     // includes the trailing NOP
-  size_t b_prog = ws_align(low_bytes), b_c = ws_align((n_consts + 1) * 32), b_p = ws_align((n_cols ? n_cols : 1) * 8);   // + zeta
-  TRP_TRY(trp_ws_reserve(ctx, b_prog + b_c + b_p + extra));
+  unsigned threads, bd_log;
+  if (!vm_geometry(ctx->q_low_regs, &threads, &bd_log))
+    TRP_FAIL(ctx, TRP_E_INVALID, "quotient program needs %u registers (max %u)", ctx->q_low_regs, 200 * 1024 / (32 * 32));
+  const size_t low_bytes = ctx->q_low.size() * 4;                     // includes the trailing NOPs
+  size_t b_prog = ws_align(low_bytes), b_c = ws_align((n_consts + 1) * 32);   // + zeta
+  TRP_TRY(trp_ws_reserve(ctx, b_prog + b_c + extra));
   char* w = (char*)ctx->ws;
-  TRP_CUDA(ctx, cudaMemcpyAsync(w, ctx->q_low.data(), low_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<uint64_t> addr(n_cols ? n_cols : 1);
+  for (size_t c = 0; c < n_cols; ++c) addr[c] = col_ptrs ? (uint64_t)(uintptr_t)col_ptrs[c] : (uint64_t)(uintptr_t)(w + b_prog + b_c + c * own_col_bytes);
+  if (!qlower::stage(ctx->q_low, ctx->q_low_regs, bd_log, addr.data(), n_cols, ctx->q_staged))
+    TRP_FAIL(ctx, TRP_E_INVALID, "quotient program: a rotation beyond +-32767 rows or too many registers");
+  TRP_CUDA(ctx, cudaMemcpyAsync(w, ctx->q_staged.data(), low_bytes, cudaMemcpyHostToDevice, ctx->stream));
   if (n_consts) TRP_CUDA(ctx, cudaMemcpyAsync(w + b_prog, consts, n_consts * 32, cudaMemcpyHostToDevice, ctx->stream));
   TRP_CUDA(ctx, cudaMemcpyAsync(w + b_prog + n_consts * 32, d->g_coset, 32, cudaMemcpyHostToDevice, ctx->stream));   // consts[n_consts] = zeta
-  if (n_cols && col_ptrs) TRP_CUDA(ctx, cudaMemcpyAsync(w + b_prog + b_c, col_ptrs, n_cols * 8, cudaMemcpyHostToDevice, ctx->stream));
   // the host arrays may be reused by the caller as soon as we return
   TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   st->prog = (const uint4*)w; st->n_instr = ctx->q_low.size() / 4 - qlower::PAD; st->n_regs = ctx->q_low_regs;
-  st->consts = (const uint4*)(w + b_prog); st->cols = (const uint4* const*)(w + b_prog + b_c);
-  st->after = w + b_prog + b_c + b_p;
+  st->consts = (const uint4*)(w + b_prog);
+  st->after = w + b_prog + b_c;
   return TRP_OK;
 }
 
@@ -327,7 +336,7 @@ int trp_dev_quotient_eval(trp_domain* d, const uint32_t* program, size_t n_instr
   TRP_TRY(validate_program(ctx, program, n_instr, n_regs, n_consts, n_cols));
   for (size_t c = 0; c < n_cols; ++c) if (!d_cols[c]) TRP_FAIL(ctx, TRP_E_INVALID, "column %zu is NULL", c);
   Staged st;
-  TRP_TRY(stage_tables(d, program, n_instr, n_regs, consts, n_consts, d_cols, n_cols, 0, &st));
+  TRP_TRY(stage_tables(d, program, n_instr, n_regs, consts, n_consts, d_cols, n_cols, 0, 0, &st));
   return launch_vm(d, st, coset, (uint4*)d_out);
 }
 
@@ -353,7 +362,7 @@ int trp_dev_quotient_eval_rows(trp_domain* d, const uint32_t* program, size_t n_
     }
   for (size_t c = 0; c < n_cols; ++c) if (!d_cols[c]) TRP_FAIL(ctx, TRP_E_INVALID, "column %zu is NULL", c);
   Staged st;
-  TRP_TRY(stage_tables(d, program, n_instr, n_regs, consts, n_consts, d_cols, n_cols, 0, &st));
+  TRP_TRY(stage_tables(d, program, n_instr, n_regs, consts, n_consts, d_cols, n_cols, 0, 0, &st));
   return launch_vm(d, st, (int)coset, (uint4*)d_out, (unsigned)row0, (unsigned)nrows, halo_before);
 }
 
@@ -370,15 +379,10 @@ int trp_quotient_eval(trp_domain* d, const uint32_t* program, size_t n_instr, un
   for (size_t c = 0; c < n_cols; ++c) if (!cols[c]) TRP_FAIL(ctx, TRP_E_INVALID, "column %zu is NULL", c);
   const size_t EN = (size_t)1 << d->ext_k;
   Staged st;
-  TRP_TRY(stage_tables(d, program, n_instr, n_regs, consts, n_consts, nullptr, n_cols, (n_cols + 1) * EN * 32, &st));
-  char* after = st.after;
-  std::vector<const uint64_t*> dptr(n_cols);
-  for (size_t c = 0; c < n_cols; ++c) {
-    dptr[c] = (const uint64_t*)(after + c * EN * 32);
-    TRP_CUDA(ctx, cudaMemcpyAsync((void*)dptr[c], cols[c], EN * 32, cudaMemcpyHostToDevice, ctx->stream));
-  }
-  if (n_cols) TRP_CUDA(ctx, cudaMemcpyAsync((void*)st.cols, dptr.data(), n_cols * 8, cudaMemcpyHostToDevice, ctx->stream));
-  TRP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // dptr goes out of scope below
+  TRP_TRY(stage_tables(d, program, n_instr, n_regs, consts, n_consts, nullptr, n_cols, EN * 32, (n_cols + 1) * EN * 32, &st));
+  char* after = st.after;                               // the staged program addresses column c at after + c * EN * 32
+  for (size_t c = 0; c < n_cols; ++c)
+    TRP_CUDA(ctx, cudaMemcpyAsync(after + c * EN * 32, cols[c], EN * 32, cudaMemcpyHostToDevice, ctx->stream));
   char* d_out = after + n_cols * EN * 32;
   TRP_TRY(launch_vm(d, st, -1, (uint4*)d_out));
   TRP_CUDA(ctx, cudaMemcpyAsync(out_ext, d_out, EN * 32, cudaMemcpyDeviceToHost, ctx->stream));

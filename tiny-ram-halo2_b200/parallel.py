@@ -151,15 +151,17 @@ def block_range(count: int, world: int, rank: int) -> Tuple[int, int, int]:
     return per, lo, min(lo + per, count)
 
 
-def all_gather_blocks_inplace(buf, per: int, dist):
+def all_gather_blocks_inplace(buf, per: int, dist, async_op: bool = False):
     """buf: (>= per * world, ...) tensor whose block [rank * per, (rank + 1) * per) this rank has filled; after the call every
-    rank holds every block (NCCL / gloo in-place all-gather: the send buffer is the rank's slot of the receive buffer)"""
+    rank holds every block (NCCL / gloo in-place all-gather: the send buffer is the rank's slot of the receive buffer).
+    async_op: return the collective's work handle instead (None if nothing was started); the caller must wait() on it before
+    anybody reads the other ranks' blocks, and must not write to buf until then."""
     world, rank = dist.get_world_size(), dist.get_rank()
     if per == 0 or world == 1:
-        return buf
+        return None if async_op else buf
     out = buf[:per * world]
-    dist.all_gather_into_tensor(out, out[rank * per:(rank + 1) * per])
-    return buf
+    work = dist.all_gather_into_tensor(out, out[rank * per:(rank + 1) * per], async_op=async_op)
+    return work if async_op else buf
 
 
 def row_slice_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
