@@ -213,23 +213,29 @@ class ShardedGpuBackend(ShardedCommits, GpuBackend):
         k = len(vs)
         if self.world == 1 or not self._arena_on or k < self.world:
             return super().lagrange_to_coeff_many(vs)
-        per, lo, hi = parallel.block_range(k, self.world, self.rank)
         first = self._arena_used
-        if first + per * self.world > self._arena.shape[0]:
+        if first + k > self._arena.shape[0]:
             return super().lagrange_to_coeff_many(vs)
+        # rank r transforms columns [r * per, (r + 1) * per) of the batch; the k mod world columns left over are transformed by
+        # EVERY rank (at most world - 1 redundant transforms), so the exchange covers whole blocks only and never writes outside the
+        # batch's own slots -- it stays in flight while the next batch fills the slots right behind it
+        per = k // self.world
+        main = per * self.world
+        lo, hi = self.rank * per, (self.rank + 1) * per
         out = []
         for i, v in enumerate(vs):
             c = self._arena[first + i]
             self._arena_slot[id(c)] = (first + i, c)
-            if lo <= i < hi:
+            if lo <= i < hi or i >= main:
                 c.copy_(v)
             out.append(c)
         self._arena_used += k
-        if hi > lo:
-            self.ctx.check(self.lib.trp_dev_lagrange_to_coeff(self.dom.handle, self._arena[first + lo].data_ptr(), hi - lo))
+        self.ctx.check(self.lib.trp_dev_lagrange_to_coeff(self.dom.handle, self._arena[first + lo].data_ptr(), hi - lo))
+        if k > main:
+            self.ctx.check(self.lib.trp_dev_lagrange_to_coeff(self.dom.handle, self._arena[first + main].data_ptr(), k - main))
         # the other ranks' blocks are not read before the quotient (which waits: _drain), so the exchange runs on NCCL's stream
         # underneath the next phases' kernels -- 15.5 GiB per proof at k = 20, a tenth of the step on 8 GPUs if it is waited for here
-        w = parallel.all_gather_blocks_inplace(self._arena[first:first + per * self.world], per, self.dist, async_op=True)
+        w = parallel.all_gather_blocks_inplace(self._arena[first:first + main], per, self.dist, async_op=True)
         if w is not None:
             self._pending.append(w)
         return out
