@@ -221,6 +221,18 @@ def _row_exchange_worker(rank, world, port, q):
         buf[lo:hi] = want[lo:hi]
         PL.all_gather_blocks_inplace(buf, per, dist)
         ok &= bool(torch.equal(buf[:ncols], want))
+        # 1b. the deferred exchange of lagrange_to_coeff_many: whole blocks only, left-over columns filled by everybody, the
+        #     all_gather in flight while the NEXT batch writes the slot right behind this one
+        per_w, main, lo_w, hi_w = PL.whole_block_range(ncols, world, rank)
+        arena = torch.full((ncols + 2, n, 4), -1, dtype=torch.int64)
+        arena[lo_w:hi_w] = want[lo_w:hi_w]
+        arena[main:ncols] = want[main:ncols]
+        work = PL.all_gather_blocks_inplace(arena[:main], per_w, dist, async_op=True)
+        arena[ncols] = 12345                                  # the next batch's first slot
+        if work is not None:
+            work.wait()
+        ok &= bool(torch.equal(arena[:ncols], want)) and bool((arena[ncols] == 12345).all()) and bool((arena[ncols + 1] == -1).all())
+        ok &= per_w * world == main <= ncols < main + world and (work is not None) == (per_w > 0)
         # 2. the quotient's exchange: every rank ends up with rows [row0 - H, row0 + S + H) (cyclic) of EVERY column
         H = 3
         row0, S = PL.row_slice_bounds(n, world, rank)

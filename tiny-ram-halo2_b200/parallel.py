@@ -151,6 +151,14 @@ def block_range(count: int, world: int, rank: int) -> Tuple[int, int, int]:
     return per, lo, min(lo + per, count)
 
 
+def whole_block_range(k: int, world: int, rank: int) -> Tuple[int, int, int, int]:
+    """(per, main, lo, hi): columns [lo, hi) = [rank * per, (rank + 1) * per) of a batch of k belong to `rank`, per = k // world; the
+    k - main left-over columns (main = per * world) belong to EVERY rank.  An exchange of [0, main) in blocks of per never touches
+    anything outside the batch, so it may stay in flight while the slots behind the batch are being written."""
+    per = k // world
+    return per, per * world, rank * per, (rank + 1) * per
+
+
 def all_gather_blocks_inplace(buf, per: int, dist, async_op: bool = False):
     """buf: (>= per * world, ...) tensor whose block [rank * per, (rank + 1) * per) this rank has filled; after the call every
     rank holds every block (NCCL / gloo in-place all-gather: the send buffer is the rank's slot of the receive buffer).

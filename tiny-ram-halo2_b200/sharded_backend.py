@@ -219,9 +219,7 @@ class ShardedGpuBackend(ShardedCommits, GpuBackend):
         # rank r transforms columns [r * per, (r + 1) * per) of the batch; the k mod world columns left over are transformed by
         # EVERY rank (at most world - 1 redundant transforms), so the exchange covers whole blocks only and never writes outside the
         # batch's own slots -- it stays in flight while the next batch fills the slots right behind it
-        per = k // self.world
-        main = per * self.world
-        lo, hi = self.rank * per, (self.rank + 1) * per
+        per, main, lo, hi = parallel.whole_block_range(k, self.world, self.rank)
         out = []
         for i, v in enumerate(vs):
             c = self._arena[first + i]
