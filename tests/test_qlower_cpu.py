@@ -175,3 +175,40 @@ def test_real_tinyram_program(shim, P):
     # and are forwarded in hardware registers instead), 187 of the 188 multiplications by zeta gone, 387 negations folded into
     # subtractions; 4 in 5 results never reach the shared-memory register file
     assert (st["in"], st["out"], st["fused"], st["negs"]) == (8188, 5883, 1920, 387) and st["nowb"] > 0.75 * st["out"]
+
+
+@pytest.mark.parametrize("seed", range(200))
+def test_lowering_preserves_arbitrary_valid_programs(shim, P, seed):
+    """the C ABI accepts ANY well-formed program, not only what a tree compiler emits: random straight-line programs over 2-6
+    registers with every opcode, registers reused / overwritten unread / read many times, several STOREs (the last one wins per row),
+    COSETX anywhere -- the lowered program must store the same values.  Only programs that read a register after writing it are
+    generated (reading an unwritten virtual register is undefined in the public format too)."""
+    rng = random.Random(7000 + seed)
+    F = pm.Fp
+    L, C, ADD, SUB, MUL, NEG, SQR, DBL, X, ST, MULC, ADDC, SUBC = range(13)
+    n_regs, n_cols, n_consts = rng.randrange(2, 7), rng.randrange(1, 5), rng.randrange(1, 4)
+    written, code = set(), []
+    for _ in range(rng.randrange(5, 120)):
+        r = rng.random()
+        dst = rng.randrange(n_regs)
+        if not written or r < 0.25:
+            op = rng.choice([L, L, L, C, X])
+            code.append((op, dst, rng.randrange(n_cols) if op == L else rng.randrange(n_consts) if op == C else 0,
+                         (rng.choice([0, 0, 1, -1, 2, -3]) & 0xffffffff) if op == L else 0))
+            written.add(dst)
+        elif r < 0.65:
+            a, b = rng.choice(sorted(written)), rng.choice(sorted(written))
+            code.append((rng.choice([ADD, SUB, MUL]), dst, a, b)); written.add(dst)
+        elif r < 0.8:
+            code.append((rng.choice([NEG, SQR, DBL]), dst, rng.choice(sorted(written)), 0)); written.add(dst)
+        elif r < 0.93:
+            code.append((rng.choice([MULC, ADDC, SUBC]), dst, rng.choice(sorted(written)), rng.randrange(n_consts))); written.add(dst)
+        else:
+            code.append((ST, 0, rng.choice(sorted(written)), 0))
+    code.append((ST, 0, rng.choice(sorted(written)), 0))
+    prog = P.Program(np.array(code, dtype=np.uint32), [rng.randrange(F.p) for _ in range(n_consts)], n_regs, n_cols)
+    rows = 8
+    polys = [[rng.randrange(F.p) for _ in range(rows)] for _ in range(n_cols)]
+    xs = [rng.randrange(F.p) for _ in range(rows)]
+    pub, low, st = run_both(shim, prog, polys, xs, rng.randrange(F.p), F.p)
+    assert (pub == low).all()
