@@ -217,10 +217,25 @@ def program_instance(prog: List[T.Instruction], word_bits: int, reg_count: int =
         raise ValueError("Empty programs are invalid / the last instruction must be Answer")
     if len(prog) > table_len:
         raise ValueError("program longer than the program table")
-    padded = list(prog) + [prog[-1]] * (table_len - len(prog))
     counter = iter(range(1 << 30))
     line = ProgramLine(lambda: next(counter), reg_count)
-    cols = [[0] * table_len for _ in range(len(line.to_vec()))]
+    n_cols = len(line.to_vec())
+    pad = table_len - len(prog)                         # the terminal Answer, repeated
+    if arrays:                                          # the same cells written into one uint64 matrix (every value is below 2^64)
+        import numpy as np
+        mat = np.zeros((n_cols, table_len), dtype=np.uint64)
+        rows_of = {}
+        for off, ins in enumerate(prog):
+            if id(ins) not in rows_of:
+                rows_of[id(ins)] = [(c, v) for c, v in line.row_values(ins).items() if v]
+            for c, v in rows_of[id(ins)]:
+                mat[c, off] = v
+        if pad:
+            for c, v in line.row_values(prog[-1]).items():
+                if v:
+                    mat[c, len(prog):] = v
+        return [mat[c] for c in range(n_cols)]
+    cols = [[0] * table_len for _ in range(n_cols)]
     rows_of = {}
     for off, ins in enumerate(prog):
         if id(ins) not in rows_of:
@@ -228,14 +243,10 @@ def program_instance(prog: List[T.Instruction], word_bits: int, reg_count: int =
         for c, v in rows_of[id(ins)].items():
             if v:
                 cols[c][off] = v
-    pad = len(padded) - len(prog)                       # the terminal Answer, repeated
     if pad:
         for c, v in line.row_values(prog[-1]).items():
             if v:
                 cols[c][len(prog):] = [v] * pad
-    if arrays:
-        import numpy as np
-        return [np.array(c, dtype=np.uint64) for c in cols]
     return cols
 
 
