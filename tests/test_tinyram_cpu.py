@@ -402,3 +402,48 @@ def test_parity_vector_of_the_reproducible_rng(mods):
     assert want["shape"] == {"advice": cs.num_advice, "instance": cs.num_instance, "fixed": cs.num_fixed, "lookups": len(cs.lookups),
                              "gates": len(cs.gates), "equality_columns": len(cs.permutation), "degree": cs.degree(),
                              "blinding_factors": cs.blinding_factors()}
+
+
+def test_constraint_degrees(mods):
+    """DESIGN.md section 3 (why every column needs all j - 1 = 5 coset transforms): the degree of every gate polynomial, lookup and
+    of the permutation argument of TinyRamCircuit<32, 8>, and per column the highest degree of any constraint that reads it"""
+    import collections
+    PL, TR, T = mods
+    cs = TR.TinyRamCircuit(PL, 32).cs
+
+    def cols_of(e, acc):
+        if isinstance(e, PL.Query):
+            acc.add((e.kind, e.column))
+        for name in ("a", "b"):
+            v = getattr(e, name, None)
+            if isinstance(v, PL.Expression):
+                cols_of(v, acc)
+
+    colmax = collections.defaultdict(int)
+    gate_deg = collections.Counter()
+    for g in cs.gates:
+        d = g.degree()
+        gate_deg[d] += 1
+        acc = set(); cols_of(g, acc)
+        for c in acc:
+            colmax[c] = max(colmax[c], d)
+    assert cs.degree() == 6 and dict(gate_deg) == {2: 11, 3: 24, 4: 102, 6: 1}
+    lookup_deg = collections.Counter()
+    for inputs, tables in cs.lookups:
+        d = max(4, 2 + max([1] + [e.degree() for e in inputs]) + max([1] + [e.degree() for e in tables]))     # lookup::Argument::required_degree
+        lookup_deg[d] += 1
+        acc = set()
+        for e in inputs + tables:
+            cols_of(e, acc)
+        for c in acc:
+            colmax[c] = max(colmax[c], d)
+    assert dict(lookup_deg) == {5: 1, 6: 30}
+    chunk = cs.degree() - 2
+    for c in cs.permutation:                                  # chunk columns + z(omega X) + the active-rows factor
+        colmax[c] = max(colmax[c], chunk + 2)
+    assert len(cs.permutation) == 188 and chunk + 2 == 6
+    by_deg = collections.Counter(colmax.values())
+    assert cs.num_advice + cs.num_instance + cs.num_fixed == 381 and sum(by_deg.values()) == 378      # 3 columns are read by no constraint
+    assert by_deg[6] == 356 and by_deg[2] + by_deg[3] + by_deg[4] + by_deg[5] == 22
+    low_advice = sum(1 for (kind, _), d in colmax.items() if kind == PL.ADVICE and d < 6)
+    assert low_advice == 21
