@@ -169,6 +169,9 @@ def test_malformed_programs_are_rejected(pkg, P, ctxs):
     assert run([[P.CONST, 0, 3, 0], [P.STORE, 0, 0, 0]]) == -1         # constant out of range
     assert run([[99, 0, 0, 0], [P.STORE, 0, 0, 0]]) == -1              # unknown opcode
     assert run([[P.LOAD, 0, 0, 0]]) == -1                              # never stores
+    assert run([[P.LOAD, 0, 0, 32767], [P.STORE, 0, 0, 0]]) == 0       # the widest rotation the staged encoding carries
+    assert run([[P.LOAD, 0, 0, (-32768) & 0xffffffff], [P.STORE, 0, 0, 0]]) == 0
+    assert run([[P.LOAD, 0, 0, 32768], [P.STORE, 0, 0, 0]]) == -1      # beyond it: rejected before anything is launched
 
 
 @pytest.mark.parametrize("j,k", [(3, 4), (6, 5), (6, 11), (9, 6), (2, 3), (5, 12)])
