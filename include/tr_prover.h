@@ -151,7 +151,10 @@ int trp_dev_extended_to_coeff(trp_domain* d, uint64_t* d_ext, uint64_t* d_out_co
  * coset = j >= 0: rows = the j-th size-n coset (zeta * extended_omega^j * <omega>); columns hold the n values
  *   produced by trp_dev_coeff_to_coset(.., j), step = 1, and results go to d_out[row * 2^(extended_k-k) + j], so
  *   2^(extended_k-k) calls fill h_ext without materialising any extended column.
- * Malformed programs are rejected with TRP_E_INVALID before anything is launched. */
+ * Malformed programs are rejected with TRP_E_INVALID before anything is launched.  The format above is the ABI and may be as naive
+ * as a post-order walk of the Ast emits it: the library rewrites the program before launch (csrc/qlower.h, cached per ctx: leaf loads
+ * folded into their consumer, x + (-y) -> x - y, the value of X computed once, results forwarded through an accumulator) and
+ * stores exactly the values the program above defines. */
 int trp_dev_quotient_eval(trp_domain* d, const uint32_t* program /* host */, size_t n_instr, unsigned n_regs,
                           const uint64_t* consts /* host, n_consts x 4 */, size_t n_consts,
                           const uint64_t* const* d_cols /* host array of n_cols DEVICE pointers */, size_t n_cols,
